@@ -1,0 +1,227 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by executing the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference (haesungpyun/seoul_tourism_recommendation_NGCF) ships no tests or golden vectors for
+this path, so these files are the parity pin: inputs and outputs of the reference's own
+``NGCF`` (model/NGCF.py), ``BPR`` (model/bprloss.py) and ``Matrix`` (model/matrix.py) on seeded
+inputs, executed on CPU with torch's stock sparse path.  Import shims:
+``sys.argv`` trimmed before ``parsers`` is imported, ``np.mat = np.asmatrix`` (removed in NumPy 2).
+No reference source is copied; the modules are imported from where they lie.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REF = "/root/reference/model"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+sys.dont_write_bytecode = True
+sys.argv = [sys.argv[0]]
+sys.path.insert(0, REF)
+np.mat = np.asmatrix
+warnings.filterwarnings("ignore")
+
+import pandas as pd  # noqa: E402
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+from NGCF import NGCF  # noqa: E402  (reference)
+from bprloss import BPR  # noqa: E402  (reference)
+from matrix import Matrix  # noqa: E402  (reference)
+
+FEATURE_CARD = {"sex": 2, "age": 76, "month": 13, "day": 32, "dayofweek": 7}
+
+
+def num_dict(n_user, n_item):
+    d = {"user": n_user, "item": n_item}
+    d.update(FEATURE_CARD)
+    return d
+
+
+def make_frame(n_user, n_item, density, seed, zero_frac=0.25, years=(18, 19)):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for y in years:
+        pairs = np.argwhere(rng.random((n_user, n_item)) < density)
+        v = (3.0 * rng.random(len(pairs))).astype(np.float32)
+        v[rng.random(len(pairs)) < zero_frac] = 0.0
+        for (u, i), r in zip(pairs, v):
+            rows.append((y, int(u), int(i), float(r)))
+    df = pd.DataFrame(rows, columns=["year", "userid", "itemid", "visitor"])
+    df["visitor"] = df["visitor"].astype(np.float32)
+    return df
+
+
+def ref_lap_list(df, n_user, n_item):
+    m = Matrix(df, ["year", "userid", "itemid", "visitor"], "visitor", {"user": n_user, "item": n_item},
+               "/tmp", False, torch.device("cpu"))
+    return m.create_matrix()
+
+
+def make_batch(n_user, n_item, B, seed, year=18, dup=True):
+    rng = np.random.default_rng(seed)
+    b = {
+        "year": np.full(B, year, dtype=np.int64),
+        "u_id": rng.integers(0, n_user, B, dtype=np.int64),
+        "age": rng.integers(0, FEATURE_CARD["age"], B, dtype=np.int64),
+        "sex": rng.integers(0, FEATURE_CARD["sex"], B, dtype=np.int64),
+        "month": rng.integers(0, FEATURE_CARD["month"], B, dtype=np.int64),
+        "day": rng.integers(0, FEATURE_CARD["day"], B, dtype=np.int64),
+        "dow": rng.integers(0, FEATURE_CARD["dayofweek"], B, dtype=np.int64),
+        "pos_item": rng.integers(0, n_item, B, dtype=np.int64),
+        "neg_item": rng.integers(0, n_item, B, dtype=np.int64),
+    }
+    if dup and B >= 4:                       # duplicated users with different features
+        b["u_id"][B // 2] = b["u_id"][0]
+        b["u_id"][B - 1] = b["u_id"][1]
+    return b
+
+
+def build_model(emb, layers, lap_list, nd, B, node_p, mess_p, emb_ratio, seed):
+    torch.manual_seed(seed)
+    m = NGCF(embed_size=emb, layer_size=layers, node_dropout=node_p, mess_dropout=mess_p,
+             emb_ratio=emb_ratio, lap_list=lap_list, num_dict=nd, batch_size=B, device=torch.device("cpu"))
+    if emb % 5 != 0:
+        # oracle-preserving patch: the last feature table absorbs the remainder so
+        # the concat is exactly emb wide; reference forward then runs unmodified
+        m.dow_emb = nn.Embedding(nd["dayofweek"], emb - 4 * (emb // 5))
+        nn.init.kaiming_uniform_(m.dow_emb.weight)
+    return m
+
+
+def run_step(m, batch, wd, B_ctor, node_flag, train_mode, rng_seed=None, neg_empty=False):
+    m.train(train_mode)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    neg = torch.empty(0) if neg_empty else tb["neg_item"]
+    if rng_seed is not None:
+        torch.manual_seed(rng_seed)
+    u, p, n = m(year=tb["year"], u_id=tb["u_id"], age=tb["age"], sex=tb["sex"], month=tb["month"],
+                day=tb["day"], dow=tb["dow"], pos_item=tb["pos_item"], neg_item=neg, node_flag=node_flag)
+    out = {"out/u": u.detach().numpy(), "out/pos": p.detach().numpy(),
+           "out/all_users_emb": m.all_users_emb.detach().numpy(),
+           "out/all_items_emb": m.all_items_emb.detach().numpy()}
+    if not neg_empty:
+        out["out/neg"] = n.detach().numpy()
+        m.zero_grad()
+        loss = BPR(weight_decay=wd, batch_size=B_ctor)(u, p, n)
+        loss.backward()
+        out["out/loss"] = loss.detach().numpy()
+        for k, prm in m.named_parameters():
+            if prm.grad is not None:
+                out["grad/" + k] = prm.grad.detach().numpy().copy()
+            else:
+                out["nograd/" + k] = np.zeros(0, dtype=np.float32)
+    out["out/user_after"] = m.user_embedding.weight.detach().numpy().copy()
+    return out
+
+
+def pack_lap(prefix, lap_list):
+    d = {}
+    for j, L in enumerate(lap_list):
+        d[f"{prefix}/{j}/indices"] = L._indices().numpy().astype(np.int32)
+        d[f"{prefix}/{j}/values"] = L._values().numpy()
+        d[f"{prefix}/{j}/shape"] = np.array(L.shape, dtype=np.int64)
+        d[f"{prefix}/{j}/coalesced"] = np.array(L.is_coalesced())
+    return d
+
+
+def case_matrix_and_step(name, n_user, n_item, density, emb, layers, B, *, graph_seed, model_seed,
+                         batch_seed, node_p=0.3, mess_p=None, emb_ratio=1.0, wd=0.025, node_flag=False,
+                         train_mode=False, rng_seed=None, neg_empty=False, B_ctor=None, year=18):
+    df = make_frame(n_user, n_item, density, graph_seed)
+    lap_list = ref_lap_list(df, n_user, n_item)
+    nd = num_dict(n_user, n_item)
+    mess_p = mess_p if mess_p is not None else [0.1] * len(layers)
+    m = build_model(emb, layers, lap_list, nd, B, node_p, mess_p, emb_ratio, model_seed)
+    batch = make_batch(n_user, n_item, B, batch_seed, year=year)
+    d = {"frame/year": df["year"].to_numpy(np.int64), "frame/userid": df["userid"].to_numpy(np.int64),
+         "frame/itemid": df["itemid"].to_numpy(np.int64), "frame/visitor": df["visitor"].to_numpy(np.float32)}
+    d.update(pack_lap("lap", lap_list))
+    for k, v in m.state_dict().items():
+        d["p/" + k] = v.detach().numpy().copy()
+    for k, v in batch.items():
+        d["batch/" + k] = v
+    cfg = dict(n_user=n_user, n_item=n_item, emb=emb, layers=layers, B=B, B_ctor=B_ctor or B, node_p=node_p,
+               mess_p=mess_p, emb_ratio=emb_ratio, wd=wd, node_flag=node_flag, train_mode=train_mode,
+               rng_seed=-1 if rng_seed is None else rng_seed, neg_empty=neg_empty)
+    d["cfg"] = np.array(repr(cfg))
+    d.update(run_step(m, batch, wd, B_ctor or B, node_flag, train_mode, rng_seed, neg_empty))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB  N={n_user + n_item} nnz={[int(L._nnz()) for L in lap_list]}"
+          + (f" loss={float(d['out/loss']):.8f}" if "out/loss" in d else ""))
+
+
+def case_checkpoint_demo(name="ckpt_demo"):
+    """The checkpoint demo.py:82 loads ([65->64,64,64]) on a Seoul-style graph cut to 300 users x 100 items;
+    the demo-mode call (demo.py:220-235): year=[0], pos_item=[0], no negatives, node_flag=False, then
+    scores = u @ all_items_emb.T and topk over all 100 items."""
+    ck = torch.load(os.path.join(REF, "saved_model_data/NGCF_implicit_15_512_5e-05_1.0_standard_2_23.pth"),
+                    map_location="cpu")
+    n_user, n_item = 300, 100
+    df = make_frame(n_user, n_item, 0.45, seed=7)
+    lap_list = ref_lap_list(df, n_user, n_item)
+    nd = num_dict(n_user, n_item)
+    m = build_model(65, [64, 64, 64], lap_list, nd, 512, 0.3, [0.1, 0.1, 0.1], 1.0, seed=0)
+    sd = {k: v.clone() for k, v in ck.items()}
+    sd["user_embedding.weight"] = sd["user_embedding.weight"][:n_user].clone()
+    m.load_state_dict(sd)
+    m.eval()
+    rng = np.random.default_rng(11)
+    U = 24
+    info = {"u_id": rng.choice(n_user, U, replace=False).astype(np.int64),
+            "age": rng.integers(0, 76, U, dtype=np.int64), "sex": rng.integers(0, 2, U, dtype=np.int64),
+            "month": rng.integers(1, 13, U, dtype=np.int64), "day": rng.integers(1, 32, U, dtype=np.int64),
+            "dow": rng.integers(0, 7, U, dtype=np.int64)}
+    d = {}
+    d.update(pack_lap("lap", lap_list))
+    for k, v in m.state_dict().items():
+        d["p/" + k] = v.detach().numpy().copy()
+    for k, v in info.items():
+        d["batch/" + k] = v
+    t = {k: torch.from_numpy(v) for k, v in info.items()}
+    with torch.no_grad():
+        u, _, _ = m(year=torch.LongTensor([0]), u_id=t["u_id"], age=t["age"], sex=t["sex"], month=t["month"],
+                    day=t["day"], dow=t["dow"], pos_item=torch.LongTensor([0]), neg_item=torch.empty(0),
+                    node_flag=False)
+        scores = torch.mm(u, m.all_items_emb.T)
+        val, rank = torch.topk(scores, 100)
+    d["out/u"] = u.numpy(); d["out/all_items_emb"] = m.all_items_emb.numpy()
+    d["out/all_users_emb"] = m.all_users_emb.numpy()
+    d["out/scores"] = scores.numpy(); d["out/topk_val"] = val.numpy(); d["out/topk_idx"] = rank.numpy()
+    d["cfg"] = np.array(repr(dict(n_user=n_user, n_item=n_item, emb=65, layers=[64, 64, 64], U=U)))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB nnz={[int(L._nnz()) for L in lap_list]}")
+
+
+if __name__ == "__main__":
+    # one thread: torch's CPU index_put_ with duplicate user ids (NGCF.py:114) is only deterministic
+    # (last write wins) single-threaded; everything else on this path is thread-count independent
+    torch.set_num_threads(1)
+    # 1. the reference's own shape family: emb 65, two layers [65,65] (saved_data_layer2), eval mode
+    case_matrix_and_step("seoul_small", 48, 10, 0.6, 65, [65, 65], 16, graph_seed=1, model_seed=0, batch_seed=1,
+                         year=19)
+    # 2. emb 64 / three layers (BASELINE configs 2-3) on a 260-node graph, batch_size ctor != actual rows
+    case_matrix_and_step("emb64_k3", 180, 80, 0.08, 64, [64, 64, 64], 64, graph_seed=2, model_seed=1,
+                         batch_seed=2, B_ctor=128)
+    # 3. emb 128 / four layers (BASELINE config 4)
+    case_matrix_and_step("emb128_k4", 90, 60, 0.12, 128, [128, 128, 128, 128], 32, graph_seed=3, model_seed=2,
+                         batch_seed=3)
+    # 4. node dropout, reference host RNG (NGCF.py:93-100) seeded right before forward; eval mode
+    case_matrix_and_step("node_dropout", 120, 50, 0.15, 65, [65, 65, 65], 32, graph_seed=4, model_seed=3,
+                         batch_seed=4, node_flag=True, rng_seed=123)
+    # 5. message dropout (training mode) + node dropout together, emb_ratio < 1
+    case_matrix_and_step("train_mode", 100, 40, 0.15, 65, [64, 64], 32, graph_seed=5, model_seed=4,
+                         batch_seed=5, node_flag=True, train_mode=True, rng_seed=321, emb_ratio=0.75,
+                         mess_p=[0.1, 0.2])
+    # 6. eval-style call: no negatives (experiment.py:82-91)
+    case_matrix_and_step("no_negatives", 60, 25, 0.3, 65, [65, 65, 65], 25, graph_seed=6, model_seed=5,
+                         batch_seed=6, neg_empty=True)
+    # 7. real checkpoint, demo-mode scoring + full ranking
+    case_checkpoint_demo()
