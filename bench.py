@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the NGCF embedding-propagation hot path (BASELINE.json metric:
+"NGCF epoch time (fwd+bwd+BPR) at Gowalla shape; propagation SpMM HBM GB/s vs peak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape gowalla]
+
+A step is one reference training step (experiment.py:45-57): NGCF.forward over the full graph for one
+1024-triple batch with node_flag=True in training mode, BPR loss, backward to every parameter gradient
+(the optimizer step is not part of the metric).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 1024                     # parsers.py:5
+WEIGHT_DECAY = 0.025             # main.py:75
+NODE_P, MESS_P = 0.3, 0.1        # parsers.py:11-12
+METRIC = "ngcf_epoch_time_fwd_bwd_bpr"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="gowalla")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
+    return ap.parse_args()
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------------
+def make_workload(shape: str, n_batches: int = 8):
+    from seoul_tourism_recommendation_ngcf_b200 import laplacian, synth
+    n_user, n_item, n_edges, emb, K = synth.SHAPES[shape]
+    t0 = time.time()
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, n_edges, alpha=0.8, seed=0)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    batches = [synth.random_batch(n_user, n_item, BATCH, seed=1 + j) for j in range(n_batches)]
+    deg = np.bincount(np.concatenate([u, i + n_user]), minlength=n_user + n_item)
+    info = dict(workload=f"{shape}-shaped synthetic power-law graph (Zipf 0.8), {n_user} users / {n_item} items / "
+                         f"{n_edges} interactions, emb {emb}, {K} layers, batch {BATCH}, node_flag=True, training mode",
+                shape=shape, n_user=n_user, n_item=n_item, interactions=n_edges, nnz=int(L._nnz()), emb=emb, layers=K,
+                batch=BATCH, steps_per_epoch=n_edges // BATCH, max_degree=int(deg.max()),
+                mean_degree=float(deg.mean()))
+    log(f"[bench] workload built in {time.time() - t0:.1f}s: N={n_user + n_item} nnz={L._nnz()} max_deg={deg.max()}")
+    return L, batches, info
+
+
+def make_model(info, L, device, rng="device"):
+    import seoul_tourism_recommendation_ngcf_b200 as pkg
+    from seoul_tourism_recommendation_ngcf_b200 import synth
+    torch.manual_seed(0)
+    K = info["layers"]
+    m = pkg.NGCF(info["emb"], [info["emb"]] * K, NODE_P, [MESS_P] * K, 1.0, [L, L],
+                 synth.num_dict_for(info["n_user"], info["n_item"]), BATCH, device, rng=rng)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.thread = [], None, None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz, mx, reasons, n_in = [], None, set(), 0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            inside = any(a - 0.05 <= ts <= b + 0.15 for a, b in windows)
+            try:
+                util = float(f[6])
+            except ValueError:
+                util = 0.0
+            if not inside and util < 5:
+                continue
+            n_in += 1
+            try:
+                mhz.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": n_in}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+class CallTimer:
+    """Wraps the ctypes library so every C-ABI call is bracketed by CUDA events (breakdown pass only)."""
+
+    def __init__(self, lib):
+        self._lib, self.rec = lib, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("ngcf_") or name in ("ngcf_last_error", "ngcf_launch_count", "ngcf_abi_version",
+                                                    "ngcf_spmm_split_threshold") or name.endswith("_workspace"):
+            return fn
+
+        def wrapped(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            self.rec.append((name, e0, e1))
+            return rc
+        return wrapped
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1 in self.rec:
+            t, c = agg.get(name, (0.0, 0))
+            agg[name] = (t + e0.elapsed_time(e1), c + 1)
+        return agg
+
+
+def run_ours(args):
+    import seoul_tourism_recommendation_ngcf_b200 as pkg
+    from seoul_tourism_recommendation_ngcf_b200 import _lib
+    from seoul_tourism_recommendation_ngcf_b200.plan import spmm
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("multi-GPU row-sharded bench is not wired up yet in this revision")
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    L, batches, info = make_workload(args.shape)
+    model = make_model(info, L, dev).to(dev)
+    model.train()
+    crit = pkg.BPR(WEIGHT_DECAY, BATCH)
+    dbatches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in batches]
+    hbatches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(b):
+        model.zero_grad(set_to_none=True)
+        u, p, n = model(year=b["year"], u_id=b["u_id"], age=b["age"], sex=b["sex"], month=b["month"], day=b["day"],
+                        dow=b["dow"], pos_item=b["pos_item"], neg_item=b["neg_item"], node_flag=True)
+        loss = crit(u, p, n)
+        loss.backward()
+        return loss
+
+    # year stays on the host for index selection (NGCF.py:117) so the step has no device sync
+    for b in dbatches:
+        b["year"] = b["year"].cpu()
+    for j in range(max(args.warmup, 3)):
+        step(dbatches[j % len(dbatches)])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    windows = []
+
+    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps -----------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.ngcf_launch_count()
+    torch.cuda.synchronize()
+    w0 = time.time()
+    for j in range(args.steps):
+        flush.zero_()
+        ev[j][0].record()
+        step(dbatches[j % len(dbatches)])
+        ev[j][1].record()
+    torch.cuda.synchronize()
+    windows.append((w0, time.time()))
+    launches = (lib.ngcf_launch_count() - launches0) / args.steps
+    times = [a.elapsed_time(b) for a, b in ev]
+    ms_per_step = sum(times) / len(times)
+
+    # ---- warm variant (no flush, back-to-back) — reported as context only -------------------------------------
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for j in range(args.steps):
+        step(dbatches[j % len(dbatches)])
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((w0, time.time()))
+    ms_warm = e0.elapsed_time(e1) / args.steps
+
+    # ---- e2e: host (pinned) inputs -> H2D inside the timed region -> step -> loss read back ---------------------
+    h2d = sum(v.numel() * v.element_size() for k, v in hbatches[0].items() if k != "year")
+    for j in range(3):
+        b = hbatches[j % len(hbatches)]
+        float(step({k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}))
+    torch.cuda.synchronize()
+    w0 = time.time()
+    e0.record()
+    for j in range(args.steps):
+        b = hbatches[j % len(hbatches)]
+        db = {k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}
+        loss_val = float(step(db))                          # device -> host read of the step's result
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((w0, time.time()))
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    # ---- roofline of the dominant kernel: the propagation SpMM, timed alone, cold L2 ----------------------------
+    plan = model._last.plan
+    N, nnz, d = plan.N, plan.nnz, info["emb"]
+    X = model._packed_table()
+    Y = torch.empty(N, d, device=dev)
+    reps = 20
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(3):
+        spmm(plan.fwd, plan.fwd.vals, X, d, out=Y, drop_p=NODE_P, seed=1, layer=0)
+    torch.cuda.synchronize()
+    w0 = time.time()
+    for j in range(reps):
+        flush.zero_()
+        kev[j][0].record()
+        spmm(plan.fwd, plan.fwd.vals, X, d, out=Y, drop_p=NODE_P, seed=1, layer=0)
+        kev[j][1].record()
+    torch.cuda.synchronize()
+    windows.append((w0, time.time()))
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    alg_bytes = 8 * nnz + 4 * (N + 1) + 8 * N * d               # SURVEY.md section 8(d), SpMM-only per layer
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.shape)
+    roofline = {"kernel": "spmm_rows_vec_kernel<16> (+ spmm_hub_vec_kernel) = one ngcf_spmm call, layer 0",
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                "kernel_ms": round(k_ms, 5), "peak_source": peak_src, "timing": "CUDA events, cold L2 (flushed)"}
+
+    clocks = sampler.stop(windows)
+
+    # ---- optional per-entry-point breakdown ------------------------------------------------------------------
+    breakdown = None
+    if args.breakdown:
+        timer = CallTimer(lib)
+        _lib._lib = timer
+        for j in range(10):
+            step(dbatches[j % len(dbatches)])
+        agg = timer.table()
+        _lib._lib = lib
+        breakdown = {k: {"ms_per_step": round(t / 10, 4), "calls_per_step": c / 10} for k, (t, c) in sorted(agg.items())}
+        for k, v in breakdown.items():
+            log(f"[breakdown] {k:28s} {v['ms_per_step']:8.4f} ms/step  x{v['calls_per_step']:.0f}")
+
+    # ---- CPU baseline beside it ------------------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = time_oracle(L, batches, info, max_steps=3, warmup=1, budget_s=40.0)
+
+    spe = info["steps_per_epoch"]
+    out = {
+        "metric": METRIC, "value": round(ms_per_step * spe / 1e3, 6), "unit": "s/epoch", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": nnz, "N": N,
+                   "rng": "device (Philox, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "api": "drop-in NGCF.forward + BPR + loss.backward(), eager"},
+        "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_val},
+        "warm_ms_per_step": round(ms_warm, 5),
+        "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    if breakdown:
+        out["breakdown"] = breakdown
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU torch.sparse path
+# ------------------------------------------------------------------------------------------------------------
+def time_oracle(L, batches, info, max_steps, warmup, budget_s):
+    from oracle import ngcf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = make_model(info, L, torch.device("cpu"))
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    K, N = info["layers"], info["n_user"] + info["n_item"]
+    dims = [info["emb"]] * K
+
+    def one(j):
+        b = {k: torch.from_numpy(v) for k, v in batches[j % len(batches)].items()}
+        keep, mult = O.reference_dropout_draws(L._nnz(), N, dims, NODE_P, [MESS_P] * K, True, True)
+        O.train_step(params, L, b, emb_ratio=1.0, weight_decay=WEIGHT_DECAY, batch_size_ctor=BATCH,
+                     edge_keep=keep, mess_mult=mult)
+
+    t_start = time.time()
+    for j in range(warmup):
+        one(j)
+    ts = []
+    for j in range(max_steps):
+        t0 = time.time()
+        one(warmup + j)
+        ts.append(time.time() - t0)
+        if time.time() - t_start > budget_s and len(ts) >= 1:
+            break
+    s = statistics.mean(ts)
+    return {"value": round(s * info["steps_per_epoch"], 3), "unit": "s/epoch", "ms_per_step": round(s * 1e3, 2),
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(ts)} full training steps (of {info['steps_per_epoch']} per epoch) of the same workload, "
+                      f"{warmup} warm-up; oracle/ngcf_oracle.py = the reference's torch.sparse CPU path incl. its host "
+                      f"float64 node-dropout mask"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    L, batches, info = make_workload(args.shape)
+    res = time_oracle(L, batches, info, max_steps=args.steps, warmup=min(args.warmup, 2), budget_s=200.0)
+    spe = info["steps_per_epoch"]
+    out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "s/epoch", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": False,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": info["workload"], "steps_per_epoch": spe, "device": "cpu"},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,168 @@
+/* ngcf_b200.h — C ABI of the B200-native NGCF embedding-propagation hot path.
+ *
+ * The reference (haesungpyun/seoul_tourism_recommendation_NGCF) is pure Python/PyTorch and has no
+ * FFI of its own; the boundary it offers is the Python class surface of model/NGCF.py and
+ * model/bprloss.py.  This library is what the drop-in NGCF / BPR modules
+ * (seoul_tourism_recommendation_ngcf_b200/NGCF.py, bprloss.py) bind through ctypes; every entry
+ * point names the reference lines whose torch calls it replaces (paths relative to
+ * /root/reference/model/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in
+ *     _host; the caller (torch) allocates and owns every buffer, the library keeps no pointer past
+ *     return and allocates nothing;
+ *   - all dense matrices are row-major fp32; `ld*` is the row stride in elements;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises, every
+ *     call is CUDA-graph capturable unless stated;
+ *   - return 0 on success, negative ngcf_status otherwise; ngcf_last_error() gives a thread-local
+ *     message.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef NGCF_B200_H
+#define NGCF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGCF_B200_ABI_VERSION 1
+#define NGCF_MAX_LAYERS 8
+#define NGCF_MAX_WIDTH 128          /* widest embedding / layer size the kernels accept */
+
+typedef enum {
+    NGCF_OK = 0,
+    NGCF_ERR_INVALID = -1,          /* bad argument (null pointer, width > NGCF_MAX_WIDTH, ...) */
+    NGCF_ERR_CUDA = -2,             /* a CUDA runtime call or launch failed */
+    NGCF_ERR_WORKSPACE = -3         /* caller-provided workspace too small */
+} ngcf_status;
+
+int ngcf_abi_version(void);
+const char* ngcf_last_error(void);
+uint64_t ngcf_launch_count(void);   /* kernels this library has launched in this process (bench accounting) */
+
+/* ---- Laplacian format: lap_list[i] (matrix.py:79-83, consumed NGCF.py:117-118,130) ------------
+ * One-off conversion of the reference's uncoalesced int64 COO into int32 CSR.  Entries are sorted by
+ * (row, col) — or by (col, row) when `transpose` != 0, giving the CSR of L^T that the backward's
+ * MmBackward0 needs — and duplicates are kept (their products sum, like coalesce()).  perm[t] is the
+ * COO position of CSR entry t, so one edge mask in COO order serves both directions.
+ * Not graph-capturable (uses a sort).  nnz < 2^31. */
+int ngcf_coo_to_csr_workspace(int64_t nnz, int64_t n_rows, size_t* bytes_host);
+int ngcf_coo_to_csr(const int64_t* coo_row, const int64_t* coo_col, int64_t nnz,
+                    int64_t n_rows, int64_t n_cols, int transpose,
+                    int32_t* rowptr /*[n+1], n = transpose ? n_cols : n_rows*/,
+                    int32_t* colidx /*[nnz]*/, int32_t* perm /*[nnz]*/,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* vals_out[t] = coo_val[perm[t]] * keep_mask[perm[t]]: CSR-ordered edge values, optionally with an explicit
+ * node-dropout mask folded in.  Replaces NGCF.sparse_dropout (NGCF.py:93-100) for masks given in COO order
+ * (the reference's host RNG stream, or a mask injected by a test): dropped entries are zeroed over the fixed
+ * structure instead of deleted (identical sums).  keep_mask: optional uint8[nnz]; perm may be NULL (identity).
+ * (Device-RNG node dropout needs no pass at all: see ngcf_spmm.) */
+int ngcf_edge_values(const float* coo_val, const int32_t* perm, const uint8_t* keep_mask,
+                     float* vals_out, int64_t nnz, void* stream);
+
+/* ---- feature mix: NGCF.py:103-115 ----------------------------------------------------------------
+ * user_w[u_id[b], :] = user_w[u_id[b], :]*(1-ratio) + concat(age,sex,month,day,dow rows)*ratio,
+ * in place.  Duplicate u_id: the LAST occurrence in the batch wins (the reference's deterministic
+ * single-thread CPU behaviour).  tables/idx are host arrays of 5 device pointers in concat order
+ * age, sex, month, day, dow (NGCF.py:110); widths[5] must sum to d.  winner is int32[n_user] scratch
+ * that must be all -1 on entry and is restored to all -1 before return. */
+int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
+                     const float* const* tables_host, const int* widths_host,
+                     const int64_t* const* idx_host, const int64_t* u_id, int64_t batch,
+                     float ratio, int32_t* winner, void* stream);
+
+/* ---- SpMM: torch.mm(L, E), NGCF.py:130, and its backward L^T·gS (autograd MmBackward0) ----------
+ * Y[i,:] = sum_t vals[t] * X[colidx[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
+ * Rows longer than the plan's split threshold are pre-reduced chunk-wise into hub_partial so that no
+ * warp walks a hub row alone:  hub_rows[n_hub] sorted row ids, hub_chunk_ptr[n_hub+1], and chunks
+ * (hub_chunk_begin/end[n_chunks], CSR positions); hub_partial is scratch [n_chunks, d]. n_hub may be 0.
+ *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
+ *               (the IndexBackward scatter of NGCF.py:151-155 folded into the last backward SpMM).
+ *   drop_p > 0: device-RNG node dropout (NGCF.py:93-100,124-126) evaluated in-kernel: entry (r,c) of L survives
+ *               layer `layer` iff its Philox draws keyed on (seed + *seed_dev, r, c) for layers 0..layer are all
+ *               >= drop_p (cumulative over layers, unscaled — the reference's semantics).  `transposed` != 0 says
+ *               this CSR holds L^T, so both directions drop the same entries of L.  hub_chunk_row[n_chunks] gives
+ *               each chunk's row.  seed_dev: optional device uint64 added to seed (graph-replay safe). */
+int ngcf_spmm_split_threshold(void);   /* rows with more entries than this must be listed in hub_rows */
+int ngcf_spmm(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+              int64_t n_rows, const float* X, int64_t ldx, int d,
+              const float* addend, int64_t ld_add,
+              const int32_t* slot, const float* gsum, int64_t ld_gsum,
+              const int32_t* hub_rows, const int32_t* hub_chunk_ptr, int32_t n_hub,
+              const int32_t* hub_chunk_begin, const int32_t* hub_chunk_end, const int32_t* hub_chunk_row,
+              int32_t n_chunks, float* hub_partial,
+              float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed,
+              float* Y, int64_t ldy, void* stream);
+
+/* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
+ * pack:  wcat[k, o] = W1[o,k] (k < d_in), W2[o,k-d_in] (k >= d_in);  bias_eff = 2*b1 + b2
+ *        (the reference applies w1_list[i] twice, NGCF.py:131,133, so its bias counts twice). */
+int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                      int d_in, int d_out, float* wcat /*[2*d_in, d_out]*/, float* bias_eff /*[d_out]*/,
+                      void* stream);
+/* E_out = Dropout(LeakyReLU_slope((S+E)·W1^T + (S*E)·W2^T + bias_eff)).
+ *   mess_mult : optional [n_rows, d_out] multipliers standing in for nn.Dropout (mask injection);
+ *   mess_p>0  : device-RNG inverted dropout keyed on (seed + *seed_dev, layer, element); ignored with mess_mult. */
+int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
+                   const float* wcat, const float* bias_eff, float slope,
+                   const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
+                   float* E_out, void* stream);
+
+/* ---- output rows: NGCF.py:144-156 -------------------------------------------------------------------
+ * out[b,:] = [ E0[r,:] | E1[r,:]/max(||E1[r,:]||,1e-12) | ... | EK[r,:]/max(...) ],  r = rows[b]+row_offset
+ * (rows == NULL: r = b + row_offset, i.e. materialise all_E).  layers_host: K+1 device pointers
+ * (E0, E'_1..E'_K, each contiguous [N, dims[k]]); dims_host: K+1 widths. */
+int ngcf_gather_concat(const float* const* layers_host, const int* dims_host, int n_layers_plus1,
+                       const int64_t* rows, int64_t row_offset, int64_t n_out,
+                       float* out, int64_t ld_out, void* stream);
+
+/* ---- BPR loss: bprloss.py:15-22, forward and row gradients in one kernel ------------------------------
+ * loss = (-sum_b logsigmoid(|u_b.p_b| - |u_b.n_b|)
+ *         + wd (reg_w_u sum|u_b|^2 + reg_w_p sum|p_b|^2 + reg_w_n sum|n_b|^2)) / batch_size_ctor  -> *loss (device)
+ * reg_w_* are 1 except for an operand the caller broadcast from one row to `batch` rows
+ * (experiment.py:96-100 passes pos_i_embeds[:1]), where it is 1/batch so the row is regularised once.
+ * gu/gp/gn = dloss/du, /dp, /dn (each [batch, D]); pass all three NULL to skip the gradients. */
+int ngcf_bpr_fwd_bwd(const float* u, const float* p, const float* n, int64_t batch, int D,
+                     float weight_decay, float batch_size_ctor, float reg_w_u, float reg_w_p, float reg_w_n,
+                     float* loss, float* gu, float* gp, float* gn, void* stream);
+
+/* ---- backward of the row gather (IndexBackward, NGCF.py:151-155) as a slot map ----------------------
+ * For the n_sets (<= 4) index sets (row ids rows[j][b] + offsets[j]) and their row gradients g[j]
+ * ([batch_j, D]): pick one slot per distinct row
+ * (slot[row] = index into gsum), and gsum[slot] = sum of that row's gradients.  slot must be all -1 on
+ * entry ([N] int32); gsum is [sum batch_j, D] and is zeroed here.  ngcf_rowgrad_reset restores slot. */
+int ngcf_rowgrad_scatter(const int64_t* const* rows_host, const int64_t* offsets_host,
+                         const float* const* g_host, const int64_t* batch_host, int n_sets, int D,
+                         int32_t* slot, float* gsum, void* stream);
+int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_host,
+                       const int64_t* batch_host, int n_sets, int32_t* slot, void* stream);
+
+/* ---- row-local backward of one layer (AddmmBackward/LeakyReluBackward/normalize backward) -----------
+ * With gH = gsum[slot[i], col_off .. col_off+d_out) (0 when slot[i] < 0), n = max(||E_out[i]||,1e-12),
+ * H = E_out[i]/n:
+ *   gE' = gE_next[i] (0 if NULL) + (gH - H (H.gH)) / n
+ *   gM  = gE' * mess_mult * (E_out > 0 ? 1 : slope)         (sign(E_out) = sign(M); dropped -> 0)
+ *   gS[i]  = gM·W1 + (gM·W2) * E[i]      gEl[i] = gM·W1 + (gM·W2) * S[i]
+ *   gW1 += gM^T (S+E)   gb1 += 2 colsum(gM)   gW2 += gM^T (S*E)   gb2 += colsum(gM)   (atomic accumulate
+ *   into caller-zeroed buffers).  W1/W2 are the nn.Linear weights, [d_out, d_in] row-major. */
+int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
+                   const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
+                   const float* W1, const float* W2, float slope,
+                   const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
+                   float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, void* stream);
+
+/* ---- scoring: demo.py:234-235, experiment.py:93,104,109 ----------------------------------------------
+ * scores = U·I^T without materialising them; per user row the k largest (descending; ties by lower item
+ * id).  k <= 128.  workspace: ngcf_score_topk_workspace bytes. */
+int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int k, size_t* bytes_host);
+int ngcf_score_topk(const float* U, int64_t n_users, const float* I, int64_t n_items, int D, int k,
+                    float* out_val /*[n_users,k]*/, int64_t* out_idx /*[n_users,k]*/,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGCF_B200_H */

@@ -1,0 +1,333 @@
+"""Drop-in ``NGCF`` module (reference: model/NGCF.py:7-156) over the B200 C-ABI kernels.
+
+Same constructor, ``forward`` signature, attributes (``all_users_emb`` / ``all_items_emb``), parameter
+names/order/shapes (``state_dict`` compatible both ways with the reference's ``.pth`` files) and the same
+initialisation stream, so ``main.py`` / ``demo.py`` run unchanged with this module on ``sys.path`` first.
+Everything numerical runs in libngcf_b200.so; there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .plan import LaplacianPlan, spmm
+
+LEAKY_SLOPE = 0.2   # NGCF.py:140
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Ctx:
+    """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "masked", "drop_p",
+                 "rows", "offsets", "W1", "W2")
+
+
+class _Propagate(torch.autograd.Function):
+    """K-layer propagation + output-row gather (NGCF.py:120-156) and its hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, mod, st: _Ctx, n_sets, user_w, item_w, *wb):
+        lib = _lib.load()
+        K = mod.n_layer
+        W1, b1, W2, b2 = wb[0:K], wb[K:2 * K], wb[2 * K:3 * K], wb[3 * K:4 * K]
+        dev = user_w.device
+        N = mod.n_user + mod.n_item
+        E = mod._packed_table()                                        # [N, d0] = cat(user, item), NGCF.py:120
+        st.E, st.S, st.W1, st.W2 = [E], [], list(W1), list(W2)
+        side = st.plan.fwd
+        for k in range(K):
+            d_in, d_out = st.dims[k], st.dims[k + 1]
+            vals = st.vals_f[k] if st.vals_f is not None else side.vals
+            S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, layer=k)   # NGCF.py:124-130
+            wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
+            bias = torch.empty(d_out, dtype=torch.float32, device=dev)
+            _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
+                                             d_in, d_out, wcat.data_ptr(), bias.data_ptr(), _stream()), "pack_weights")
+            En = torch.empty(N, d_out, dtype=torch.float32, device=dev)
+            mm = st.mess_mult[k] if st.mess_mult is not None else None
+            _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), st.E[k].data_ptr(), N, d_in, d_out, wcat.data_ptr(),
+                                          bias.data_ptr(), LEAKY_SLOPE, _lib.ptr(mm), float(st.mess_p[k]),
+                                          st.seed, None, k, En.data_ptr(), _stream()), "dense_fwd")   # NGCF.py:131-142
+            st.S.append(S)
+            st.E.append(En)
+        D = sum(st.dims)
+        outs = []
+        layers, dims = _lib.ptr_array(st.E), _lib.int_array(st.dims)
+        for j in range(n_sets):
+            rows = st.rows[j]
+            o = torch.empty(rows.numel(), D, dtype=torch.float32, device=dev)
+            _lib.check(lib.ngcf_gather_concat(layers, dims, K + 1, rows.data_ptr(), st.offsets[j], rows.numel(),
+                                              o.data_ptr(), D, _stream()), "gather_concat")      # NGCF.py:144-155
+            outs.append(o)
+        ctx.st, ctx.mod, ctx.n_sets = st, mod, n_sets
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        st, mod, n_sets = ctx.st, ctx.mod, ctx.n_sets
+        K, dims = mod.n_layer, st.dims
+        dev = st.E[0].device
+        N = mod.n_user + mod.n_item
+        D = sum(dims)
+        g = [(go.contiguous() if go is not None else torch.zeros(st.rows[j].numel(), D, device=dev))
+             for j, go in enumerate(gouts)]
+        batch = [r.numel() for r in st.rows[:n_sets]]
+        rows_h, offs_h = _lib.ptr_array(st.rows[:n_sets]), _lib.i64_array(st.offsets[:n_sets])
+        g_h, batch_h = _lib.ptr_array(g), _lib.i64_array(batch)
+        slot = mod._slot_map(N, dev)
+        gsum = torch.empty(sum(batch), D, dtype=torch.float32, device=dev)
+        _lib.check(lib.ngcf_rowgrad_scatter(rows_h, offs_h, g_h, batch_h, n_sets, D, slot.data_ptr(),
+                                            gsum.data_ptr(), _stream()), "rowgrad_scatter")
+        sizes = [dims[k + 1] * dims[k] for k in range(K)]
+        flat = torch.zeros(2 * sum(sizes) + 2 * sum(dims[1:]), dtype=torch.float32, device=dev)
+        gW1, gW2, gb1, gb2, o = [], [], [], [], 0
+        for k in range(K):
+            gW1.append(flat[o:o + sizes[k]].view(dims[k + 1], dims[k])); o += sizes[k]
+            gW2.append(flat[o:o + sizes[k]].view(dims[k + 1], dims[k])); o += sizes[k]
+            gb1.append(flat[o:o + dims[k + 1]]); o += dims[k + 1]
+            gb2.append(flat[o:o + dims[k + 1]]); o += dims[k + 1]
+        # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
+        # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
+        side = st.plan.side(True, st.vals_b is not None)
+        gE_next = None
+        col_off = D
+        for k in range(K - 1, -1, -1):
+            d_in, d_out = dims[k], dims[k + 1]
+            col_off -= d_out
+            gS = torch.empty(N, d_in, dtype=torch.float32, device=dev)
+            gEl = torch.empty(N, d_in, dtype=torch.float32, device=dev)
+            mm = st.mess_mult[k] if st.mess_mult is not None else None
+            _lib.check(lib.ngcf_dense_bwd(_lib.ptr(gE_next), slot.data_ptr(), gsum.data_ptr(), D, col_off,
+                                          st.E[k + 1].data_ptr(), st.S[k].data_ptr(), st.E[k].data_ptr(), N, d_in, d_out,
+                                          st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE, _lib.ptr(mm),
+                                          float(st.mess_p[k]), st.seed, None, k, gS.data_ptr(), gEl.data_ptr(),
+                                          gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
+                                          _stream()), "dense_bwd")
+            vals = st.vals_b[k] if st.vals_b is not None else side.vals
+            last = (k == 0)
+            gE_next = spmm(side, vals, gS, d_in, addend=gEl, slot=slot if last else None, gsum=gsum if last else None,
+                           drop_p=st.drop_p, seed=st.seed, layer=k,
+                           transposed=True)                           # gE_k = gEl + L^T gS (+ layer-0 row grads)
+        _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
+                   "rowgrad_reset")
+        gU, gI = gE_next[:mod.n_user], gE_next[mod.n_user:]
+        return (None, None, None, gU, gI, *gW1, *gb1, *gW2, *gb2)
+
+
+class NGCF(nn.Module):
+    """Same surface as the reference ``NGCF`` (NGCF.py:8-17).  Extra keyword-only knobs:
+
+    rng : "device" (default) draws node- and message-dropout decisions in-kernel from a Philox stream keyed
+          on a per-forward seed taken from torch's CPU generator;  "reference" reproduces the reference's host
+          float64 ``nn.Dropout`` node mask bit for bit (NGCF.py:94) at its host cost.
+    """
+
+    def __init__(self, embed_size: int, layer_size: list, node_dropout: float, mess_dropout: list,
+                 emb_ratio: float, lap_list: list, num_dict: dict, batch_size: int, device, *, rng: str = "device"):
+        super().__init__()
+        if rng not in ("device", "reference"):
+            raise ValueError("rng must be 'device' or 'reference'")
+        self.n_user = int(num_dict['user'])
+        self.n_item = int(num_dict['item'])
+        self.emb_size = int(embed_size)
+        self.weight_size = list(layer_size)
+        self.n_layer = len(self.weight_size)
+        self.batch_size = batch_size
+        self.device = device
+        self.node_dropout = node_dropout
+        self.mess_dropout = mess_dropout
+        self.emb_ratio = emb_ratio
+        self.rng = rng
+        if max([self.emb_size] + self.weight_size) > 128 or self.n_layer > 8:
+            raise ValueError("embedding/layer widths up to 128 and up to 8 layers are supported")
+
+        # Feature tables in the reference's registration order (NGCF.py:39-45).  The reference needs
+        # embed_size % 5 == 0 (its concat is 5*(emb//5) wide, NGCF.py:110-114); here the last table of the
+        # concat order (dow) absorbs the remainder, which is the same thing whenever emb % 5 == 0.
+        w = self.emb_size // 5
+        self.feat_widths = [w, w, w, w, self.emb_size - 4 * w]          # age, sex, month, day, dow
+        self.month_emb = nn.Embedding(int(num_dict['month']), w)
+        self.day_emb = nn.Embedding(int(num_dict['day']), w)
+        self.sex_emb = nn.Embedding(int(num_dict['sex']), w)
+        self.age_emb = nn.Embedding(int(num_dict['age']), w)
+        self.dow_emb = nn.Embedding(int(num_dict['dayofweek']), self.feat_widths[4])
+        self.item_embedding = nn.Embedding(self.n_item, self.emb_size)
+        self.user_embedding = nn.Embedding(self.n_user, self.emb_size)
+        self.lap_list = lap_list
+        self.set_layers()
+        self._plans = {}
+        self._table = None
+        self._slot = None
+        self._winner = None
+        self._last = None
+        self._all_E = None
+        self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
+
+    def set_layers(self):
+        """Same initialisation calls in the same order as NGCF.py:56-91 (same RNG stream, same values)."""
+        init = nn.init.kaiming_uniform_
+        init(self.user_embedding.weight)
+        init(self.item_embedding.weight)
+        init(self.age_emb.weight)
+        init(self.sex_emb.weight)
+        init(self.month_emb.weight)
+        init(self.dow_emb.weight)
+        init(self.day_emb.weight)
+        sizes = [self.emb_size] + self.weight_size
+        w1, w2, nd, md = [], [], [], []
+        for k in range(self.n_layer):
+            w1.append(nn.Linear(sizes[k], sizes[k + 1], bias=True))
+            w2.append(nn.Linear(sizes[k], sizes[k + 1], bias=True))
+            if self.node_dropout is not None:
+                nd.append(nn.Dropout(p=self.node_dropout))
+            if self.mess_dropout is not None:
+                md.append(nn.Dropout(p=self.mess_dropout[k]))
+        self.w1_list = nn.Sequential(*w1)
+        self.w2_list = nn.Sequential(*w2)
+        self.node_dropout_list = nn.Sequential(*nd)
+        self.mess_dropout_list = nn.Sequential(*md)
+
+    # ---- internal buffers ---------------------------------------------------------------------------
+    def _packed_table(self) -> torch.Tensor:
+        """[N, d] view over user_embedding.weight and item_embedding.weight laid out back to back, so that
+        ``cat(user, item)`` (NGCF.py:120) costs nothing.  Re-packs (and rebinds both ``.data``) whenever the
+        two parameters are not adjacent, e.g. after ``model.to(device)`` or ``load_state_dict``."""
+        u, i = self.user_embedding.weight, self.item_embedding.weight
+        d = self.emb_size
+        adjacent = (u.is_contiguous() and i.is_contiguous() and u.dtype == torch.float32 and
+                    u.data_ptr() + self.n_user * d * 4 == i.data_ptr() and
+                    getattr(self, "_table", None) is not None and self._table.data_ptr() == u.data_ptr())
+        if not adjacent:
+            table = torch.empty(self.n_user + self.n_item, d, dtype=torch.float32, device=u.device)
+            table[:self.n_user].copy_(u.data)
+            table[self.n_user:].copy_(i.data)
+            u.data = table[:self.n_user]
+            i.data = table[self.n_user:]
+            self._table = table
+        return self._table
+
+    def _slot_map(self, N, dev):
+        if self._slot is None or self._slot.device != dev or self._slot.numel() != N:
+            self._slot = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        return self._slot
+
+    def _plan(self, year_idx: int, dev) -> LaplacianPlan:
+        L = self.lap_list[year_idx]
+        p = self._plans.get(year_idx)
+        if p is None or p.src is not L or p.coo_val.device != dev:
+            p = LaplacianPlan(L, dev)
+            self._plans[year_idx] = p
+        return p
+
+    def _reference_node_masks(self, nnz: int, dev):
+        """Bit-exact reproduction of NGCF.sparse_dropout's host RNG stream (NGCF.py:94): float64 ones through a
+        fresh (always-training) nn.Dropout on the CPU generator, over the surviving entries only."""
+        alive = np.arange(nnz)
+        out = []
+        for _ in range(self.n_layer):
+            m = nn.Dropout(self.node_dropout)(torch.tensor(np.ones(alive.size))).type(torch.bool).numpy()
+            alive = alive[m]
+            full = np.zeros(nnz, dtype=np.uint8)
+            full[alive] = 1
+            out.append(torch.from_numpy(full).to(dev))
+        return out
+
+    # ---- forward ---------------------------------------------------------------------------------------
+    def forward(self, year, u_id, age, sex, month, day, dow, pos_item, neg_item, node_flag):
+        lib = _lib.load()
+        dev = self.user_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("NGCF (B200) runs on a CUDA device only; there is no CPU fallback. "
+                               "Move the module with .to('cuda').")
+        K, N = self.n_layer, self.n_user + self.n_item
+
+        def ix(t):
+            return t.to(device=dev, dtype=torch.int64).contiguous()
+
+        u_id, pos_item = ix(u_id), ix(pos_item)
+        feats_idx = [ix(age), ix(sex), ix(month), ix(day), ix(dow)]          # concat order, NGCF.py:110
+        has_neg = len(neg_item) > 0                                          # NGCF.py:154
+        neg_item = ix(neg_item) if has_neg else None
+        year_idx = int(year.min()) % 18                                      # == year.unique()[0] % 18, NGCF.py:117
+
+        table = self._packed_table()
+        if self._winner is None or self._winner.device != dev or self._winner.numel() != self.n_user:
+            self._winner = torch.full((self.n_user,), -1, dtype=torch.int32, device=dev)
+        tabs = [self.age_emb.weight, self.sex_emb.weight, self.month_emb.weight, self.day_emb.weight, self.dow_emb.weight]
+        _lib.check(lib.ngcf_feature_mix(table.data_ptr(), self.n_user, self.emb_size, _lib.ptr_array(tabs),
+                                        _lib.int_array(self.feat_widths), _lib.ptr_array(feats_idx), u_id.data_ptr(),
+                                        u_id.numel(), float(self.emb_ratio), self._winner.data_ptr(), _stream()),
+                   "feature_mix")                                            # NGCF.py:103-115
+
+        st = _Ctx()
+        st.plan = plan = self._plan(year_idx, dev)
+        if plan.N != N:
+            raise ValueError(f"Laplacian is {plan.N}x{plan.N} but n_user+n_item = {N}")
+        st.dims = [self.emb_size] + self.weight_size
+        inj = self._inject or {}
+        # node dropout: active whenever node_flag is set, in eval mode too (NGCF.py:124-126)
+        st.masked = bool(node_flag) and (self.node_dropout is not None) and \
+            (self.node_dropout > 0 or "edge_keep" in inj)
+        st.vals_f = st.vals_b = None
+        st.drop_p = 0.0
+        masks = None
+        if st.masked:
+            if "edge_keep" in inj:
+                masks = [m.to(device=dev, dtype=torch.uint8).contiguous() for m in inj["edge_keep"]]
+            elif self.rng == "reference":
+                masks = self._reference_node_masks(plan.nnz, dev)
+            else:
+                st.drop_p = float(self.node_dropout)               # decided in-kernel, no mask pass
+        # message dropout: nn.Dropout semantics, only in training mode (NGCF.py:142)
+        st.mess_mult = None
+        st.mess_p = [0.0] * K
+        if "mess_mult" in inj:
+            st.mess_mult = [m.to(device=dev, dtype=torch.float32).contiguous() for m in inj["mess_mult"]]
+        elif self.training and self.mess_dropout is not None:
+            st.mess_p = [float(p) for p in self.mess_dropout[:K]]
+        # per-forward Philox key from torch's CPU generator (reproducible under torch.manual_seed); drawn only when
+        # a device-RNG stream is live and only after the reference-mode mask draws, whose RNG stream it must not shift
+        need_seed = st.drop_p > 0 or any(p > 0 for p in st.mess_p)
+        st.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0
+        if masks is not None:
+            st.vals_f = [plan.masked_values(plan.fwd, masks[k]) for k in range(K)]
+            st.vals_b = [plan.masked_values(plan.bwd, masks[k]) for k in range(K)]
+        st.rows = [u_id, pos_item] + ([neg_item] if has_neg else [])
+        st.offsets = [0, self.n_user] + ([self.n_user] if has_neg else [])
+
+        wb = [l.weight for l in self.w1_list] + [l.bias for l in self.w1_list] + \
+             [l.weight for l in self.w2_list] + [l.bias for l in self.w2_list]
+        outs = _Propagate.apply(self, st, len(st.rows), self.user_embedding.weight, self.item_embedding.weight, *wb)
+        self._last, self._all_E = st, None
+        u_embeddings, pos_i_embeddings = outs[0], outs[1]
+        neg_i_embeddings = outs[2] if has_neg else torch.empty(0)           # NGCF.py:153
+        return u_embeddings, pos_i_embeddings, neg_i_embeddings
+
+    # ---- attributes the reference sets in forward (NGCF.py:147-149), materialised on first read ---------
+    def _materialize(self):
+        if self._last is None:
+            raise AttributeError("all_users_emb / all_items_emb exist after the first forward (NGCF.py:148-149)")
+        if self._all_E is None:
+            st, lib = self._last, _lib.load()
+            N, D = self.n_user + self.n_item, sum(st.dims)
+            out = torch.empty(N, D, dtype=torch.float32, device=st.E[0].device)
+            _lib.check(lib.ngcf_gather_concat(_lib.ptr_array(st.E), _lib.int_array(st.dims), self.n_layer + 1, None, 0,
+                                              N, out.data_ptr(), D, _stream()), "gather_concat")
+            self._all_E = out
+        return self._all_E
+
+    @property
+    def all_users_emb(self):
+        return self._materialize()[:self.n_user, :]
+
+    @property
+    def all_items_emb(self):
+        return self._materialize()[self.n_user:, :]

@@ -1,0 +1,83 @@
+"""ctypes binding of libngcf_b200.so (the C ABI declared in include/ngcf_b200.h).
+
+There is no CPU fallback and no pure-PyTorch path: if the shared library is missing or a call fails,
+a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libngcf_b200.so")
+
+_vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_size_t
+
+# name -> argtypes (restype is int unless noted); mirrors include/ngcf_b200.h one to one
+SIGNATURES = {
+    "ngcf_abi_version": [],
+    "ngcf_last_error": [],
+    "ngcf_launch_count": [],
+    "ngcf_coo_to_csr_workspace": [_i64, _i64, C.POINTER(_sz)],
+    "ngcf_coo_to_csr": [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp],
+    "ngcf_edge_values": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "ngcf_feature_mix": [_vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(_vp), _vp, _i64, _f32,
+                         _vp, _vp],
+    "ngcf_spmm_split_threshold": [],
+    "ngcf_spmm": [_vp, _vp, _vp, _i64, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp,
+                  _i32, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _vp, _i64, _vp],
+    "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
+    "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32, _u64, _vp, C.c_int, _vp, _vp],
+    "ngcf_gather_concat": [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, _vp, _i64, _i64, _vp, _i64, _vp],
+    "ngcf_bpr_fwd_bwd": [_vp, _vp, _vp, _i64, C.c_int, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
+    "ngcf_rowgrad_scatter": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64), C.c_int, C.c_int, _vp,
+                             _vp, _vp],
+    "ngcf_rowgrad_reset": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, _vp, _vp],
+    "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32,
+                       _u64, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.POINTER(_sz)],
+    "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the in-tree shared library; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the NGCF B200 hot path has no CPU/PyTorch fallback. "
+            "Build it with `python -m seoul_tourism_recommendation_ngcf_b200.build` (needs nvcc, targets sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = {"ngcf_last_error": C.c_char_p, "ngcf_launch_count": C.c_uint64}.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ngcf_last_error()
+        raise RuntimeError(f"ngcf_b200 {what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def ptr_array(tensors):
+    return (_vp * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def i64_array(vals):
+    return (_i64 * len(vals))(*[int(v) for v in vals])

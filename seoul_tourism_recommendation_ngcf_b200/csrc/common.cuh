@@ -1,0 +1,122 @@
+// Shared device/host helpers for the NGCF B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ngcf_b200.h"
+
+// ---- host-side error plumbing (thread-local message behind ngcf_last_error) ----------------------
+void ngcf_set_error(const char* fmt, ...);
+
+#define NGCF_REQUIRE(cond, ...)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            ngcf_set_error(__VA_ARGS__);             \
+            return NGCF_ERR_INVALID;                 \
+        }                                            \
+    } while (0)
+
+#define NGCF_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            ngcf_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return NGCF_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+void ngcf_count_launch();   // bumps the counter behind ngcf_launch_count()
+
+#define NGCF_LAUNCH_OK(name)                                                              \
+    do {                                                                                  \
+        ngcf_count_launch();                                                              \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            ngcf_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+            return NGCF_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int ngcf_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---- device helpers ------------------------------------------------------------------------------
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// streaming (read-once) loads: keep CSR arrays out of L1 so gathered embedding rows stay resident
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011): stateless, so forward and backward can
+// regenerate the same dropout decisions from (seed, layer, element) without storing masks.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01_from_bits(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// one uniform in [0,1) for (seed, stream, layer, element)
+__device__ __forceinline__ float ngcf_uniform(uint64_t seed, uint32_t stream_id, uint32_t layer, uint64_t elem) {
+    uint4 c = make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), layer, stream_id);
+    uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    return u01_from_bits(philox4x32_10(c, k).x);
+}
+#define NGCF_STREAM_NODE 0x4e4f4445u   // 'NODE'
+#define NGCF_STREAM_MESS 0x4d455353u   // 'MESS'
+
+// Per-step randomness: `seed` is a host value baked into the launch, `seed_dev` an optional device counter
+// added to it, so a captured CUDA graph draws fresh decisions on every replay.
+__device__ __forceinline__ uint64_t ngcf_seed(uint64_t seed, const uint64_t* seed_dev) {
+    return seed + (seed_dev ? *seed_dev : 0ull);
+}
+
+// Node dropout (NGCF.py:93-100,124-126) in device-RNG mode: entry (row, col) of L survives layer `layer` iff its
+// draws for layers 0..layer are all >= p (cumulative over layers, values unscaled).  Keyed on the entry's
+// coordinates in L, so the forward CSR and the CSR of L^T agree without a permutation.
+__device__ __forceinline__ bool node_keep(float p, uint64_t seed, int layer, uint32_t row, uint32_t col) {
+    const uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    bool keep = true;
+    for (int g = 0; g * 4 <= layer && keep; ++g) {
+        const uint4 r = philox4x32_10(make_uint4(row, col, (uint32_t)g, NGCF_STREAM_NODE), k);
+        const int last = layer - 4 * g;
+        keep = u01_from_bits(r.x) >= p;
+        if (last >= 1) keep = keep && (u01_from_bits(r.y) >= p);
+        if (last >= 2) keep = keep && (u01_from_bits(r.z) >= p);
+        if (last >= 3) keep = keep && (u01_from_bits(r.w) >= p);
+    }
+    return keep;
+}
+
+// inverted-dropout multiplier of message dropout (NGCF.py:142) in device-RNG mode
+__device__ __forceinline__ float mess_multiplier(float p, uint64_t seed, int layer, uint64_t elem) {
+    float u = ngcf_uniform(seed, NGCF_STREAM_MESS, (uint32_t)layer, elem);
+    return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}

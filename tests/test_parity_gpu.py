@@ -1,0 +1,319 @@
+"""GPU parity: the CUDA path (through the C ABI, behind the drop-in NGCF / BPR modules) against
+(1) the golden vectors produced by the reference itself and (2) the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): max|a-b| / max|b| <= 1e-4 on layer embeddings, loss and gradients;
+identical top-k lists apart from score ties.
+"""
+import numpy as np
+import pytest
+import torch
+
+import seoul_tourism_recommendation_ngcf_b200 as pkg
+from oracle import ngcf_oracle as O
+from seoul_tourism_recommendation_ngcf_b200 import laplacian, synth
+from tests._golden import STEP_CASES, Golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda"
+
+
+def _build(g, rng="device"):
+    cfg = g.cfg
+    nd = synth.num_dict_for(cfg["n_user"], cfg["n_item"])
+    m = pkg.NGCF(cfg["emb"], cfg["layers"], cfg.get("node_p", 0.3), cfg.get("mess_p", [0.1] * len(cfg["layers"])),
+                 cfg.get("emb_ratio", 1.0), g.lap_list(), nd, cfg.get("B", 512), torch.device(DEV), rng=rng)
+    m.load_state_dict(g.params())
+    return m.to(DEV)
+
+
+def _call(m, b, node_flag, neg=True):
+    d = {k: v.to(DEV) for k, v in b.items()}
+    return m(year=d["year"], u_id=d["u_id"], age=d["age"], sex=d["sex"], month=d["month"], day=d["day"], dow=d["dow"],
+             pos_item=d["pos_item"], neg_item=d["neg_item"] if neg else torch.empty(0), node_flag=node_flag)
+
+
+def _check_step(m, g, u, p, n):
+    cfg = g.cfg
+    assert rel_err(u.detach().cpu().numpy(), g.out("u")) <= TOL
+    assert rel_err(p.detach().cpu().numpy(), g.out("pos")) <= TOL
+    assert rel_err(n.detach().cpu().numpy(), g.out("neg")) <= TOL
+    assert rel_err(m.all_users_emb.cpu().numpy(), g.out("all_users_emb")) <= TOL
+    assert rel_err(m.all_items_emb.cpu().numpy(), g.out("all_items_emb")) <= TOL
+    assert rel_err(m.user_embedding.weight.detach().cpu().numpy(), g.out("user_after")) <= 1e-6
+    loss = pkg.BPR(cfg["wd"], cfg["B_ctor"])(u, p, n)
+    assert loss.dim() == 0
+    assert abs(float(loss) - float(g.out("loss"))) <= TOL * abs(float(g.out("loss")))
+    m.zero_grad()
+    loss.backward()
+    for k, gr in g.grads().items():
+        got = dict(m.named_parameters())[k].grad
+        assert got is not None, k
+        assert rel_err(got.cpu().numpy(), gr) <= TOL, k
+    for k in g.nograd_keys():
+        assert dict(m.named_parameters())[k].grad is None, k       # feature tables: no gradient (NGCF.py:115)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_training_step_matches_reference_golden(name):
+    """Forward + BPR + backward against the reference's own outputs; dropout decisions injected as masks
+    reproduced from the reference's host RNG stream."""
+    g = Golden(name)
+    cfg = g.cfg
+    m = _build(g)
+    m.train(cfg["train_mode"])
+    L = g.lap_list()[O.select_year(g.batch()["year"])]
+    if cfg["rng_seed"] >= 0:
+        torch.manual_seed(cfg["rng_seed"])
+    keep, mult = O.reference_dropout_draws(L._nnz(), L.shape[0], cfg["layers"], cfg["node_p"], cfg["mess_p"],
+                                           cfg["node_flag"], cfg["train_mode"])
+    inj = {}
+    if keep is not None:
+        inj["edge_keep"] = [torch.from_numpy(k.astype(np.uint8)) for k in keep]
+    if mult is not None:
+        inj["mess_mult"] = mult
+    m._inject = inj or None
+    u, p, n = _call(m, g.batch(), cfg["node_flag"])
+    _check_step(m, g, u, p, n)
+
+
+def test_reference_rng_mode_reproduces_host_node_dropout():
+    """rng='reference': the node mask comes from the same torch CPU calls as NGCF.py:94 — no injection."""
+    g = Golden("node_dropout")
+    m = _build(g, rng="reference")
+    m.eval()
+    torch.manual_seed(g.cfg["rng_seed"])
+    u, p, n = _call(m, g.batch(), True)
+    _check_step(m, g, u, p, n)
+
+
+def test_no_negatives_and_eval_style_bpr():
+    """experiment.py:82-100: neg_item=torch.empty(0) -> third output is an empty CPU tensor; BPR is then called
+    with a single positive row broadcast against the batch."""
+    g = Golden("no_negatives")
+    m = _build(g)
+    m.eval()
+    with torch.no_grad():
+        u, p, n = _call(m, g.batch(), False, neg=False)
+    assert n.numel() == 0 and n.device.type == "cpu"
+    assert rel_err(u.cpu().numpy(), g.out("u")) <= TOL and rel_err(p.cpu().numpy(), g.out("pos")) <= TOL
+    neg = torch.cat((p[1:], p[:1]))
+    got = pkg.BPR(0.025, 25)(u, p[:1], neg)
+    want = O.bpr_loss(u.cpu(), p[:1].cpu(), neg.cpu(), 0.025, 25)
+    assert abs(float(got) - float(want)) <= TOL * abs(float(want))
+
+
+def test_demo_checkpoint_topk():
+    """demo.py:220-235 with the real checkpoint: CPU index tensors for year / pos_item, full ranking of 100 items."""
+    g = Golden("ckpt_demo")
+    m = _build(g)
+    m.eval()
+    info = g.batch()
+    with torch.no_grad():
+        u, _, _ = m(year=torch.LongTensor([0]), u_id=info["u_id"].to(DEV), age=info["age"].to(DEV),
+                    sex=info["sex"].to(DEV), month=info["month"].to(DEV), day=info["day"].to(DEV),
+                    dow=info["dow"].to(DEV), pos_item=torch.LongTensor([0]), neg_item=torch.empty(0), node_flag=False)
+    assert rel_err(u.cpu().numpy(), g.out("u")) <= TOL
+    assert rel_err(m.all_items_emb.cpu().numpy(), g.out("all_items_emb")) <= TOL
+    val, idx = pkg.score_topk(u, m.all_items_emb, 100)
+    _assert_topk(val.cpu().numpy(), idx.cpu().numpy(), g.out("scores"), 100)
+    val20, idx20 = pkg.score_topk(u, m.all_items_emb, 20)
+    _assert_topk(val20.cpu().numpy(), idx20.cpu().numpy(), g.out("scores"), 20)
+    assert np.array_equal(idx20.cpu().numpy(), idx.cpu().numpy()[:, :20])
+
+
+def _assert_topk(val, idx, ref_scores, k, tie=2e-5):
+    """Same list as sorting the reference scores, except where reference scores tie within `tie` (relative)."""
+    scale = np.abs(ref_scores).max()
+    order = np.argsort(-ref_scores, axis=1, kind="stable")[:, :k]
+    for r in range(ref_scores.shape[0]):
+        assert len(set(idx[r].tolist())) == k
+        got_ref_scores = ref_scores[r, idx[r]]
+        want = ref_scores[r, order[r]]
+        assert np.all(np.abs(got_ref_scores - want) <= tie * scale), (r, idx[r], order[r])
+        assert np.all(np.abs(val[r] - want) <= 1e-4 * scale)
+        assert np.all(np.diff(val[r]) <= 0)
+
+
+# ---- kernel-level checks against torch on seeded inputs ------------------------------------------------
+def _random_coo(N, nnz, hubs, seed, dup=True):
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, N, nnz)
+    col = rng.integers(0, N, nnz)
+    for h, cnt in hubs:                       # hub rows (longer than the split threshold) and hub columns
+        row = np.concatenate([row, np.full(cnt, h)]); col = np.concatenate([col, rng.integers(0, N, cnt)])
+        col = np.concatenate([col, np.full(cnt, h)]); row = np.concatenate([row, rng.integers(0, N, cnt)])
+    if dup:
+        row = np.concatenate([row, row[:50]]); col = np.concatenate([col, col[:50]])
+    perm = rng.permutation(row.size)          # unsorted, with duplicates: what coalesce() would have to fix
+    row, col = row[perm], col[perm]
+    val = rng.standard_normal(row.size).astype(np.float32)
+    return torch.sparse_coo_tensor(torch.from_numpy(np.stack([row, col])), torch.from_numpy(val), (N, N))
+
+
+@pytest.mark.parametrize("d", [4, 20, 64, 65, 96, 128])
+def test_spmm_forward_and_transpose_vs_torch(d):
+    from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, spmm
+    N = 3000
+    L = _random_coo(N, 40000, hubs=[(7, 5000), (1500, 700), (2999, 300)], seed=d)
+    plan = LaplacianPlan(L, DEV)
+    assert plan.fwd.n_hub >= 3 and not plan.symmetric
+    X = torch.randn(N, d, generator=torch.Generator().manual_seed(1))
+    Ld = L.to(torch.float64).coalesce()
+    want = torch.sparse.mm(Ld, X.double())
+    got = spmm(plan.fwd, plan.fwd.vals, X.to(DEV), d)
+    assert rel_err(got.cpu().numpy(), want.numpy()) <= 1e-5
+    want_t = torch.sparse.mm(Ld.t().coalesce(), X.double())
+    add = torch.randn(N, d, generator=torch.Generator().manual_seed(2))
+    got_t = spmm(plan.side(True, False), plan.side(True, False).vals, X.to(DEV), d, addend=add.to(DEV))
+    assert rel_err(got_t.cpu().numpy(), (want_t + add.double()).numpy()) <= 1e-5
+    # CSR invariants: sorted rows, permutation is a bijection onto the COO entries
+    perm = plan.fwd.perm.cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(plan.nnz))
+    rp = plan.fwd.rowptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == plan.nnz and np.all(np.diff(rp) >= 0)
+    rows_of = np.repeat(np.arange(N), np.diff(rp))
+    assert np.array_equal(rows_of, L._indices()[0].numpy()[perm])
+
+
+def test_symmetric_laplacian_shares_csr_and_empty_rows():
+    from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, spmm
+    u, i, r = synth.powerlaw_bipartite(400, 300, 3000, seed=3)
+    L = laplacian.laplacian_coo(u, i, r, 400, 320)            # 20 items without any edge -> empty rows
+    ref = O.laplacian_from_R(__import__("scipy.sparse", fromlist=["x"]).csr_matrix((r, (u, i)), shape=(400, 320)), 400, 320)
+    assert torch.equal(L._indices(), ref._indices()) and torch.equal(L._values(), ref._values())
+    plan = LaplacianPlan(L, DEV)
+    assert plan.symmetric and plan.side(True, False) is plan.fwd and plan.side(True, True) is plan.bwd
+    X = torch.randn(720, 64)
+    got = spmm(plan.fwd, plan.fwd.vals, X.to(DEV), 64)
+    want = torch.mm(L, X)
+    assert rel_err(got.cpu().numpy(), want.numpy()) <= 1e-5
+    assert float(got[700:].abs().max()) == 0.0
+
+
+def test_feature_mix_last_duplicate_wins():
+    g = Golden("emb64_k3")
+    m = _build(g)
+    b = g.batch()
+    assert b["u_id"][0] == b["u_id"][32]
+    with torch.no_grad():
+        _call(m, b, False)
+    assert np.array_equal(m.user_embedding.weight.detach().cpu().numpy(), g.out("user_after"))
+
+
+@pytest.mark.parametrize("U,I,D,k", [(3, 100, 257, 100), (37, 5000, 256, 20), (1, 129, 65, 128), (200, 300, 640, 7)])
+def test_score_topk_vs_torch(U, I, D, k):
+    gen = torch.Generator().manual_seed(U * 7 + k)
+    u = torch.randn(U, D, generator=gen)
+    it = torch.randn(I, D, generator=gen)
+    it[I // 2] = it[I // 3]                                      # an exact tie
+    val, idx = pkg.score_topk(u.to(DEV), it.to(DEV), k)
+    scores = (u.double() @ it.double().T).numpy()
+    _assert_topk(val.cpu().numpy(), idx.cpu().numpy(), scores, k)
+
+
+def test_bpr_gradients_vs_autograd():
+    gen = torch.Generator().manual_seed(5)
+    u, p, n = (torch.randn(300, 195, generator=gen) * 0.3 for _ in range(3))
+    p[3] = 0                                                      # sign(0) = 0 branch of |x|
+    ref_in = [t.clone().requires_grad_(True) for t in (u, p, n)]
+    want = O.bpr_loss(*ref_in, 0.025, 1024)
+    want.backward()
+    got_in = [t.clone().to(DEV).requires_grad_(True) for t in (u, p, n)]
+    got = pkg.BPR(0.025, 1024)(*got_in)
+    (got * 3.0).backward()
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    for a, b in zip(got_in, ref_in):
+        assert rel_err(a.grad.cpu().numpy(), 3.0 * b.grad.numpy()) <= 1e-5
+
+
+def test_device_rng_dropout_statistics_and_consistency():
+    """Device-RNG mode: keep fractions follow the reference's semantics (node: cumulative (1-p)^k, unscaled;
+    message: Bernoulli(1-p) scaled by 1/(1-p)) and forward/backward see the same decisions."""
+    from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, spmm
+    # (a) the effective masked matrix, read back through the SpMM itself with X = identity (N = 128 = max width)
+    us, is_, rs = synth.powerlaw_bipartite(70, 58, 2500, seed=9, alpha=0.2)
+    Ls = laplacian.laplacian_coo(us, is_, rs, 70, 58)
+    ps = LaplacianPlan(Ls, DEV)
+    eye = torch.eye(128, device=DEV)
+    dense = Ls.to_dense().to(DEV)
+    m0 = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=1234, layer=0)
+    m2 = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=1234, layer=2)
+    nz = dense != 0
+    f0, f2 = float((m0 != 0)[nz].float().mean()), float((m2 != 0)[nz].float().mean())
+    assert abs(f0 - 0.7) < 0.04 and abs(f2 - 0.343) < 0.04
+    assert bool(((m2 != 0) <= (m0 != 0)).all())                  # cumulative: survivors of layer 2 survived layer 0
+    assert torch.equal(m0[m0 != 0], dense[m0 != 0])              # unscaled
+    assert not torch.equal(m0, m0.T)                             # (i,j) and (j,i) are dropped independently
+    for side in (ps.bwd, ps.fwd):                                # L^T from its own CSR, and from L's (symmetric L)
+        mt = spmm(side, side.vals, eye, 128, drop_p=0.3, seed=1234, layer=0, transposed=True)
+        assert torch.equal(mt, m0.T)
+    m0b = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=99, layer=0)
+    assert not torch.equal(m0b, m0)
+    sd = torch.tensor([1234 - 99], dtype=torch.int64, device=DEV)   # device-side seed offset (graph replay path)
+    assert torch.equal(spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=99, seed_dev=sd, layer=0), m0)
+
+    u, i, r = synth.powerlaw_bipartite(2000, 1500, 60000, seed=9)
+    L = laplacian.laplacian_coo(u, i, r, 2000, 1500)
+    # whole module in training mode with device RNG: analytic gradient == finite-difference directional
+    # derivative under the same seed (same masks), which fails if forward and backward disagree on any mask
+    nd = synth.num_dict_for(2000, 1500)
+    torch.manual_seed(0)
+    m = pkg.NGCF(64, [64, 64], 0.3, [0.2, 0.2], 1.0, [L, L], nd, 256, torch.device(DEV)).to(DEV)
+    m.train()
+    b = {k: torch.from_numpy(v) for k, v in synth.random_batch(2000, 1500, 256, seed=4).items()}
+    crit = pkg.BPR(0.025, 256)
+
+    def loss_at(seed):
+        torch.manual_seed(seed)
+        return crit(*_call(m, b, True))
+
+    loss = loss_at(77)
+    m.zero_grad(); loss.backward()
+    w = m.w1_list[1].weight
+    gdir = torch.randn_like(w)
+    analytic = float((w.grad * gdir).sum())
+    eps = 1e-2
+    with torch.no_grad():
+        w.add_(eps * gdir); lp = float(loss_at(77)); w.sub_(2 * eps * gdir); lm = float(loss_at(77)); w.add_(eps * gdir)
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - analytic) <= 2e-2 * max(abs(analytic), 1e-3), (fd, analytic)
+    E1 = m._last.E[1]
+    assert abs(float((E1 == 0).float().mean()) - 0.2) < 0.02     # message dropout zeroes ~p of the entries
+
+
+@pytest.mark.parametrize("shape", ["seoul", "gowalla"])
+def test_full_size_step_vs_oracle(shape):
+    """BASELINE.json configs 1-2 at full size against the CPU oracle (the reference's torch.sparse path):
+    Seoul shape = width 65 (scalar kernels, item rows of ~4000 entries -> hub split), Gowalla shape = width 64."""
+    n_user, n_item, n_edges, emb, K = synth.SHAPES[shape]
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, n_edges, seed=0, weighted=(shape == "seoul"),
+                                       alpha=0.3 if shape == "seoul" else 0.8)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    nd = synth.num_dict_for(n_user, n_item)
+    torch.manual_seed(0)
+    m = pkg.NGCF(emb, [emb] * K, 0.3, [0.1] * K, 1.0, [L, L], nd, 1024, torch.device("cpu"))
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, 1024, seed=1).items()}
+    loss_ref, grads_ref, mid = O.train_step(params, L, b, emb_ratio=1.0, weight_decay=0.025, batch_size_ctor=1024)
+    uu, pp, nn_ = _call(m, b, False)
+    assert rel_err(uu.detach().cpu().numpy(), mid["u"].numpy()) <= TOL
+    assert rel_err(pp.detach().cpu().numpy(), mid["pos"].numpy()) <= TOL
+    assert rel_err(nn_.detach().cpu().numpy(), mid["neg"].numpy()) <= TOL
+    all_E = mid["out"]["all_E"].detach().numpy()
+    assert rel_err(m.all_users_emb.cpu().numpy(), all_E[:n_user]) <= TOL
+    assert rel_err(m.all_items_emb.cpu().numpy(), all_E[n_user:]) <= TOL
+    loss = pkg.BPR(0.025, 1024)(uu, pp, nn_)
+    assert abs(float(loss) - float(loss_ref)) <= TOL * abs(float(loss_ref))
+    loss.backward()
+    for k, gr in grads_ref.items():
+        got = dict(m.named_parameters())[k].grad
+        if gr is None:
+            assert got is None, k
+        else:
+            assert rel_err(got.cpu().numpy(), gr.numpy()) <= TOL, k
+    # top-20 over every item for 64 batch users (BASELINE north_star: identical top-20 apart from ties)
+    val, idx = pkg.score_topk(uu[:64].detach(), m.all_items_emb, 20)
+    scores = (mid["u"][:64].double() @ torch.from_numpy(all_E[n_user:]).double().T).numpy()
+    _assert_topk(val.cpu().numpy(), idx.cpu().numpy(), scores, 20, tie=5e-5)
