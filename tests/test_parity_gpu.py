@@ -273,11 +273,11 @@ def test_device_rng_dropout_statistics_and_consistency():
     w = m.w1_list[1].weight
     gdir = torch.randn_like(w)
     analytic = float((w.grad * gdir).sum())
-    eps = 1e-2
+    eps = 1e-3
     with torch.no_grad():
         w.add_(eps * gdir); lp = float(loss_at(77)); w.sub_(2 * eps * gdir); lm = float(loss_at(77)); w.add_(eps * gdir)
     fd = (lp - lm) / (2 * eps)
-    assert abs(fd - analytic) <= 2e-2 * max(abs(analytic), 1e-3), (fd, analytic)
+    assert abs(fd - analytic) <= 3e-2 * max(abs(analytic), 1e-3), (fd, analytic)
     E1 = m._last.E[1]
     assert abs(float((E1 == 0).float().mean()) - 0.2) < 0.02     # message dropout zeroes ~p of the entries
 
