@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NGCF_B200_ABI_VERSION 1
+#define NGCF_B200_ABI_VERSION 2
 #define NGCF_MAX_LAYERS 8
 #define NGCF_MAX_WIDTH 128          /* widest embedding / layer size the kernels accept */
 
@@ -55,13 +55,43 @@ int ngcf_coo_to_csr(const int64_t* coo_row, const int64_t* coo_col, int64_t nnz,
                     int32_t* colidx /*[nnz]*/, int32_t* perm /*[nnz]*/,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* vals_out[t] = coo_val[perm[t]] * keep_mask[perm[t]]: CSR-ordered edge values, optionally with an explicit
- * node-dropout mask folded in.  Replaces NGCF.sparse_dropout (NGCF.py:93-100) for masks given in COO order
- * (the reference's host RNG stream, or a mask injected by a test): dropped entries are zeroed over the fixed
- * structure instead of deleted (identical sums).  keep_mask: optional uint8[nnz]; perm may be NULL (identity).
- * (Device-RNG node dropout needs no pass at all: see ngcf_spmm.) */
-int ngcf_edge_values(const float* coo_val, const int32_t* perm, const uint8_t* keep_mask,
-                     float* vals_out, int64_t nnz, void* stream);
+/* ---- execution layout of one Laplacian direction (built once by plan.py from the CSR above) ----------------
+ * ngcf_csr is a HOST struct of DEVICE pointers.  Entries are interleaved (col, float-bits) int32 pairs.  Rows
+ * with more than ngcf_spmm_split_threshold() entries ("hubs") are empty in rowptr/ent and live in hub_ent, cut
+ * into chunks of at most that many entries; chunk c covers hub_ent[chunk_ptr[c] .. chunk_ptr[c+1]) and belongs
+ * to row chunk_row[c]; hub row with id h = hub_of_row[row] owns chunks hub_chunk_ptr[h] .. hub_chunk_ptr[h+1].
+ * Tiles are int32 quadruples {r0, r1, e0, e1}: rows [r0, r1) with entries [e0, e1) of ent (tiles, ftiles) or
+ * chunks [r0, r1) with entries [e0, e1) of hub_ent (chunk_tiles).  `tiles`/`chunk_tiles` hold at most
+ * ngcf_spmm_tile_rows() rows and ngcf_spmm_tile_entries() entries (standalone SpMM); `ftiles` at most
+ * ngcf_fused_tile_rows() rows and ngcf_fused_tile_entries() entries (fused forward layer). */
+typedef struct ngcf_csr {
+    int64_t n_rows;
+    const int32_t* rowptr;          /* [n_rows+1], hub rows empty */
+    const int32_t* ent;             /* [2*nnz_short] */
+    const int32_t* tiles;           /* [4*n_tiles] */
+    const int32_t* ftiles;          /* [4*n_ftiles] */
+    const int32_t* hub_of_row;      /* [n_rows] hub id or -1; may be NULL when n_hub == 0 */
+    const int32_t* hub_chunk_ptr;   /* [n_hub+1] */
+    const int32_t* chunk_ptr;       /* [n_chunks+1] */
+    const int32_t* hub_ent;         /* [2*nnz_hub] */
+    const int32_t* chunk_row;       /* [n_chunks] */
+    const int32_t* chunk_tiles;     /* [4*n_chunk_tiles] */
+    int32_t n_tiles, n_ftiles, n_hub, n_chunks, n_chunk_tiles, reserved;
+} ngcf_csr;
+
+int ngcf_spmm_split_threshold(void);
+int ngcf_spmm_tile_rows(void);
+int ngcf_spmm_tile_entries(void);
+int ngcf_fused_tile_rows(void);
+int ngcf_fused_tile_entries(void);
+
+/* ent_out[t] = (colidx[t], coo_val[perm[t]] * keep_mask[perm[t]]): entry pairs in execution order (ordinary rows
+ * first, then hub chunks; colidx/perm in that order), optionally with an explicit node-dropout mask folded in.
+ * Replaces NGCF.sparse_dropout (NGCF.py:93-100) for masks given in COO order (the reference's host RNG stream, or
+ * a mask injected by a test): dropped entries are zeroed over the fixed structure instead of deleted (identical
+ * sums).  keep_mask: optional uint8[nnz].  (Device-RNG node dropout needs no pass at all: see ngcf_spmm.) */
+int ngcf_edge_entries(const int32_t* colidx, const float* coo_val, const int32_t* perm, const uint8_t* keep_mask,
+                      int32_t* ent_out, int64_t nnz, void* stream);
 
 /* ---- feature mix: NGCF.py:103-115 ----------------------------------------------------------------
  * user_w[u_id[b], :] = user_w[u_id[b], :]*(1-ratio) + concat(age,sex,month,day,dow rows)*ratio,
@@ -75,25 +105,20 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
                      float ratio, int32_t* winner, void* stream);
 
 /* ---- SpMM: torch.mm(L, E), NGCF.py:130, and its backward L^T·gS (autograd MmBackward0) ----------
- * Y[i,:] = sum_t vals[t] * X[colidx[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
- * Rows longer than the plan's split threshold are pre-reduced chunk-wise into hub_partial so that no
- * warp walks a hub row alone:  hub_rows[n_hub] sorted row ids, hub_chunk_ptr[n_hub+1], and chunks
- * (hub_chunk_begin/end[n_chunks], CSR positions); hub_partial is scratch [n_chunks, d]. n_hub may be 0.
+ * Y[i,:] = sum_t val[t] * X[col[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
+ * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in order by the row
+ * pass, so the result is deterministic (no float atomics).
  *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
  *               (the IndexBackward scatter of NGCF.py:151-155 folded into the last backward SpMM).
  *   drop_p > 0: device-RNG node dropout (NGCF.py:93-100,124-126) evaluated in-kernel: entry (r,c) of L survives
  *               layer `layer` iff its Philox draws keyed on (seed + *seed_dev, r, c) for layers 0..layer are all
  *               >= drop_p (cumulative over layers, unscaled — the reference's semantics).  `transposed` != 0 says
- *               this CSR holds L^T, so both directions drop the same entries of L.  hub_chunk_row[n_chunks] gives
- *               each chunk's row.  seed_dev: optional device uint64 added to seed (graph-replay safe). */
-int ngcf_spmm_split_threshold(void);   /* rows with more entries than this must be listed in hub_rows */
-int ngcf_spmm(const int32_t* rowptr, const int32_t* colidx, const float* vals,
-              int64_t n_rows, const float* X, int64_t ldx, int d,
+ *               this CSR holds L^T, so both directions drop the same entries of L.
+ *               seed_dev: optional device uint64 added to seed (graph-replay safe). */
+int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
               const float* addend, int64_t ld_add,
               const int32_t* slot, const float* gsum, int64_t ld_gsum,
-              const int32_t* hub_rows, const int32_t* hub_chunk_ptr, int32_t n_hub,
-              const int32_t* hub_chunk_begin, const int32_t* hub_chunk_end, const int32_t* hub_chunk_row,
-              int32_t n_chunks, float* hub_partial,
+              float* hub_partial,
               float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed,
               float* Y, int64_t ldy, void* stream);
 

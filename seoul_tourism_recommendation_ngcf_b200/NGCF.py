@@ -44,7 +44,7 @@ class _Propagate(torch.autograd.Function):
         side = st.plan.fwd
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
-            vals = st.vals_f[k] if st.vals_f is not None else side.vals
+            vals = st.vals_f[k] if st.vals_f is not None else None
             S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, layer=k)   # NGCF.py:124-130
             wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
             bias = torch.empty(d_out, dtype=torch.float32, device=dev)
@@ -111,7 +111,7 @@ class _Propagate(torch.autograd.Function):
                                           float(st.mess_p[k]), st.seed, None, k, gS.data_ptr(), gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           _stream()), "dense_bwd")
-            vals = st.vals_b[k] if st.vals_b is not None else side.vals
+            vals = st.vals_b[k] if st.vals_b is not None else None
             last = (k == 0)
             gE_next = spmm(side, vals, gS, d_in, addend=gEl, slot=slot if last else None, gsum=gsum if last else None,
                            drop_p=st.drop_p, seed=st.seed, layer=k,
@@ -298,8 +298,8 @@ class NGCF(nn.Module):
         need_seed = st.drop_p > 0 or any(p > 0 for p in st.mess_p)
         st.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0
         if masks is not None:
-            st.vals_f = [plan.masked_values(plan.fwd, masks[k]) for k in range(K)]
-            st.vals_b = [plan.masked_values(plan.bwd, masks[k]) for k in range(K)]
+            st.vals_f = [plan.entries(plan.fwd, masks[k]) for k in range(K)]
+            st.vals_b = [plan.entries(plan.bwd, masks[k]) for k in range(K)]
         st.rows = [u_id, pos_item] + ([neg_item] if has_neg else [])
         st.offsets = [0, self.n_user] + ([self.n_user] if has_neg else [])
 

@@ -13,6 +13,19 @@ LIB_PATH = os.path.join(_PKG, "libngcf_b200.so")
 
 _vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_size_t
 
+
+
+class NgcfCsr(C.Structure):
+    """Mirror of ``ngcf_csr`` (include/ngcf_b200.h): a host struct of device pointers."""
+    _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp), ("ftiles", _vp),
+                ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
+                ("chunk_row", _vp), ("chunk_tiles", _vp),
+                ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
+                ("n_chunk_tiles", _i32), ("reserved", _i32)]
+
+
+_csr_p = C.POINTER(NgcfCsr)
+
 # name -> argtypes (restype is int unless noted); mirrors include/ngcf_b200.h one to one
 SIGNATURES = {
     "ngcf_abi_version": [],
@@ -20,12 +33,16 @@ SIGNATURES = {
     "ngcf_launch_count": [],
     "ngcf_coo_to_csr_workspace": [_i64, _i64, C.POINTER(_sz)],
     "ngcf_coo_to_csr": [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp],
-    "ngcf_edge_values": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "ngcf_edge_entries": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "ngcf_spmm_tile_rows": [],
+    "ngcf_spmm_tile_entries": [],
+    "ngcf_fused_tile_rows": [],
+    "ngcf_fused_tile_entries": [],
     "ngcf_feature_mix": [_vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(_vp), _vp, _i64, _f32,
                          _vp, _vp],
     "ngcf_spmm_split_threshold": [],
-    "ngcf_spmm": [_vp, _vp, _vp, _i64, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp,
-                  _i32, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _vp, _i64, _vp],
+    "ngcf_spmm": [_csr_p, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _vp,
+                  _i64, _vp],
     "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
     "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32, _u64, _vp, C.c_int, _vp, _vp],
     "ngcf_gather_concat": [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, _vp, _i64, _i64, _vp, _i64, _vp],

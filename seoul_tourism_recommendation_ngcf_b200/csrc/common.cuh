@@ -115,8 +115,18 @@ __device__ __forceinline__ bool node_keep(float p, uint64_t seed, int layer, uin
     return keep;
 }
 
-// inverted-dropout multiplier of message dropout (NGCF.py:142) in device-RNG mode
+// inverted-dropout multipliers of message dropout (NGCF.py:142) in device-RNG mode: one Philox call covers the four
+// consecutive elements 4*quad .. 4*quad+3 of the flattened [N, d_out] layer output
+__device__ __forceinline__ float4 mess_multiplier4(float p, uint64_t seed, int layer, uint64_t quad) {
+    const uint4 c = make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)layer, NGCF_STREAM_MESS);
+    const uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 r = philox4x32_10(c, k);
+    const float s = 1.0f / (1.0f - p);
+    return make_float4(u01_from_bits(r.x) >= p ? s : 0.f, u01_from_bits(r.y) >= p ? s : 0.f,
+                       u01_from_bits(r.z) >= p ? s : 0.f, u01_from_bits(r.w) >= p ? s : 0.f);
+}
 __device__ __forceinline__ float mess_multiplier(float p, uint64_t seed, int layer, uint64_t elem) {
-    float u = ngcf_uniform(seed, NGCF_STREAM_MESS, (uint32_t)layer, elem);
-    return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+    const float4 m = mess_multiplier4(p, seed, layer, elem >> 2);
+    const int j = (int)(elem & 3);
+    return j == 0 ? m.x : j == 1 ? m.y : j == 2 ? m.z : m.w;
 }

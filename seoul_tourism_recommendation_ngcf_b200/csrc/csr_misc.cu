@@ -131,23 +131,25 @@ extern "C" int ngcf_coo_to_csr(const int64_t* coo_row, const int64_t* coo_col, i
 // ------------------------------------------------------------------------------------------------
 // edge values with node dropout folded in (NGCF.py:93-100, 124-126)
 // ------------------------------------------------------------------------------------------------
-__global__ void edge_values_kernel(const float* __restrict__ coo_val, const int32_t* __restrict__ perm,
-                                   const uint8_t* __restrict__ keep_mask, float* __restrict__ out, int64_t nnz) {
+__global__ void edge_entries_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ coo_val,
+                                    const int32_t* __restrict__ perm, const uint8_t* __restrict__ keep_mask,
+                                    int2* __restrict__ out, int64_t nnz) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nnz) return;
     int64_t e = perm ? (int64_t)perm[t] : t;
     float v = coo_val[e];
     if (keep_mask && !keep_mask[e]) v = 0.0f;
-    out[t] = v;
+    out[t] = make_int2(colidx[t], __float_as_int(v));
 }
 
-extern "C" int ngcf_edge_values(const float* coo_val, const int32_t* perm, const uint8_t* keep_mask,
-                                float* vals_out, int64_t nnz, void* stream) {
-    NGCF_REQUIRE(nnz >= 0 && (nnz == 0 || (coo_val && vals_out)), "edge_values: null pointer");
+extern "C" int ngcf_edge_entries(const int32_t* colidx, const float* coo_val, const int32_t* perm,
+                                 const uint8_t* keep_mask, int32_t* ent_out, int64_t nnz, void* stream) {
+    NGCF_REQUIRE(nnz >= 0 && (nnz == 0 || (colidx && coo_val && ent_out)), "edge_entries: null pointer");
+    NGCF_REQUIRE((reinterpret_cast<uintptr_t>(ent_out) & 7) == 0, "edge_entries: ent_out must be 8-byte aligned");
     if (nnz == 0) return NGCF_OK;
-    edge_values_kernel<<<(unsigned)ceil_div64(nnz, 256), 256, 0, as_stream(stream)>>>(coo_val, perm, keep_mask,
-                                                                                     vals_out, nnz);
-    NGCF_LAUNCH_OK("edge_values_kernel");
+    edge_entries_kernel<<<(unsigned)ceil_div64(nnz, 256), 256, 0, as_stream(stream)>>>(
+        colidx, coo_val, perm, keep_mask, reinterpret_cast<int2*>(ent_out), nnz);
+    NGCF_LAUNCH_OK("edge_entries_kernel");
     return NGCF_OK;
 }
 

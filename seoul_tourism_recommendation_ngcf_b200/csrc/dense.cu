@@ -3,6 +3,9 @@
 //
 // v1 arithmetic: exact fp32 FFMA register-tiled micro-kernels (4x4 per thread, operands in shared memory,
 // LDS.128).  Every width 1..128 is accepted (the reference's own width is 65).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -417,7 +420,25 @@ int set_smem(K kernel, size_t bytes) {
     return NGCF_OK;
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
+
+// dense_tc.cu: tcgen05 / TMEM versions (3xTF32) of the dense parts, used whenever the widths allow
+bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out);
+int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
+                      const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
+                      const uint64_t* seed_dev, int layer, float* E_out, cudaStream_t st);
+
+// NGCF_B200_DENSE=ffma forces the exact-fp32 FFMA kernels (A/B comparisons); default: tensor cores where eligible
+bool ngcf_use_tensor_cores() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("NGCF_B200_DENSE");
+        cached = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    }
+    return cached == 1;
+}
 
 extern "C" int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2, int d_in,
                                  int d_out, float* wcat, float* bias_eff, void* stream) {
@@ -438,6 +459,10 @@ extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, in
     NGCF_REQUIRE(mess_p >= 0.f && mess_p < 1.f, "dense_fwd: mess_p %f not in [0,1)", mess_p);
     NGCF_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "dense_fwd: n_rows %lld", (long long)n_rows);
     if (n_rows == 0) return NGCF_OK;
+    if (ngcf_use_tensor_cores() && ngcf_dense_fwd_tc_eligible(d_in, d_out) && aligned16(S) && aligned16(E) &&
+        aligned16(E_out) && (!mess_mult || aligned16(mess_mult)))
+        return ngcf_dense_fwd_tc(S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev,
+                                 layer, E_out, as_stream(stream));
     FwdArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
               (2 * d_in + 3) & ~3, (int)ceil_div64(n_rows, FWD_R)};
     const int ncg = d_out <= 64 ? 1 : 2;

@@ -1,0 +1,178 @@
+// Device-side core of the tiled CSR SpMM, shared by the standalone SpMM (spmm.cu: backward L^T·gS, inference
+// helpers) and the fused forward layer (fused_fwd.cu).
+//
+// Layout (built once per Laplacian by plan.py, see ngcf_csr in ngcf_b200.h):
+//   * entries are interleaved (col, value-bits) pairs, so one 8-byte shared-memory read yields both;
+//   * rows longer than the split threshold ("hubs" of the power-law graph) are removed from the row CSR and
+//     stored as fixed-size chunks = pseudo-rows of a second CSR whose results (hub_partial) are summed, in
+//     order, by the owning row: no warp walks a hub alone and no float atomics are needed (deterministic);
+//   * rows are grouped into tiles (<= TILE_ROWS rows, <= TILE_ENT entries).  A CTA stages a tile's row
+//     pointers and entries in shared memory with two coalesced reads, which removes the
+//     rowptr -> entries -> gather dependency chain from every row; node dropout (device RNG) is applied to the
+//     staged values; then each warp gathers whole rows with 128-bit loads, UNROLL gathers in flight per lane.
+#pragma once
+#include "common.cuh"
+
+namespace ngcf {
+
+constexpr int SPLIT = 128;          // rows with more entries than this are hubs; also the hub chunk size
+constexpr int UNROLL = 8;           // gathered rows in flight per lane group
+
+struct TileInfo {                   // int4: rows [r0, r1), entries [e0, e1) of one tile
+    int r0, r1, e0, e1;
+};
+
+__device__ __forceinline__ int2 ld_stream_i2(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
+struct DropArgs {
+    float p;            // 0 = off
+    uint64_t seed;      // already combined with the device counter
+    int layer;
+    int transposed;     // the CSR holds L^T: entry (row, col) here is entry (col, row) of L
+};
+
+// Stages one tile: rp_s[0 .. nr] = rowptr[r0 .. r1] - e0 (tile-relative), ent_s[0 .. cnt) = entries with node
+// dropout folded in.  row_key: optional per-row id used as the dropout key instead of the row index (hub chunks).
+// All `nthreads` threads of the calling group take part; `sync()` is the group's barrier.
+template <int NTHREADS, typename Sync>
+__device__ __forceinline__ void stage_tile(const TileInfo ti, const int32_t* __restrict__ rowptr,
+                                           const int2* __restrict__ ent, const int32_t* __restrict__ row_key,
+                                           const DropArgs& dr, int* rp_s, int2* ent_s, int tid, Sync sync) {
+    const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
+    for (int i = tid; i <= nr; i += NTHREADS) rp_s[i] = rowptr[ti.r0 + i] - ti.e0;
+    if (dr.p > 0.f) {
+        sync();                                                   // rp_s visible: entries need their row
+        for (int i = tid; i < cnt; i += NTHREADS) {
+            int2 e = ld_stream_i2(ent + ti.e0 + i);
+            int lo = 0, hi = nr - 1;                              // last row with rp_s[row] <= i
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t r = (uint32_t)(row_key ? row_key[ti.r0 + lo] : ti.r0 + lo);
+            const uint32_t r0 = dr.transposed ? (uint32_t)e.x : r;
+            const uint32_t c0 = dr.transposed ? r : (uint32_t)e.x;
+            if (!node_keep(dr.p, dr.seed, dr.layer, r0, c0)) e.y = 0;
+            ent_s[i] = e;
+        }
+    } else {
+        for (int i = tid; i < cnt; i += NTHREADS) ent_s[i] = ld_stream_i2(ent + ti.e0 + i);
+    }
+    sync();
+}
+
+// ---- vector path: d % 4 == 0, 16-byte aligned rows.  A warp is cut into 32/G groups of G lanes; lane l of a
+// group owns columns [4l, 4l+4) and a group fetches one gathered row per LDG.128. ------------------------------
+template <int G>
+__device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b, const float* __restrict__ X,
+                                                 uint32_t ldx, int d, int lane) {
+    constexpr int NG = 32 / G;
+    const int g = lane / G, l = lane % G;
+    const bool active = (l * 4) < d;
+    const float* xl = X + l * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = a; j0 < b; j0 += NG * UNROLL) {
+        float4 x[UNROLL];
+        float w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int idx = j0 + u * NG + g;
+            const bool ok = (idx < b) && active;
+            int2 e = make_int2(0, 0);
+            if (ok) e = ent_s[idx];
+            w[u] = __int_as_float(e.y);
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) x[u] = ld_f4(xl + (uint64_t)(uint32_t)e.x * ldx);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            acc.x = fmaf(w[u], x[u].x, acc.x);
+            acc.y = fmaf(w[u], x[u].y, acc.y);
+            acc.z = fmaf(w[u], x[u].z, acc.z);
+            acc.w = fmaf(w[u], x[u].w, acc.w);
+        }
+    }
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(FULL_MASK, acc.x, off);
+        acc.y += __shfl_xor_sync(FULL_MASK, acc.y, off);
+        acc.z += __shfl_xor_sync(FULL_MASK, acc.z, off);
+        acc.w += __shfl_xor_sync(FULL_MASK, acc.w, off);
+    }
+    return acc;
+}
+
+// in-order sum of the hub partial rows [c0, c1) for this lane's slice (every group computes the same sum)
+template <int G>
+__device__ __forceinline__ float4 sum_partials_vec(const float* __restrict__ partial, int c0, int c1, int d,
+                                                   int lane) {
+    const int l = lane % G;
+    const bool active = (l * 4) < d;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!active) return acc;
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = ld_f4(partial + (int64_t)(c + u) * d + l * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+    }
+    for (; c < c1; ++c) {
+        const float4 x = ld_f4(partial + (int64_t)c * d + l * 4);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    return acc;
+}
+
+// ---- scalar path: any d <= 128 (the reference's own width is 65: 260-byte rows).  Lane owns columns
+// lane + 32q; the whole warp fetches one gathered row per step. -------------------------------------------------
+constexpr int SC_MAXQ = NGCF_MAX_WIDTH / 32;
+constexpr int SC_UNROLL = 4;
+
+__device__ __forceinline__ void gather_row_sc(const int2* ent_s, int a, int b, const float* __restrict__ X,
+                                              uint32_t ldx, int d, int lane, float (&acc)[SC_MAXQ]) {
+#pragma unroll
+    for (int q = 0; q < SC_MAXQ; ++q) acc[q] = 0.f;
+    for (int j0 = a; j0 < b; j0 += SC_UNROLL) {
+        float x[SC_UNROLL][SC_MAXQ];
+        float w[SC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SC_UNROLL; ++u) {
+            const int idx = j0 + u;
+            const bool ok = idx < b;
+            int2 e = make_int2(0, 0);
+            if (ok) e = ent_s[idx];
+            w[u] = __int_as_float(e.y);
+            const float* xr = X + (uint64_t)(uint32_t)e.x * ldx;
+#pragma unroll
+            for (int q = 0; q < SC_MAXQ; ++q) {
+                const int col = lane + 32 * q;
+                x[u][q] = (ok && col < d) ? xr[col] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SC_UNROLL; ++u)
+#pragma unroll
+            for (int q = 0; q < SC_MAXQ; ++q) acc[q] = fmaf(w[u], x[u][q], acc[q]);
+    }
+}
+
+__device__ __forceinline__ void sum_partials_sc(const float* __restrict__ partial, int c0, int c1, int d, int lane,
+                                                float (&acc)[SC_MAXQ]) {
+#pragma unroll
+    for (int q = 0; q < SC_MAXQ; ++q) acc[q] = 0.f;
+    for (int c = c0; c < c1; ++c) {
+#pragma unroll
+        for (int q = 0; q < SC_MAXQ; ++q) {
+            const int col = lane + 32 * q;
+            if (col < d) acc[q] += partial[(int64_t)c * d + col];
+        }
+    }
+}
+
+}  // namespace ngcf

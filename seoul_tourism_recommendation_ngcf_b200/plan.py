@@ -2,13 +2,20 @@
 
 The reference keeps each Laplacian as an uncoalesced int64 ``torch.sparse_coo`` (matrix.py:79-83) and lets
 ``torch.mm`` re-sort it on every call (NGCF.py:130; again, transposed, in the backward).  The plan converts it
-ONCE into int32 CSR for L and for L^T, with the permutations back to COO order so a per-edge node-dropout
-mask generated in COO order serves both directions, plus the hub-row split tables the SpMM kernel uses.
+ONCE into the layout the kernels execute (``ngcf_csr`` in include/ngcf_b200.h), for L and for L^T:
+
+* int32 CSR with interleaved (col, value) entry pairs;
+* rows longer than the split threshold (the hubs of a power-law graph) moved out of the row CSR into
+  fixed-size chunks that are reduced separately and summed in order (deterministic, no float atomics);
+* row tiles (bounded rows and entries) that a CTA stages in shared memory in one go;
+* the permutation back to COO order, so a per-edge node-dropout mask generated in COO order (the reference's
+  host RNG stream, NGCF.py:93-100) serves both directions.
 """
 from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -18,38 +25,108 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-class CsrSide:
-    """CSR of L (or of L^T) on the device: rowptr/colidx/perm int32, base values fp32, hub split tables."""
+def greedy_tiles(rowptr: np.ndarray, max_rows: int, max_ent: int) -> np.ndarray:
+    """Cuts rows [0, n) into consecutive tiles of at most ``max_rows`` rows and ``max_ent`` entries (a single
+    row longer than ``max_ent`` gets a tile of its own).  Returns int32 [n_tiles, 4] = (r0, r1, e0, e1)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    n = rowptr.size - 1
+    out = []
+    r = 0
+    while r < n:
+        k = int(np.searchsorted(rowptr, rowptr[r] + max_ent, side="right")) - 1   # last k with rowptr[k] <= limit
+        r1 = max(r + 1, min(r + max_rows, k, n))
+        out.append((r, r1, rowptr[r], rowptr[r1]))
+        r = r1
+    return np.asarray(out, dtype=np.int32).reshape(-1, 4)
 
-    def __init__(self, rowptr, colidx, perm, vals, n_rows, chunk):
-        self.rowptr, self.colidx, self.perm, self.vals = rowptr, colidx, perm, vals
-        self.n_rows = int(n_rows)
+
+class CsrSide:
+    """One direction (L or L^T) in execution layout; owns the device arrays behind an ``ngcf_csr`` struct."""
+
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, perm: torch.Tensor, n_rows: int, nnz: int):
         lib = _lib.load()
-        split = lib.ngcf_spmm_split_threshold()
-        deg = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
-        hub = torch.nonzero(deg > split).flatten()
-        self.n_hub = int(hub.numel())
         dev = rowptr.device
+        self.n_rows, self.nnz = int(n_rows), int(nnz)
+        split = lib.ngcf_spmm_split_threshold()
+        i32 = dict(dtype=torch.int32, device=dev)
+        deg = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+        hub_mask = deg > split
+        hub = torch.nonzero(hub_mask).flatten()
+        self.n_hub = int(hub.numel())
+        colidx, perm = colidx[:self.nnz], perm[:self.nnz]
         if self.n_hub:
+            row_of_entry = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), deg)
+            ent_is_hub = hub_mask[row_of_entry]
+            order = torch.cat([torch.nonzero(~ent_is_hub).flatten(), torch.nonzero(ent_is_hub).flatten()])
+            self.colidx, self.perm = colidx[order].contiguous(), perm[order].contiguous()
             hdeg = deg[hub]
-            nch = (hdeg + chunk - 1) // chunk
+            self.nnz_hub = int(hdeg.sum())
+            short_deg = torch.where(hub_mask, torch.zeros_like(deg), deg)
+            nch = (hdeg + split - 1) // split
             cptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=dev)
             cptr[1:] = torch.cumsum(nch, 0)
-            n_chunks = int(cptr[-1])
+            self.n_chunks = int(cptr[-1])
+            hub_base = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=dev)
+            hub_base[1:] = torch.cumsum(hdeg, 0)
             owner = torch.repeat_interleave(torch.arange(self.n_hub, device=dev), nch)
-            local = torch.arange(n_chunks, device=dev) - cptr[owner]
-            beg = rowptr[hub][owner].to(torch.int64) + local * chunk
-            end = torch.minimum(beg + chunk, rowptr[hub + 1][owner].to(torch.int64))
-            self.hub_rows = hub.to(torch.int32)
+            local = torch.arange(self.n_chunks, device=dev) - cptr[owner]
+            chunk_ptr = torch.empty(self.n_chunks + 1, dtype=torch.int64, device=dev)
+            chunk_ptr[:-1] = hub_base[owner] + local * split
+            chunk_ptr[-1] = self.nnz_hub
+            self.hub_of_row = torch.full((self.n_rows,), -1, **i32)
+            self.hub_of_row[hub] = torch.arange(self.n_hub, **i32)
             self.hub_chunk_ptr = cptr.to(torch.int32)
-            self.hub_chunk_begin = beg.to(torch.int32)
-            self.hub_chunk_end = end.to(torch.int32)
-            self.hub_chunk_row = hub[owner].to(torch.int32)
-            self.n_chunks = n_chunks
+            self.chunk_ptr = chunk_ptr.to(torch.int32)
+            self.chunk_row = hub[owner].to(torch.int32)
         else:
-            self.hub_rows = self.hub_chunk_ptr = self.hub_chunk_begin = self.hub_chunk_end = self.hub_chunk_row = None
-            self.n_chunks = 0
+            self.colidx, self.perm = colidx.contiguous(), perm.contiguous()
+            self.nnz_hub, self.n_chunks = 0, 0
+            short_deg = deg
+            self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = None
+        self.nnz_short = self.nnz - self.nnz_hub
+        self.rowptr = torch.zeros(self.n_rows + 1, **i32)
+        self.rowptr[1:] = torch.cumsum(short_deg, 0).to(torch.int32)
+        rp_host = self.rowptr.cpu().numpy()
+        self.tiles = torch.from_numpy(greedy_tiles(rp_host, lib.ngcf_spmm_tile_rows(),
+                                                   lib.ngcf_spmm_tile_entries())).to(dev)
+        self.ftiles = torch.from_numpy(greedy_tiles(rp_host, lib.ngcf_fused_tile_rows(),
+                                                    lib.ngcf_fused_tile_entries())).to(dev)
+        if self.n_chunks:
+            self.chunk_tiles = torch.from_numpy(greedy_tiles(self.chunk_ptr.cpu().numpy(), lib.ngcf_spmm_tile_rows(),
+                                                             lib.ngcf_spmm_tile_entries())).to(dev)
+        else:
+            self.chunk_tiles = None
+        self.ent = None          # base entry pairs, set by LaplacianPlan
         self._partial = {}
+        self._struct_cache = {}
+
+    def descriptor(self, ent: torch.Tensor | None = None) -> "_lib.NgcfCsr":
+        """``ngcf_csr`` over this side's arrays; ``ent`` = alternative [nnz, 2] entry pairs (masked values)."""
+        ent = self.ent if ent is None else ent
+        key = ent.data_ptr()
+        s = self._struct_cache.get(key)
+        if s is None:
+            if len(self._struct_cache) > 64:
+                self._struct_cache.clear()
+            s = _lib.NgcfCsr()
+            s.n_rows = self.n_rows
+            s.rowptr = self.rowptr.data_ptr()
+            s.ent = ent.data_ptr()
+            s.tiles = self.tiles.data_ptr()
+            s.ftiles = self.ftiles.data_ptr()
+            s.hub_of_row = _lib.ptr(self.hub_of_row)
+            s.hub_chunk_ptr = _lib.ptr(self.hub_chunk_ptr)
+            s.chunk_ptr = _lib.ptr(self.chunk_ptr)
+            s.hub_ent = ent.data_ptr() + 8 * self.nnz_short
+            s.chunk_row = _lib.ptr(self.chunk_row)
+            s.chunk_tiles = _lib.ptr(self.chunk_tiles)
+            s.n_tiles = int(self.tiles.shape[0])
+            s.n_ftiles = int(self.ftiles.shape[0])
+            s.n_hub = self.n_hub
+            s.n_chunks = self.n_chunks
+            s.n_chunk_tiles = int(self.chunk_tiles.shape[0]) if self.chunk_tiles is not None else 0
+            self._struct_cache[key] = s
+        return s
 
     def hub_partial(self, d: int):
         if not self.n_hub:
@@ -62,7 +139,7 @@ class CsrSide:
 
 
 class LaplacianPlan:
-    def __init__(self, L: torch.Tensor, device, hub_chunk: int = 256):
+    def __init__(self, L: torch.Tensor, device):
         if not (L.is_sparse and L.dim() == 2 and L.shape[0] == L.shape[1]):
             raise ValueError("lap_list entries must be square torch.sparse_coo tensors (matrix.py:79-83)")
         device = torch.device(device)
@@ -88,46 +165,42 @@ class LaplacianPlan:
             _lib.check(lib.ngcf_coo_to_csr(row.data_ptr(), col.data_ptr(), self.nnz, self.N, self.N, transpose,
                                            rowptr.data_ptr(), colidx.data_ptr(), perm.data_ptr(), ws.data_ptr(),
                                            need.value, _stream()), "coo_to_csr")
-            vals = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=device)
-            _lib.check(lib.ngcf_edge_values(self.coo_val.data_ptr(), perm.data_ptr(), None, vals.data_ptr(), self.nnz,
-                                            _stream()), "edge_values")
-            sides.append(CsrSide(rowptr, colidx, perm, vals, self.N, hub_chunk))
+            side = CsrSide(rowptr, colidx, perm, self.N, self.nnz)
+            side.ent = self.entries(side, None)
+            sides.append(side)
         torch.cuda.current_stream().synchronize()
         del ws
         self.fwd, self.bwd = sides
-        # L = D^-1/2 A D^-1/2 is symmetric (matrix.py:48-62): then L^T's CSR is L's, and sharing the arrays
+        # L = D^-1/2 A D^-1/2 is symmetric (matrix.py:48-62): then L^T's layout is L's, and sharing the arrays
         # halves the distinct bytes a training step touches.  Node dropout breaks the symmetry per step, which
-        # is handled by giving the two directions separate masked value arrays.
-        self.symmetric = bool(torch.equal(self.fwd.rowptr, self.bwd.rowptr) and torch.equal(self.fwd.colidx, self.bwd.colidx)
-                              and torch.equal(self.fwd.vals, self.bwd.vals))
+        # is handled by giving the two directions separate masked entry arrays.
+        self.symmetric = bool(torch.equal(self.fwd.rowptr, self.bwd.rowptr) and torch.equal(self.fwd.ent, self.bwd.ent))
 
     def side(self, transposed: bool, masked: bool) -> CsrSide:
         if transposed and not (self.symmetric and not masked):
             return self.bwd
         return self.fwd
 
-    def masked_values(self, side: CsrSide, keep_mask):
-        """CSR-ordered edge values with an explicit COO-order node-dropout mask folded in (NGCF.py:93-100)."""
+    def entries(self, side: CsrSide, keep_mask):
+        """Entry pairs in execution order, optionally with an explicit COO-order node-dropout mask folded in
+        (NGCF.py:93-100).  Two trailing pad pairs keep vector reads in bounds."""
         lib = _lib.load()
-        out = torch.empty_like(side.vals)
-        _lib.check(lib.ngcf_edge_values(self.coo_val.data_ptr(), side.perm.data_ptr(), _lib.ptr(keep_mask),
-                                        out.data_ptr(), self.nnz, _stream()), "edge_values")
+        out = torch.zeros(self.nnz + 2, 2, dtype=torch.int32, device=self.coo_val.device)
+        _lib.check(lib.ngcf_edge_entries(side.colidx.data_ptr(), self.coo_val.data_ptr(), side.perm.data_ptr(),
+                                         _lib.ptr(keep_mask), out.data_ptr(), self.nnz, _stream()), "edge_entries")
         return out
 
 
-def spmm(side: CsrSide, vals, X, d: int, out=None, addend=None, slot=None, gsum=None, drop_p: float = 0.0,
+def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=None, drop_p: float = 0.0,
          seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False):
     """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout."""
     lib = _lib.load()
     if out is None:
         out = torch.empty(side.n_rows, d, dtype=torch.float32, device=X.device)
-    _lib.check(lib.ngcf_spmm(side.rowptr.data_ptr(), side.colidx.data_ptr(), vals.data_ptr(), side.n_rows,
-                             X.data_ptr(), X.stride(0), d,
+    _lib.check(lib.ngcf_spmm(C.byref(side.descriptor(ent)), X.data_ptr(), X.stride(0), d,
                              _lib.ptr(addend), addend.stride(0) if addend is not None else 0,
                              _lib.ptr(slot), _lib.ptr(gsum), gsum.stride(0) if gsum is not None else 0,
-                             _lib.ptr(side.hub_rows), _lib.ptr(side.hub_chunk_ptr), side.n_hub,
-                             _lib.ptr(side.hub_chunk_begin), _lib.ptr(side.hub_chunk_end), _lib.ptr(side.hub_chunk_row),
-                             side.n_chunks, _lib.ptr(side.hub_partial(d)),
+                             _lib.ptr(side.hub_partial(d)),
                              float(drop_p), int(seed) & (2 ** 64 - 1), _lib.ptr(seed_dev), int(layer), int(transposed),
                              out.data_ptr(), out.stride(0), _stream()), "spmm")
     return out

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.ngcf_abi_version() == 1
+    assert lib.ngcf_abi_version() == 2
     assert lib.ngcf_spmm_split_threshold() > 0
     # argument validation happens before any CUDA call
     need = ctypes.c_size_t(0)
@@ -102,3 +102,23 @@ def test_synthetic_graph_generator():
     assert deg.max() > 5 * max(1.0, np.median(deg))           # skewed popularity
     b = synth.random_batch(300, 200, 64)
     assert set(b) == {"year", "u_id", "age", "sex", "month", "day", "dow", "pos_item", "neg_item"}
+
+
+def test_greedy_tiles_cover_rows_within_caps():
+    """Row tiling of the execution plan (plan.greedy_tiles): consecutive, complete, capped."""
+    from seoul_tourism_recommendation_ngcf_b200.plan import greedy_tiles
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 129, size=5000)
+    deg[rng.integers(0, 5000, 200)] = 0
+    rp = np.concatenate([[0], np.cumsum(deg)])
+    for max_rows, max_ent in ((16, 512), (64, 2048), (1, 128), (16, 128)):
+        t = greedy_tiles(rp, max_rows, max_ent)
+        assert t.dtype == np.int32 and t.shape[1] == 4
+        assert t[0, 0] == 0 and t[-1, 1] == 5000 and np.array_equal(t[1:, 0], t[:-1, 1])
+        assert np.all(t[:, 1] - t[:, 0] >= 1) and np.all(t[:, 1] - t[:, 0] <= max_rows)
+        assert np.all(t[:, 3] - t[:, 2] <= max_ent)
+        assert np.array_equal(t[:, 2], rp[t[:, 0]]) and np.array_equal(t[:, 3], rp[t[:, 1]])
+    # a single over-long row gets a tile of its own instead of an endless loop
+    t = greedy_tiles(np.array([0, 5, 1005, 1010]), 16, 512)
+    assert t.tolist() == [[0, 1, 0, 5], [1, 2, 5, 1005], [2, 3, 1005, 1010]]
+    assert greedy_tiles(np.array([0]), 16, 512).shape == (0, 4)

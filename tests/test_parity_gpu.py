@@ -161,19 +161,31 @@ def test_spmm_forward_and_transpose_vs_torch(d):
     X = torch.randn(N, d, generator=torch.Generator().manual_seed(1))
     Ld = L.to(torch.float64).coalesce()
     want = torch.sparse.mm(Ld, X.double())
-    got = spmm(plan.fwd, plan.fwd.vals, X.to(DEV), d)
+    got = spmm(plan.fwd, None, X.to(DEV), d)
     assert rel_err(got.cpu().numpy(), want.numpy()) <= 1e-5
     want_t = torch.sparse.mm(Ld.t().coalesce(), X.double())
     add = torch.randn(N, d, generator=torch.Generator().manual_seed(2))
-    got_t = spmm(plan.side(True, False), plan.side(True, False).vals, X.to(DEV), d, addend=add.to(DEV))
+    got_t = spmm(plan.side(True, False), None, X.to(DEV), d, addend=add.to(DEV))
     assert rel_err(got_t.cpu().numpy(), (want_t + add.double()).numpy()) <= 1e-5
-    # CSR invariants: sorted rows, permutation is a bijection onto the COO entries
-    perm = plan.fwd.perm.cpu().numpy()
+    # layout invariants: the permutation is a bijection onto the COO entries; ordinary rows first (row CSR with
+    # the hub rows emptied), then the hub rows' entries in row order, cut into chunks of <= split entries
+    side = plan.fwd
+    perm = side.perm.cpu().numpy()
     assert np.array_equal(np.sort(perm), np.arange(plan.nnz))
-    rp = plan.fwd.rowptr.cpu().numpy()
-    assert rp[0] == 0 and rp[-1] == plan.nnz and np.all(np.diff(rp) >= 0)
+    rp = side.rowptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == side.nnz_short and np.all(np.diff(rp) >= 0)
+    coo_rows = L._indices()[0].numpy()
     rows_of = np.repeat(np.arange(N), np.diff(rp))
-    assert np.array_equal(rows_of, L._indices()[0].numpy()[perm])
+    assert np.array_equal(rows_of, coo_rows[perm[:side.nnz_short]])
+    cp, crow = side.chunk_ptr.cpu().numpy(), side.chunk_row.cpu().numpy()
+    assert cp[0] == 0 and cp[-1] == side.nnz_hub and np.all(np.diff(cp) > 0) and np.diff(cp).max() <= 128
+    assert np.array_equal(np.repeat(crow, np.diff(cp)), coo_rows[perm[side.nnz_short:]])
+    hub_of = side.hub_of_row.cpu().numpy()
+    assert set(np.nonzero(hub_of >= 0)[0]) == set(crow) and np.all(np.diff(rp)[hub_of >= 0] == 0)
+    for tiles, ptr in ((side.tiles, rp), (side.ftiles, rp), (side.chunk_tiles, cp)):
+        t = tiles.cpu().numpy()
+        assert t[0, 0] == 0 and t[-1, 1] == ptr.size - 1 and np.array_equal(t[1:, 0], t[:-1, 1])
+        assert np.array_equal(t[:, 2], ptr[t[:, 0]]) and np.array_equal(t[:, 3], ptr[t[:, 1]])
 
 
 def test_symmetric_laplacian_shares_csr_and_empty_rows():
@@ -185,7 +197,7 @@ def test_symmetric_laplacian_shares_csr_and_empty_rows():
     plan = LaplacianPlan(L, DEV)
     assert plan.symmetric and plan.side(True, False) is plan.fwd and plan.side(True, True) is plan.bwd
     X = torch.randn(720, 64)
-    got = spmm(plan.fwd, plan.fwd.vals, X.to(DEV), 64)
+    got = spmm(plan.fwd, None, X.to(DEV), 64)
     want = torch.mm(L, X)
     assert rel_err(got.cpu().numpy(), want.numpy()) <= 1e-5
     assert float(got[700:].abs().max()) == 0.0
@@ -237,8 +249,8 @@ def test_device_rng_dropout_statistics_and_consistency():
     ps = LaplacianPlan(Ls, DEV)
     eye = torch.eye(128, device=DEV)
     dense = Ls.to_dense().to(DEV)
-    m0 = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=1234, layer=0)
-    m2 = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=1234, layer=2)
+    m0 = spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=1234, layer=0)
+    m2 = spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=1234, layer=2)
     nz = dense != 0
     f0, f2 = float((m0 != 0)[nz].float().mean()), float((m2 != 0)[nz].float().mean())
     assert abs(f0 - 0.7) < 0.04 and abs(f2 - 0.343) < 0.04
@@ -246,12 +258,12 @@ def test_device_rng_dropout_statistics_and_consistency():
     assert torch.equal(m0[m0 != 0], dense[m0 != 0])              # unscaled
     assert not torch.equal(m0, m0.T)                             # (i,j) and (j,i) are dropped independently
     for side in (ps.bwd, ps.fwd):                                # L^T from its own CSR, and from L's (symmetric L)
-        mt = spmm(side, side.vals, eye, 128, drop_p=0.3, seed=1234, layer=0, transposed=True)
+        mt = spmm(side, None, eye, 128, drop_p=0.3, seed=1234, layer=0, transposed=True)
         assert torch.equal(mt, m0.T)
-    m0b = spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=99, layer=0)
+    m0b = spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=99, layer=0)
     assert not torch.equal(m0b, m0)
     sd = torch.tensor([1234 - 99], dtype=torch.int64, device=DEV)   # device-side seed offset (graph replay path)
-    assert torch.equal(spmm(ps.fwd, ps.fwd.vals, eye, 128, drop_p=0.3, seed=99, seed_dev=sd, layer=0), m0)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=99, seed_dev=sd, layer=0), m0)
 
     u, i, r = synth.powerlaw_bipartite(2000, 1500, 60000, seed=9)
     L = laplacian.laplacian_coo(u, i, r, 2000, 1500)
@@ -317,3 +329,43 @@ def test_full_size_step_vs_oracle(shape):
     val, idx = pkg.score_topk(uu[:64].detach(), m.all_items_emb, 20)
     scores = (mid["u"][:64].double() @ torch.from_numpy(all_E[n_user:]).double().T).numpy()
     _assert_topk(val.cpu().numpy(), idx.cpu().numpy(), scores, 20, tie=5e-5)
+
+
+def _dense_fwd(S, E, W1, b1, W2, b2, mess_mult=None):
+    """ngcf_pack_weights + ngcf_dense_fwd through the C ABI on device tensors."""
+    from seoul_tourism_recommendation_ngcf_b200 import _lib
+    lib = _lib.load()
+    N, d_in = S.shape
+    d_out = W1.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    wcat = torch.empty(2 * d_in * d_out, device=DEV)
+    bias = torch.empty(d_out, device=DEV)
+    _lib.check(lib.ngcf_pack_weights(W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d_in, d_out,
+                                     wcat.data_ptr(), bias.data_ptr(), st))
+    out = torch.empty(N, d_out, device=DEV)
+    _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E.data_ptr(), N, d_in, d_out, wcat.data_ptr(), bias.data_ptr(), 0.2,
+                                  _lib.ptr(mess_mult), 0.0, 0, None, 0, out.data_ptr(), st), "dense_fwd")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("N,d_in,d_out", [(1000, 64, 64), (128, 64, 64), (70839, 64, 64), (333, 32, 48), (777, 64, 16),
+                                          (500, 65, 64), (300, 128, 128), (257, 20, 36)])
+def test_dense_forward_vs_float64(N, d_in, d_out):
+    """Per-layer epilogue (NGCF.py:131-142) against a float64 restatement.  Widths 32/64 take the tcgen05 3xTF32
+    kernel, everything else the FFMA kernel; both must be at fp32 accuracy (1e-5 here, far inside the 1e-4 bar:
+    a plain TF32 product would sit near 5e-4)."""
+    g = torch.Generator().manual_seed(N + d_in)
+    S, E = torch.randn(N, d_in, generator=g), torch.randn(N, d_in, generator=g)
+    W1, W2 = torch.randn(d_out, d_in, generator=g) * 0.2, torch.randn(d_out, d_in, generator=g) * 0.2
+    b1, b2 = torch.randn(d_out, generator=g), torch.randn(d_out, generator=g)
+    mult = (torch.rand(N, d_out, generator=g) > 0.3).float() * 1.25
+    for mm in (None, mult):
+        got = _dense_fwd(S.to(DEV), E.to(DEV), W1.to(DEV), b1.to(DEV), W2.to(DEV), b2.to(DEV),
+                         None if mm is None else mm.to(DEV))
+        Sd, Ed = S.double(), E.double()
+        M = (Sd + Ed) @ W1.double().T + (Sd * Ed) @ W2.double().T + 2 * b1.double() + b2.double()
+        want = torch.where(M > 0, M, 0.2 * M)
+        if mm is not None:
+            want = want * mm.double()
+        assert rel_err(got.cpu().numpy(), want.numpy()) <= 1e-5

@@ -26,9 +26,9 @@ for r in range(reps):
     flush.zero_()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    spmm(plan.fwd, plan.fwd.vals, X, d, out=Y, drop_p=drop, seed=1, layer=0)
+    spmm(plan.fwd, None, X, d, out=Y, drop_p=drop, seed=1, layer=0)
     e1.record()
-    spmm(plan.fwd, plan.fwd.vals, X, d, out=Y, drop_p=drop, seed=1, layer=0)
+    spmm(plan.fwd, None, X, d, out=Y, drop_p=drop, seed=1, layer=0)
     e2.record()
     torch.cuda.synchronize()
     print(f"rep {r}: cold {e0.elapsed_time(e1) * 1e3:.1f} us, warm {e1.elapsed_time(e2) * 1e3:.1f} us")
