@@ -302,9 +302,13 @@ def bpr_f64(eu, ep, en, wd, batch_size):
     return loss, g_u, g_p, g_n
 
 
-def backward_f64(fw: dict, W1, W2, G, mess_mult=None, slope=0.2):
+def backward_f64(fw: dict, W1, W2, G, mess_mult=None, slope=0.2, act_pos=None):
     """Hand-derived backward of ``propagate_f64`` given G = dLoss/d all_E  [N, D_total]
-    (SURVEY.md section 3.4).  Returns dict(gE0, gW1[k], gb1[k], gW2[k], gb2[k])."""
+    (SURVEY.md section 3.4).  Returns dict(gE0, gW1[k], gb1[k], gW2[k], gb2[k]).
+    act_pos: optional list of K boolean [N, d_k] arrays used as the LeakyReLU branch (M > 0) instead of this
+    forward's own signs: LeakyReLU'(M) jumps at M = 0, so two correct forwards that differ by rounding can
+    disagree on the branch of a numerically-zero pre-activation; passing the other implementation's branches
+    makes the comparison of the gradients well defined."""
     K = len(W1)
     dims = [fw["E"][0].shape[1]] + [fw["E"][k + 1].shape[1] for k in range(K)]
     offs = np.cumsum([0] + dims)
@@ -314,7 +318,7 @@ def backward_f64(fw: dict, W1, W2, G, mess_mult=None, slope=0.2):
         H, n, M, S, E = fw["H"][k], fw["n"][k], fw["M"][k], fw["S"][k], fw["E"][k]
         gH = G[:, offs[k + 1]:offs[k + 2]]
         gEp = gE_next + (gH - H * (H * gH).sum(1, keepdims=True)) / n
-        gM = gEp * np.where(M > 0, 1.0, slope)
+        gM = gEp * np.where(M > 0 if act_pos is None else np.asarray(act_pos[k]), 1.0, slope)
         if mess_mult is not None:
             gM = gM * np.asarray(mess_mult[k], np.float64)
         w1, w2 = np.asarray(W1[k], np.float64), np.asarray(W2[k], np.float64)
@@ -325,3 +329,35 @@ def backward_f64(fw: dict, W1, W2, G, mess_mult=None, slope=0.2):
         gE_next = T1 + T2 * S + fw["L"][k].T @ gS
     gE0 = gE_next + G[:, :dims[0]]
     return dict(gE0=gE0, gW1=gW1, gb1=gb1, gW2=gW2, gb2=gb2)
+
+
+def train_step_f64(params: dict, L, batch: dict, *, emb_ratio, weight_decay, batch_size_ctor, act_pos=None):
+    """float64 restatement of one whole training step without dropout (feature mix in fp32 exactly as the reference
+    does it, then propagate_f64 + bpr_f64 + backward_f64).  Returns (loss, grads dict keyed like the state_dict,
+    forward dict).  See backward_f64 for act_pos."""
+    K = sum(1 for k in params if k.startswith("w1_list.") and k.endswith(".weight"))
+    n_user = params["user_embedding.weight"].shape[0]
+    user = params["user_embedding.weight"].detach().clone()
+    tables = {"age": params["age_emb.weight"], "sex": params["sex_emb.weight"], "month": params["month_emb.weight"],
+              "day": params["day_emb.weight"], "dow": params["dow_emb.weight"]}
+    feature_mix_(user, tables, {k: batch[k] for k in FEATURE_ORDER}, batch["u_id"], emb_ratio)
+    E0 = torch.cat([user, params["item_embedding.weight"]]).numpy()
+    W1 = [params[f"w1_list.{k}.weight"].numpy() for k in range(K)]
+    b1 = [params[f"w1_list.{k}.bias"].numpy() for k in range(K)]
+    W2 = [params[f"w2_list.{k}.weight"].numpy() for k in range(K)]
+    b2 = [params[f"w2_list.{k}.bias"].numpy() for k in range(K)]
+    fw = propagate_f64(L, E0, W1, b1, W2, b2)
+    A = fw["all_E"]
+    uid = batch["u_id"].numpy()
+    pid, nid = batch["pos_item"].numpy() + n_user, batch["neg_item"].numpy() + n_user
+    loss, gu, gp, gn = bpr_f64(A[uid], A[pid], A[nid], weight_decay, batch_size_ctor)
+    G = np.zeros_like(A)
+    np.add.at(G, uid, gu)
+    np.add.at(G, pid, gp)
+    np.add.at(G, nid, gn)
+    bw = backward_f64(fw, W1, W2, G, act_pos=act_pos)
+    grads = {"user_embedding.weight": bw["gE0"][:n_user], "item_embedding.weight": bw["gE0"][n_user:]}
+    for k in range(K):
+        grads[f"w1_list.{k}.weight"], grads[f"w1_list.{k}.bias"] = bw["gW1"][k], bw["gb1"][k]
+        grads[f"w2_list.{k}.weight"], grads[f"w2_list.{k}.bias"] = bw["gW2"][k], bw["gb2"][k]
+    return loss, grads, fw

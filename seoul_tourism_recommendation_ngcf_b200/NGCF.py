@@ -99,6 +99,7 @@ class _Propagate(torch.autograd.Function):
         side = st.plan.side(True, st.vals_b is not None)
         gE_next = None
         col_off = D
+        gM_scratch = torch.empty(N, max(dims[1:]), dtype=torch.float32, device=dev)
         for k in range(K - 1, -1, -1):
             d_in, d_out = dims[k], dims[k + 1]
             col_off -= d_out
@@ -110,12 +111,14 @@ class _Propagate(torch.autograd.Function):
                                           st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE, _lib.ptr(mm),
                                           float(st.mess_p[k]), st.seed, None, k, gS.data_ptr(), gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
-                                          _stream()), "dense_bwd")
+                                          gM_scratch.data_ptr(), _stream()), "dense_bwd")
             vals = st.vals_b[k] if st.vals_b is not None else None
             last = (k == 0)
             gE_next = spmm(side, vals, gS, d_in, addend=gEl, slot=slot if last else None, gsum=gsum if last else None,
                            drop_p=st.drop_p, seed=st.seed, layer=k,
                            transposed=True)                           # gE_k = gEl + L^T gS (+ layer-0 row grads)
+            if mod._trace is not None:                                # debugging aid: per-layer backward tensors
+                mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
                    "rowgrad_reset")
         gU, gI = gE_next[:mod.n_user], gE_next[mod.n_user:]
@@ -169,6 +172,7 @@ class NGCF(nn.Module):
         self._winner = None
         self._last = None
         self._all_E = None
+        self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
     def set_layers(self):

@@ -430,14 +430,17 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                       const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
                       const uint64_t* seed_dev, int layer, float* E_out, cudaStream_t st);
 
+bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out);
+int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
+                      const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
+                      const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
+                      uint64_t seed, const uint64_t* seed_dev, int layer, float* gS, float* gEl, float* gW1,
+                      float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st);
+
 // NGCF_B200_DENSE=ffma forces the exact-fp32 FFMA kernels (A/B comparisons); default: tensor cores where eligible
 bool ngcf_use_tensor_cores() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("NGCF_B200_DENSE");
-        cached = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
-    }
-    return cached == 1;
+    const char* e = getenv("NGCF_B200_DENSE");
+    return !(e && strcmp(e, "ffma") == 0);
 }
 
 extern "C" int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2, int d_in,
@@ -485,7 +488,8 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
                               int col_off, const float* E_out, const float* S, const float* E, int64_t n_rows,
                               int d_in, int d_out, const float* W1, const float* W2, float slope,
                               const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                              float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, void* stream) {
+                              float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch,
+                              void* stream) {
     NGCF_REQUIRE(E_out && S && E && W1 && W2 && gS && gEl && gW1 && gb1 && gW2 && gb2, "dense_bwd: null pointer");
     NGCF_REQUIRE(!slot || gsum, "dense_bwd: slot given without gsum");
     NGCF_REQUIRE(d_in > 0 && d_in <= NGCF_MAX_WIDTH && d_out > 0 && d_out <= NGCF_MAX_WIDTH,
@@ -493,6 +497,11 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
     NGCF_REQUIRE(mess_p >= 0.f && mess_p < 1.f, "dense_bwd: mess_p %f not in [0,1)", mess_p);
     NGCF_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "dense_bwd: n_rows %lld", (long long)n_rows);
     if (n_rows == 0) return NGCF_OK;
+    if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out) && aligned16(S) &&
+        aligned16(E) && aligned16(gS) && aligned16(gEl) && aligned16(gM_scratch))
+        return ngcf_dense_bwd_tc(gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2,
+                                 slope, mess_mult, mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2,
+                                 gM_scratch, as_stream(stream));
     BwdArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
               mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0};
     int rc;

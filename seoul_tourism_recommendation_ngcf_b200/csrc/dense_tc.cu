@@ -11,6 +11,8 @@
 // A is pipelined per 32-wide K block: block kb of the next tile is refilled as soon as the MMAs that read it have
 // completed (tcgen05.commit -> empty[kb]); the accumulator is double buffered in TMEM so the epilogue of tile t
 // overlaps the loads and MMAs of tile t+1.
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace {
@@ -23,6 +25,7 @@ constexpr int TC_LOAD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_LOAD_WARPS) * 32;
 constexpr int TC_MAX_KB = 4;                 // K blocks of 32 TF32 (128 bytes): 2*d_in/32 <= 4  ->  d_in <= 64
 constexpr int TC_A_BLOCK = TC_ROWS * 128;    // bytes of one K block of A (hi or lo)
+constexpr int FW_STAGE_PITCH = 36;           // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
 
 struct FwdTcArgs {
     const float* S;
@@ -61,7 +64,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     uint8_t* B_hi = A_lo + KB * TC_A_BLOCK;
     uint8_t* B_lo = B_hi + KB * b_block;
     float* bias_s = reinterpret_cast<float*>(B_lo + KB * b_block);
-    Bars* bars = reinterpret_cast<Bars*>(bias_s + 64);
+    float* stage = bias_s + 64;                                           // [4 warps][32][FW_STAGE_PITCH]
+    Bars* bars = reinterpret_cast<Bars*>(stage + TC_EPI_WARPS * 32 * FW_STAGE_PITCH);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -101,44 +105,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
 
     if (warp < TC_EPI_WARPS) {
         // ======================= epilogue =======================================================================
+        // TMEM lane = tile row, so a thread holds one row; bias + LeakyReLU + dropout are applied in that layout, then
+        // the 32x32 block goes through a per-warp transposition buffer so the global stores are coalesced.
         const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        float* st = stage + warp * 32 * FW_STAGE_PITCH;
+        const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int buf = it & 1;
             mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
             tc_fence_after_sync();
-            float acc[64];
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
-            {
-                float lo[32], hi[32];
-                tmem_ld_32x32(taddr, lo);
-                if (d_out > 32) tmem_ld_32x32(taddr + 32, hi);
+            const int64_t row_base = (int64_t)tile * TC_ROWS + warp * 32;
+            const int n_chunks = d_out / 32 + (d_out % 32 != 0);
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c) {
+                float v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                if (c == n_chunks - 1) {                                  // accumulator drained: next tile may reuse it
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+                }
+                const int64_t my_row = row_base + lane;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { acc[j] = lo[j]; acc[32 + j] = d_out > 32 ? hi[j] : 0.f; }
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);          // accumulator drained: next tile may reuse it
-            const int64_t row = (int64_t)tile * TC_ROWS + warp * 32 + lane;
-            if (row < a.n_rows) {
-                float* out = a.E_out + row * d_out;
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    if (j < d_out) {
-                        float o[4];
+                    for (int t = 0; t < 4; ++t) {
+                        const float m = v[j + t] + bias_s[c * 32 + j + t];
+                        o[t] = m > 0.f ? m : a.slope * m;                               // LeakyReLU, NGCF.py:140
+                    }
+                    if (!a.mess_mult && a.mess_p > 0.f) {
+                        const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)(my_row * d_out + c * 32 + j) >> 2);
+                        o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
+                    }
+                    st_f4(st + lane * FW_STAGE_PITCH + j, make_float4(o[0], o[1], o[2], o[3]));
+                }
+                __syncwarp();
+                float4 r4[8];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float m = acc[j + c] + bias_s[j + c];
-                            o[c] = m > 0.f ? m : a.slope * m;                       // LeakyReLU, NGCF.py:140
+                for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + (i * 4 + rr) * FW_STAGE_PITCH + c4 * 4);
+                __syncwarp();
+                const int col = c * 32 + c4 * 4;
+                if (col < d_out) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t row = row_base + i * 4 + rr;
+                        if (row < a.n_rows) {
+                            if (a.mess_mult) {
+                                const float4 mm = ld_f4(a.mess_mult + row * d_out + col);
+                                r4[i].x *= mm.x; r4[i].y *= mm.y; r4[i].z *= mm.z; r4[i].w *= mm.w;
+                            }
+                            st_f4(a.E_out + row * d_out + col, r4[i]);
                         }
-                        if (a.mess_mult) {
-                            const float4 mm = ld_f4(a.mess_mult + row * d_out + j);
-                            o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
-                        } else if (a.mess_p > 0.f) {
-                            const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)(row * d_out + j) >> 2);
-                            o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
-                        }
-                        st_f4(out + j, make_float4(o[0], o[1], o[2], o[3]));
                     }
                 }
             }
@@ -233,6 +253,455 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     }
 }
 
+
+// ====================================================================================================================
+// Backward of the same layer (row-local part), d_in = 64, as two kernels:
+//
+// dense_bwd_tc_kernel (per 128-row tile, persistent)
+//   gM   = (gE_next + normalize-backward(gH)) * dropout * LeakyReLU'       loader warps, CUDA cores; also -> global
+//   T    = gM · [W1 | W2]            [128 x 128], K = d_out                GEMM 1, K-major operands, 3xTF32
+//   gS   = T1 + T2*E,  gEl = T1 + T2*S                                      epilogue warps (TMEM -> per-warp
+//                                                                           transposition buffer -> coalesced I/O)
+//   gb2 += colsum(gM), gb1 += 2 colsum(gM)
+//
+// wgrad_tc_kernel (split over rows, 64 rows per pipeline stage, persistent)
+//   [gW1 | gW2]^T = [S+E | S*E]^T · gM   [128 x d_out], K = rows           GEMM 2, both operands MN-major
+//   (SWIZZLE_128B_BASE32B), accumulator resident in TMEM across the CTA's whole row range, flushed once with
+//   coalesced atomics.
+// gM is kept in two shared-memory buffers in the first kernel so the loaders run one tile ahead of the MMAs.
+// ====================================================================================================================
+constexpr int BW_STAGE_PITCH = 36;            // floats per staged row (32 + 4: keeps 16-byte alignment, no conflicts)
+
+struct BwdTcArgs {
+    const float* gE_next;
+    const int32_t* slot;
+    const float* gsum;
+    int64_t ld_gsum;
+    int col_off;
+    const float* E_out;
+    const float* S;
+    const float* E;
+    int64_t n_rows;
+    int d_in, d_out;
+    const float* W1;
+    const float* W2;
+    float slope;
+    const float* mess_mult;
+    float mess_p;
+    uint64_t seed;
+    const uint64_t* seed_dev;
+    int layer;
+    float* gS;
+    float* gEl;
+    float* gM;                // [n_rows, d_out] scratch, consumed by wgrad_tc_kernel
+    float* gb1;
+    float* gb2;
+    int n_tiles;
+};
+
+struct BwdBars {
+    uint64_t full_gm[2], empty_gm[2], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int d_in = 64;
+    const int d_out = a.d_out;
+    const int KBo = d_out / 32;                                           // 32-column blocks of gM
+    const int gm_buf = 2 * KBo * TC_A_BLOCK;                              // hi + lo of one gM buffer
+    uint8_t* GM = smem;                                                   // [2 buffers][hi | lo][KBo blocks]
+    uint8_t* BT_hi = GM + 2 * gm_buf;                                     // [n = 0..127][k = o], K blocks of 32 o
+    uint8_t* BT_lo = BT_hi + KBo * TC_A_BLOCK;
+    float* stage = reinterpret_cast<float*>(BT_lo + KBo * TC_A_BLOCK);    // [4 warps][32][BW_STAGE_PITCH]
+    BwdBars* bars = reinterpret_cast<BwdBars*>(stage + TC_EPI_WARPS * 32 * BW_STAGE_PITCH);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->full_gm[i], TC_LOAD_WARPS);
+            mbar_init(&bars->empty_gm[i], 1);
+            mbar_init(&bars->tmem_full[i], 1);
+            mbar_init(&bars->tmem_empty[i], TC_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // T x2 (128 columns each)
+    // BT[n][o] = W1[o][n] (n < 64), W2[o][n-64]; W1/W2 are [d_out, d_in] row-major
+    for (int i = tid; i < 128 * KBo * 8; i += TC_THREADS) {
+        const int c = i & 7, n = (i >> 3) & 127, kb = i >> 10;
+        const float* W = (n < d_in ? a.W1 : a.W2) + (n & 63);
+        const int o0 = kb * 32 + c * 4;
+        float4 w = make_float4(W[(int64_t)o0 * d_in], W[(int64_t)(o0 + 1) * d_in], W[(int64_t)(o0 + 2) * d_in],
+                               W[(int64_t)(o0 + 3) * d_in]);
+        float4 hi, lo;
+        split_tf32(w, hi, lo);
+        const uint32_t off = kb * TC_A_BLOCK + sw128_offset(n, c);
+        *reinterpret_cast<float4*>(BT_hi + off) = hi;
+        *reinterpret_cast<float4*>(BT_lo + off) = lo;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < TC_EPI_WARPS) {
+        // ======================= epilogue: gS / gEl ==============================================================
+        float* st = stage + warp * 32 * BW_STAGE_PITCH;
+        const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int buf = it & 1;
+            mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 128;
+            const int64_t row_base = (int64_t)tile * TC_ROWS + warp * 32;
+#pragma unroll 1
+            for (int c = 0; c < d_in / 32; ++c) {
+                float4 t1[8], t2[8];
+                float v[32];
+                tmem_ld_32x32(taddr + c * 32, v);                         // T1[row = lane][32c .. 32c+32)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_f4(st + lane * BW_STAGE_PITCH + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t1[i] = ld_f4(st + (i * 4 + rr) * BW_STAGE_PITCH + c4 * 4);
+                __syncwarp();
+                tmem_ld_32x32(taddr + d_in + c * 32, v);                  // T2
+                if (c == d_in / 32 - 1) {                                 // accumulator fully read
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_f4(st + lane * BW_STAGE_PITCH + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t2[i] = ld_f4(st + (i * 4 + rr) * BW_STAGE_PITCH + c4 * 4);
+                __syncwarp();
+#pragma unroll
+                for (int ib = 0; ib < 8; ib += 4) {                       // 4 rows at a time: loads first, then math + stores
+                    float4 e4[4], s4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t row = min(row_base + (ib + i) * 4 + rr, a.n_rows - 1);
+                        const int64_t o = row * d_in + c * 32 + c4 * 4;
+                        e4[i] = ld_f4(a.E + o);
+                        s4[i] = ld_f4(a.S + o);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t row = row_base + (ib + i) * 4 + rr;
+                        if (row < a.n_rows) {
+                            const int64_t o = row * d_in + c * 32 + c4 * 4;
+                            const float4 x1 = t1[ib + i], x2 = t2[ib + i];
+                            st_f4(a.gS + o, make_float4(fmaf(x2.x, e4[i].x, x1.x), fmaf(x2.y, e4[i].y, x1.y),
+                                                        fmaf(x2.z, e4[i].z, x1.z), fmaf(x2.w, e4[i].w, x1.w)));
+                            st_f4(a.gEl + o, make_float4(fmaf(x2.x, s4[i].x, x1.x), fmaf(x2.y, s4[i].y, x1.y),
+                                                         fmaf(x2.z, s4[i].z, x1.z), fmaf(x2.w, s4[i].w, x1.w)));
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ======================= MMA issuer =====================================================================
+        const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, 2 * d_in, 0, 0);
+        for (int it = 0; it < n_my; ++it) {
+            const int buf = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(&bars->full_gm[buf], ph);
+            mbar_wait(&bars->tmem_empty[buf], ph ^ 1);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t tmem_t = tmem_base + buf * 128;
+                const uint32_t gm_hi = smem_u32(GM + buf * gm_buf), gm_lo = gm_hi + KBo * TC_A_BLOCK;
+                uint32_t acc1 = 0;
+                for (int kb = 0; kb < KBo; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = kb * TC_A_BLOCK + k * 32;
+                        const uint64_t dah = umma_desc_sw128(gm_hi + off, 16, 1024);
+                        const uint64_t dal = umma_desc_sw128(gm_lo + off, 16, 1024);
+                        const uint64_t dbh = umma_desc_sw128(smem_u32(BT_hi) + off, 16, 1024);
+                        const uint64_t dbl = umma_desc_sw128(smem_u32(BT_lo) + off, 16, 1024);
+                        umma_tf32(tmem_t, dah, dbh, idesc1, acc1);
+                        umma_tf32(tmem_t, dal, dbh, idesc1, 1);
+                        umma_tf32(tmem_t, dah, dbl, idesc1, 1);
+                        acc1 = 1;
+                    }
+                }
+                umma_commit(&bars->tmem_full[buf]);
+                umma_commit(&bars->empty_gm[buf]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ======================= loaders: gM rows ====================================================================
+        // half a warp per row: lane owns the four columns 4*(lane & 15) .. +3 (one Philox call = exactly its four
+        // dropout decisions, 128-bit loads and shared-memory stores); 8 row pairs in flight per warp
+        const int lw = warp - (TC_EPI_WARPS + 1);                         // 0 .. 7
+        const int hl = lane & 15, hsel = lane >> 4;
+        const int c0 = hl * 4;
+        const bool col_ok = c0 < d_out;
+        const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int PAIRS = TC_ROWS / (2 * TC_LOAD_WARPS);              // row pairs per warp per tile
+        constexpr int PB = 4;                                             // row pairs in flight
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int buf = it & 1;
+            const int64_t row0 = (int64_t)tile * TC_ROWS;
+            uint8_t* GM_hi = GM + buf * gm_buf;
+            uint8_t* GM_lo = GM_hi + KBo * TC_A_BLOCK;
+            mbar_wait(&bars->empty_gm[buf], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+            for (int jb = 0; jb < PAIRS; jb += PB) {
+            float4 e[PB], gn[PB];
+            int sl[PB];
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const int64_t row = row0 + 2 * (lw + TC_LOAD_WARPS * (jb + j)) + hsel;
+                const bool ok = row < a.n_rows && col_ok;
+                e[j] = gn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sl[j] = -1;
+                if (ok) {
+                    e[j] = ld_f4(a.E_out + row * d_out + c0);
+                    if (a.gE_next) gn[j] = ld_f4(a.gE_next + row * d_out + c0);
+                    if (a.slot) sl[j] = a.slot[row];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const int r = 2 * (lw + TC_LOAD_WARPS * (jb + j)) + hsel;
+                const int64_t row = row0 + r;
+                const bool in = row < a.n_rows;
+                float4 g = gn[j];
+                const int s = sl[j];
+                if (__any_sync(FULL_MASK, s >= 0)) {                      // rows of the batch only (~4 % of all rows)
+                    float4 gh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s >= 0) {                                         // col_off need not be a multiple of 4 (width 65 first)
+                        const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + c0;
+                        gh = make_float4(gp[0], gp[1], gp[2], gp[3]);
+                    }
+                    float nrm2 = e[j].x * e[j].x + e[j].y * e[j].y + e[j].z * e[j].z + e[j].w * e[j].w;
+                    float dot = e[j].x * gh.x + e[j].y * gh.y + e[j].z * gh.z + e[j].w * gh.w;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) {                     // reduce over the 16 lanes of the row
+                        nrm2 += __shfl_xor_sync(FULL_MASK, nrm2, o);
+                        dot += __shfl_xor_sync(FULL_MASK, dot, o);
+                    }
+                    if (s >= 0) {
+                        const float n = fmaxf(sqrtf(nrm2), 1e-12f);       // F.normalize eps, NGCF.py:144
+                        const float hd = dot / n;                         // H . gH
+                        g.x += (gh.x - (e[j].x / n) * hd) / n;            // normalize backward
+                        g.y += (gh.y - (e[j].y / n) * hd) / n;
+                        g.z += (gh.z - (e[j].z / n) * hd) / n;
+                        g.w += (gh.w - (e[j].w / n) * hd) / n;
+                    }
+                }
+                if (col_ok) {
+                    float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (in) {
+                        if (a.mess_mult) mult = ld_f4(a.mess_mult + row * d_out + c0);
+                        else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)(row * d_out + c0) >> 2);
+                    }
+                    g.x *= mult.x * (e[j].x > 0.f ? 1.f : a.slope);       // dropout + LeakyReLU backward
+                    g.y *= mult.y * (e[j].y > 0.f ? 1.f : a.slope);
+                    g.z *= mult.z * (e[j].z > 0.f ? 1.f : a.slope);
+                    g.w *= mult.w * (e[j].w > 0.f ? 1.f : a.slope);
+                    if (in) st_f4(a.gM + row * d_out + c0, g);
+                    else g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
+                    float4 hi, lo;
+                    split_tf32(g, hi, lo);
+                    const uint32_t off = (hl >> 3) * TC_A_BLOCK + sw128_offset(r, hl & 7);
+                    *reinterpret_cast<float4*>(GM_hi + off) = hi;
+                    *reinterpret_cast<float4*>(GM_lo + off) = lo;
+                }
+            }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->full_gm[buf]);
+        }
+        colsum.x += __shfl_xor_sync(FULL_MASK, colsum.x, 16);
+        colsum.y += __shfl_xor_sync(FULL_MASK, colsum.y, 16);
+        colsum.z += __shfl_xor_sync(FULL_MASK, colsum.z, 16);
+        colsum.w += __shfl_xor_sync(FULL_MASK, colsum.w, 16);
+        if (hsel == 0 && col_ok) {
+            const float cs[4] = {colsum.x, colsum.y, colsum.z, colsum.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                atomicAdd(a.gb2 + c0 + t, cs[t]);
+                atomicAdd(a.gb1 + c0 + t, 2.0f * cs[t]);                  // w1_list[i] is applied twice (NGCF.py:131,133)
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// weight gradients: D[j][o] = sum_rows X[row][j] * gM[row][o],  X = [S+E | S*E]  (gW1[o][j] = D[j][o], gW2[o][j] = D[64+j][o])
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 64;                   // rows (= GEMM K) per pipeline stage
+constexpr int WG_BLOCK = WG_ROWS * 128;       // bytes of one 32-wide M/N group of a stage (hi or lo)
+
+struct WgradArgs {
+    const float* S;
+    const float* E;
+    const float* gM;
+    int64_t n_rows;
+    int d_out;
+    float* gW1;
+    float* gW2;
+    int n_chunks;
+};
+
+struct WgBars {
+    uint64_t full[2], empty[2], d_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int d_in = 64;
+    const int d_out = a.d_out;
+    const int KBo = d_out / 32;
+    const int stage_bytes = (8 + 2 * KBo) * WG_BLOCK;                     // X hi (4) + X lo (4) + gM hi + gM lo
+    WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * stage_bytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->full[i], TC_LOAD_WARPS);
+            mbar_init(&bars->empty[i], 1);
+        }
+        mbar_init(&bars->d_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 64);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = bars->tmem_base;
+    const int n_my = (a.n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < TC_EPI_WARPS) {
+        // ======================= final flush =====================================================================
+        mbar_wait(&bars->d_full, 0);
+        tc_fence_after_sync();
+        const int m = warp * 32 + lane;                                   // TMEM lane = column j of [W1 | W2]
+        float* gw = (m < d_in ? a.gW1 : a.gW2) + (m & 63);
+        for (int c = 0; c < KBo; ++c) {
+            float v[32];
+            tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(gw + (int64_t)(c * 32 + j) * d_in, v[j]);
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ======================= MMA issuer =====================================================================
+        const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 1, 1);
+        constexpr uint32_t layout = UMMA_SW128_BASE32B, sbo = 512;       // 4-row K atoms of 512 bytes
+        uint32_t acc = 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int sgi = it & 1;
+            mbar_wait(&bars->full[sgi], (it >> 1) & 1);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t x_hi = smem_u32(smem + sgi * stage_bytes), x_lo = x_hi + 4 * WG_BLOCK;
+                const uint32_t g_hi = x_lo + 4 * WG_BLOCK, g_lo = g_hi + KBo * WG_BLOCK;
+#pragma unroll
+                for (int kk = 0; kk < WG_ROWS / 8; ++kk) {                // K = 8 rows per MMA = two 4-row atoms
+                    const uint32_t off = kk * 1024;
+                    const uint64_t dah = umma_desc(x_hi + off, WG_BLOCK, sbo, layout);
+                    const uint64_t dal = umma_desc(x_lo + off, WG_BLOCK, sbo, layout);
+                    const uint64_t dbh = umma_desc(g_hi + off, WG_BLOCK, sbo, layout);
+                    const uint64_t dbl = umma_desc(g_lo + off, WG_BLOCK, sbo, layout);
+                    umma_tf32(tmem_d, dah, dbh, idesc, acc);
+                    umma_tf32(tmem_d, dal, dbh, idesc, 1);
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                    acc = 1;
+                }
+                umma_commit(&bars->empty[sgi]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(&bars->d_full);
+        __syncwarp();
+    } else {
+        // ======================= loaders =========================================================================
+        const int lt = tid - (TC_EPI_WARPS + 1) * 32;                     // 0 .. 255
+        constexpr int LT = TC_LOAD_WARPS * 32;
+        const int gq = d_out / 4;                                         // float4 per gM row
+        for (int it = 0; it < n_my; ++it) {
+            const int chunk = blockIdx.x + it * gridDim.x;
+            const int sgi = it & 1;
+            const int64_t row0 = (int64_t)chunk * WG_ROWS;
+            uint8_t* x_hi = smem + sgi * stage_bytes;
+            uint8_t* x_lo = x_hi + 4 * WG_BLOCK;
+            uint8_t* g_hi = x_lo + 4 * WG_BLOCK;
+            uint8_t* g_lo = g_hi + KBo * WG_BLOCK;
+            float4 s4[4], e4[4], g4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                                 // 64 rows x 16 float4 = 4 per thread
+                const int idx = q * LT + lt, r = idx >> 4, c = idx & 15;
+                const int64_t row = row0 + r;
+                s4[q] = e4[q] = g4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < a.n_rows) {
+                    s4[q] = ld_f4(a.S + row * d_in + c * 4);
+                    e4[q] = ld_f4(a.E + row * d_in + c * 4);
+                    if (c < gq) g4[q] = ld_f4(a.gM + row * d_out + c * 4);
+                }
+            }
+            mbar_wait(&bars->empty[sgi], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = q * LT + lt, r = idx >> 4, c = idx & 15;
+                const uint32_t off = (c >> 3) * WG_BLOCK + sw128b32_offset(r, c & 7);
+                const float4 x1 = make_float4(s4[q].x + e4[q].x, s4[q].y + e4[q].y, s4[q].z + e4[q].z, s4[q].w + e4[q].w);
+                const float4 x2 = make_float4(s4[q].x * e4[q].x, s4[q].y * e4[q].y, s4[q].z * e4[q].z, s4[q].w * e4[q].w);
+                float4 hi, lo;
+                split_tf32(x1, hi, lo);
+                *reinterpret_cast<float4*>(x_hi + off) = hi;
+                *reinterpret_cast<float4*>(x_lo + off) = lo;
+                split_tf32(x2, hi, lo);
+                *reinterpret_cast<float4*>(x_hi + 2 * WG_BLOCK + off) = hi;
+                *reinterpret_cast<float4*>(x_lo + 2 * WG_BLOCK + off) = lo;
+                if (c < gq) {
+                    split_tf32(g4[q], hi, lo);
+                    *reinterpret_cast<float4*>(g_hi + off) = hi;
+                    *reinterpret_cast<float4*>(g_lo + off) = lo;
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->full[sgi]);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_d, 64);
+    }
+}
+
 }  // namespace
 
 bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out) {
@@ -245,7 +714,8 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     FwdTcArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
                 (int)ceil_div64(n_rows, TC_ROWS)};
     const int KB = 2 * d_in / 32;
-    const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) + sizeof(Bars);
+    const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) +
+                        TC_EPI_WARPS * 32 * FW_STAGE_PITCH * sizeof(float) + sizeof(Bars);
     static bool attr_set = false;
     if (!attr_set) {
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -254,5 +724,35 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
     dense_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
     NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
+    return NGCF_OK;
+}
+
+bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out) { return d_in == 64 && (d_out == 32 || d_out == 64); }
+
+int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
+                      const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
+                      const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
+                      uint64_t seed, const uint64_t* seed_dev, int layer, float* gS, float* gEl, float* gW1,
+                      float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st) {
+    BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
+                mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS)};
+    const int KBo = d_out / 32;
+    const size_t smem = 1024 + (size_t)6 * KBo * TC_A_BLOCK + TC_EPI_WARPS * 32 * BW_STAGE_PITCH * sizeof(float) +
+                        sizeof(BwdBars);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NGCF_CUDA(cudaFuncSetAttribute(dense_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
+    dense_bwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
+
+    WgradArgs w{S, E, gM_scratch, n_rows, d_out, gW1, gW2, (int)ceil_div64(n_rows, WG_ROWS)};
+    const size_t smem2 = 1024 + (size_t)2 * (8 + 2 * KBo) * WG_BLOCK + sizeof(WgBars);
+    const int grid2 = (int)min((int64_t)w.n_chunks, (int64_t)ngcf_num_sms());
+    wgrad_tc_kernel<<<grid2, TC_THREADS, smem2, st>>>(w);
+    NGCF_LAUNCH_OK("wgrad_tc_kernel");
     return NGCF_OK;
 }

@@ -3,7 +3,7 @@
 //
 // Numerics: the reference computes the W1/W2 products in fp32 (cuBLAS SGEMM / MKL).  A single TF32 product has a
 // 2^-11 relative rounding error per operand, which breaks the 1e-4 parity bound, so every product here is the
-// error-compensated "3xTF32" split  a·b ~= a_hi·b_hi + a_lo·b_hi + a_hi·b_lo  with a_hi = a truncated to TF32 and
+// error-compensated "3xTF32" split  a·b ~= a_hi·b_hi + a_lo·b_hi + a_hi·b_lo  with a_hi = a rounded to TF32 and
 // a_lo = a - a_hi (exact in fp32): three tcgen05.mma per K step into the same fp32 TMEM accumulator.
 #pragma once
 #include "common.cuh"
@@ -60,14 +60,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 //   between 8-row groups.
 //   MN-major operand (rows of 128 bytes = 32 TF32 along M/N; 8 K-rows per 1024-byte atom): LBO = bytes between
 //   32-element M/N groups, SBO = bytes between 8-row K groups.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   32-bit MN-major operands exist in ONE layout only, SWIZZLE_128B_BASE32B = 1 (CUTLASS sm100_common.inl: "for
+//   mn-major tf32 operands, SW128_32B is the only available smem layout"): rows of 128 bytes along M/N, 4 K-rows
+//   per 512-byte atom, the 32-byte chunk index XORed with the K-row index inside the atom (Swizzle<2,5,2> on byte
+//   addresses); LBO = bytes between 32-element M/N groups, SBO = bytes between 4-row K groups.
+constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_desc(saddr, lbo_bytes, sbo_bytes, UMMA_SW128);
 }
 
 // Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6),
@@ -114,9 +122,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ---- 3xTF32 operand split and the swizzled operand layouts -----------------------------------------------------------
+// hi = x rounded to nearest TF32, lo = the exactly representable remainder rounded to TF32 as well, so the tensor
+// core's operand truncation changes neither.  Round-to-nearest keeps the split errors zero-mean: with a truncating
+// split they all share the sign of x and add up coherently over the ~10^5-row weight-gradient sums.
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
 }
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
     split_tf32(x.x, hi.x, lo.x);
@@ -129,6 +145,11 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 // rows are 128 bytes: 8-row atoms of 1024 bytes, chunk index XORed with the row index inside the atom
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) {
     return (r >> 3) * 1024u + (r & 7u) * 128u + ((c ^ (r & 7u)) << 4);
+}
+
+// byte offset of the 16-byte chunk c (0..7) of K-row r inside an MN-major SWIZZLE_128B_BASE32B block (128-byte rows)
+__device__ __forceinline__ uint32_t sw128b32_offset(uint32_t r, uint32_t c) {
+    return r * 128u + ((((c >> 1) ^ (r & 3u)) << 5) | ((c & 1u) << 4));
 }
 
 }  // namespace tc
