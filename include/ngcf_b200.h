@@ -114,12 +114,14 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
  *               layer `layer` iff its Philox draws keyed on (seed + *seed_dev, r, c) for layers 0..layer are all
  *               >= drop_p (cumulative over layers, unscaled — the reference's semantics).  `transposed` != 0 says
  *               this CSR holds L^T, so both directions drop the same entries of L.
- *               seed_dev: optional device uint64 added to seed (graph-replay safe). */
+ *               seed_dev: optional device uint64 added to seed (graph-replay safe).
+ *   row_offset: global index of row 0 of this CSR.  RNG keys use global coordinates, so a row shard (rows
+ *               [row_offset, row_offset + n_rows) of L, all columns) draws exactly the single-GPU decisions. */
 int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
               const float* addend, int64_t ld_add,
               const int32_t* slot, const float* gsum, int64_t ld_gsum,
               float* hub_partial,
-              float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed,
+              float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
               float* Y, int64_t ldy, void* stream);
 
 /* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
@@ -130,11 +132,12 @@ int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const f
                       void* stream);
 /* E_out = Dropout(LeakyReLU_slope((S+E)·W1^T + (S*E)·W2^T + bias_eff)).
  *   mess_mult : optional [n_rows, d_out] multipliers standing in for nn.Dropout (mask injection);
- *   mess_p>0  : device-RNG inverted dropout keyed on (seed + *seed_dev, layer, element); ignored with mess_mult. */
+ *   mess_p>0  : device-RNG inverted dropout keyed on (seed + *seed_dev, layer, element); ignored with mess_mult.
+ *   row_offset: global index of row 0 (RNG keys only; 0 unless the rows are a shard of the full table). */
 int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* wcat, const float* bias_eff, float slope,
                    const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                   float* E_out, void* stream);
+                   int64_t row_offset, float* E_out, void* stream);
 
 /* ---- output rows: NGCF.py:144-156 -------------------------------------------------------------------
  * out[b,:] = [ E0[r,:] | E1[r,:]/max(||E1[r,:]||,1e-12) | ... | EK[r,:]/max(...) ],  r = rows[b]+row_offset
@@ -179,8 +182,8 @@ int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,
                    const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                   float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch,
-                   void* stream);
+                   int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
+                   float* gM_scratch, void* stream);
 
 /* ---- scoring: demo.py:234-235, experiment.py:93,104,109 ----------------------------------------------
  * scores = U·I^T without materialising them; per user row the k largest (descending; ties by lower item

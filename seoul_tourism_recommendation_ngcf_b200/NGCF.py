@@ -13,8 +13,11 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import torch.distributed as dist
+
 from . import _lib
 from .plan import LaplacianPlan, spmm
+from .sharded import RowShards, all_gather_rows
 
 LEAKY_SLOPE = 0.2   # NGCF.py:140
 
@@ -30,7 +33,12 @@ class _Ctx:
 
 
 class _Propagate(torch.autograd.Function):
-    """K-layer propagation + output-row gather (NGCF.py:120-156) and its hand-written backward."""
+    """K-layer propagation + output-row gather (NGCF.py:120-156) and its hand-written backward.
+
+    With ``mod._shard`` set (row-sharded multi-GPU run, sharded.py) every per-layer tensor below holds this rank's
+    row block only, ``st.E[k]`` is the all-gathered full ``[N_pad, d_k]`` layer input, and the collectives are: one
+    all-gather per layer in each direction, one all-gather of the table gradient and one all-reduce of the W/b
+    gradients.  Without it ``st.E[k]`` is simply E_k and nothing is communicated."""
 
     @staticmethod
     def forward(ctx, mod, st: _Ctx, n_sets, user_w, item_w, *wb):
@@ -38,25 +46,36 @@ class _Propagate(torch.autograd.Function):
         K = mod.n_layer
         W1, b1, W2, b2 = wb[0:K], wb[K:2 * K], wb[2 * K:3 * K], wb[3 * K:4 * K]
         dev = user_w.device
+        sh = mod._shard
         N = mod.n_user + mod.n_item
-        E = mod._packed_table()                                        # [N, d0] = cat(user, item), NGCF.py:120
-        st.E, st.S, st.W1, st.W2 = [E], [], list(W1), list(W2)
+        r0, nloc, nv = (sh.r0, sh.rows, sh.valid) if sh is not None else (0, N, N)
+        X0 = mod._packed_table()                                       # [N(_pad), d0] = cat(user, item), NGCF.py:120
+        st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
-            S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, layer=k)   # NGCF.py:124-130
+            S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, layer=k, row_offset=r0)  # NGCF.py:124-130
             wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
             bias = torch.empty(d_out, dtype=torch.float32, device=dev)
             _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
                                              d_in, d_out, wcat.data_ptr(), bias.data_ptr(), _stream()), "pack_weights")
-            En = torch.empty(N, d_out, dtype=torch.float32, device=dev)
+            if sh is None:
+                Xn = En = torch.empty(N, d_out, dtype=torch.float32, device=dev)
+            else:
+                Xn = torch.empty(sh.N_pad, d_out, dtype=torch.float32, device=dev)
+                En = torch.zeros(nloc, d_out, dtype=torch.float32, device=dev) if nv < nloc else \
+                    torch.empty(nloc, d_out, dtype=torch.float32, device=dev)
             mm = st.mess_mult[k] if st.mess_mult is not None else None
-            _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), st.E[k].data_ptr(), N, d_in, d_out, wcat.data_ptr(),
-                                          bias.data_ptr(), LEAKY_SLOPE, _lib.ptr(mm), float(st.mess_p[k]),
-                                          st.seed, None, k, En.data_ptr(), _stream()), "dense_fwd")   # NGCF.py:131-142
+            E_loc = st.E[k][r0:r0 + nloc]
+            _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E_loc.data_ptr(), nv, d_in, d_out, wcat.data_ptr(),
+                                          bias.data_ptr(), LEAKY_SLOPE, _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
+                                          float(st.mess_p[k]), st.seed, None, k, r0, En.data_ptr(), _stream()),
+                       "dense_fwd")                                                          # NGCF.py:131-142
+            if sh is not None:
+                all_gather_rows(Xn, En, mod._group)                    # every rank needs all of E_{k+1}
             st.S.append(S)
-            st.E.append(En)
+            st.E.append(Xn)
         D = sum(st.dims)
         outs = []
         layers, dims = _lib.ptr_array(st.E), _lib.int_array(st.dims)
@@ -75,17 +94,20 @@ class _Propagate(torch.autograd.Function):
         st, mod, n_sets = ctx.st, ctx.mod, ctx.n_sets
         K, dims = mod.n_layer, st.dims
         dev = st.E[0].device
+        sh = mod._shard
         N = mod.n_user + mod.n_item
+        r0, nloc, nv, N_all = (sh.r0, sh.rows, sh.valid, sh.N_pad) if sh is not None else (0, N, N, N)
         D = sum(dims)
         g = [(go.contiguous() if go is not None else torch.zeros(st.rows[j].numel(), D, device=dev))
              for j, go in enumerate(gouts)]
         batch = [r.numel() for r in st.rows[:n_sets]]
         rows_h, offs_h = _lib.ptr_array(st.rows[:n_sets]), _lib.i64_array(st.offsets[:n_sets])
         g_h, batch_h = _lib.ptr_array(g), _lib.i64_array(batch)
-        slot = mod._slot_map(N, dev)
+        slot = mod._slot_map(N_all, dev)
         gsum = torch.empty(sum(batch), D, dtype=torch.float32, device=dev)
         _lib.check(lib.ngcf_rowgrad_scatter(rows_h, offs_h, g_h, batch_h, n_sets, D, slot.data_ptr(),
                                             gsum.data_ptr(), _stream()), "rowgrad_scatter")
+        slot_loc = slot[r0:r0 + nloc]
         sizes = [dims[k + 1] * dims[k] for k in range(K)]
         flat = torch.zeros(2 * sum(sizes) + 2 * sum(dims[1:]), dtype=torch.float32, device=dev)
         gW1, gW2, gb1, gb2, o = [], [], [], [], 0
@@ -99,29 +121,42 @@ class _Propagate(torch.autograd.Function):
         side = st.plan.side(True, st.vals_b is not None)
         gE_next = None
         col_off = D
-        gM_scratch = torch.empty(N, max(dims[1:]), dtype=torch.float32, device=dev)
+        gM_scratch = torch.empty(nloc, max(dims[1:]), dtype=torch.float32, device=dev)
         for k in range(K - 1, -1, -1):
             d_in, d_out = dims[k], dims[k + 1]
             col_off -= d_out
-            gS = torch.empty(N, d_in, dtype=torch.float32, device=dev)
-            gEl = torch.empty(N, d_in, dtype=torch.float32, device=dev)
+            gS = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
+            gEl = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
             mm = st.mess_mult[k] if st.mess_mult is not None else None
-            _lib.check(lib.ngcf_dense_bwd(_lib.ptr(gE_next), slot.data_ptr(), gsum.data_ptr(), D, col_off,
-                                          st.E[k + 1].data_ptr(), st.S[k].data_ptr(), st.E[k].data_ptr(), N, d_in, d_out,
-                                          st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE, _lib.ptr(mm),
-                                          float(st.mess_p[k]), st.seed, None, k, gS.data_ptr(), gEl.data_ptr(),
+            _lib.check(lib.ngcf_dense_bwd(_lib.ptr(gE_next), slot_loc.data_ptr(), gsum.data_ptr(), D, col_off,
+                                          st.E[k + 1][r0:r0 + nloc].data_ptr(), st.S[k].data_ptr(),
+                                          st.E[k][r0:r0 + nloc].data_ptr(), nv, d_in, d_out,
+                                          st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE,
+                                          _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
+                                          float(st.mess_p[k]), st.seed, None, k, r0, gS.data_ptr(), gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           gM_scratch.data_ptr(), _stream()), "dense_bwd")
+            if sh is not None:                                        # L^T gS needs every rank's rows of gS
+                gS_all = torch.empty(N_all, d_in, dtype=torch.float32, device=dev)
+                all_gather_rows(gS_all, gS, mod._group)
+            else:
+                gS_all = gS
             vals = st.vals_b[k] if st.vals_b is not None else None
             last = (k == 0)
-            gE_next = spmm(side, vals, gS, d_in, addend=gEl, slot=slot if last else None, gsum=gsum if last else None,
-                           drop_p=st.drop_p, seed=st.seed, layer=k,
-                           transposed=True)                           # gE_k = gEl + L^T gS (+ layer-0 row grads)
+            gE_next = spmm(side, vals, gS_all, d_in, addend=gEl, slot=slot_loc if last else None,
+                           gsum=gsum if last else None, drop_p=st.drop_p, seed=st.seed, layer=k,
+                           transposed=True, row_offset=r0)            # gE_k = gEl + L^T gS (+ layer-0 row grads)
             if mod._trace is not None:                                # debugging aid: per-layer backward tensors
                 mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
                    "rowgrad_reset")
-        gU, gI = gE_next[:mod.n_user], gE_next[mod.n_user:]
+        if sh is not None:
+            gE0 = torch.empty(N_all, dims[0], dtype=torch.float32, device=dev)
+            all_gather_rows(gE0, gE_next, mod._group)                 # tables are replicated: full gradient everywhere
+            dist.all_reduce(flat, group=mod._group)                   # W/b gradients: sum of the row blocks
+        else:
+            gE0 = gE_next
+        gU, gI = gE0[:mod.n_user], gE0[mod.n_user:N]
         return (None, None, None, gU, gI, *gW1, *gb1, *gW2, *gb2)
 
 
@@ -172,6 +207,8 @@ class NGCF(nn.Module):
         self._winner = None
         self._last = None
         self._all_E = None
+        self._shard = None       # sharded.RowShards once shard() was called
+        self._group = None
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
@@ -199,6 +236,22 @@ class NGCF(nn.Module):
         self.node_dropout_list = nn.Sequential(*nd)
         self.mess_dropout_list = nn.Sequential(*md)
 
+    # ---- multi-GPU ------------------------------------------------------------------------------------
+    def shard(self, group=None):
+        """Row-partitions the propagation over the ranks of ``group`` (default process group): this rank then
+        computes rows [rank*rows, (rank+1)*rows) of every layer (sharded.py).  Parameters stay replicated; every
+        rank must call forward with the same batch and the same torch CPU RNG state (the per-step Philox key is drawn
+        from it).  Explicit-mask node dropout (rng="reference") is not available in this mode."""
+        if not dist.is_initialized():
+            raise RuntimeError("NGCF.shard() needs an initialised torch.distributed process group")
+        if self.rng != "device":
+            raise ValueError("row-sharded runs need rng='device' (masks are keyed on global coordinates in-kernel)")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self._shard = RowShards(self.n_user + self.n_item, world, rank)
+        self._group = group
+        self._plans, self._table, self._slot = {}, None, None
+        return self
+
     # ---- internal buffers ---------------------------------------------------------------------------
     def _packed_table(self) -> torch.Tensor:
         """[N, d] view over user_embedding.weight and item_embedding.weight laid out back to back, so that
@@ -210,13 +263,14 @@ class NGCF(nn.Module):
                     u.data_ptr() + self.n_user * d * 4 == i.data_ptr() and
                     getattr(self, "_table", None) is not None and self._table.data_ptr() == u.data_ptr())
         if not adjacent:
-            table = torch.empty(self.n_user + self.n_item, d, dtype=torch.float32, device=u.device)
+            n_rows = self._shard.N_pad if self._shard is not None else self.n_user + self.n_item
+            table = torch.zeros(n_rows, d, dtype=torch.float32, device=u.device)   # rows past N: shard padding
             table[:self.n_user].copy_(u.data)
             table[self.n_user:].copy_(i.data)
             u.data = table[:self.n_user]
             i.data = table[self.n_user:]
             self._table = table
-        return self._table
+        return self._table if self._shard is None else self._table   # [N_pad, d] when sharded (pad rows are zero)
 
     def _slot_map(self, N, dev):
         if self._slot is None or self._slot.device != dev or self._slot.numel() != N:
@@ -227,7 +281,7 @@ class NGCF(nn.Module):
         L = self.lap_list[year_idx]
         p = self._plans.get(year_idx)
         if p is None or p.src is not L or p.coo_val.device != dev:
-            p = LaplacianPlan(L, dev)
+            p = LaplacianPlan(L, dev, shard=self._shard)
             self._plans[year_idx] = p
         return p
 
@@ -273,6 +327,8 @@ class NGCF(nn.Module):
 
         st = _Ctx()
         st.plan = plan = self._plan(year_idx, dev)
+        if self._shard is not None and "edge_keep" in (self._inject or {}):
+            raise ValueError("explicit edge masks are not supported in row-sharded mode")
         if plan.N != N:
             raise ValueError(f"Laplacian is {plan.N}x{plan.N} but n_user+n_item = {N}")
         st.dims = [self.emb_size] + self.weight_size

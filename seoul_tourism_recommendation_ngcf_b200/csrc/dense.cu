@@ -47,6 +47,7 @@ struct FwdArgs {
     float* E_out;
     int KP;        // padded K = round_up(2*d_in, 4)
     int n_tiles;
+    int64_t row_off;   // global index of local row 0 (RNG keys only)
 };
 
 template <int NCG>
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(FWD_THREADS) dense_fwd_kernel(FwdArgs a) {
                     const int col = c0 + c;
                     if (col < d_out) {
                         if (a.mess_mult) v *= a.mess_mult[row * d_out + col];
-                        else if (a.mess_p > 0.f) v *= mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)(row * d_out + col));
+                        else if (a.mess_p > 0.f) v *= mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + col));
                     }
                     o[c] = v;
                 }
@@ -196,6 +197,7 @@ struct BwdArgs {
     float* gW2;
     float* gb2;
     int n_tiles;
+    int64_t row_off;
 };
 
 template <int DC, int R, int THREADS>
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(THREADS) dense_bwd_kernel(BwdArgs a) {
                     if (s >= 0) g += (gh[q] - (e[q] / n) * dot) / n;     // normalize backward
                     float mult = 1.f;
                     if (a.mess_mult) mult = a.mess_mult[row * d_out + c];
-                    else if (a.mess_p > 0.f) mult = mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)(row * d_out + c));
+                    else if (a.mess_p > 0.f) mult = mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c));
                     g *= mult * (e[q] > 0.f ? 1.f : a.slope);            // dropout + LeakyReLU backward
                 }
                 gm[q] = g;
@@ -428,14 +430,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out);
 int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
                       const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
-                      const uint64_t* seed_dev, int layer, float* E_out, cudaStream_t st);
+                      const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, cudaStream_t st);
 
 bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out);
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
-                      uint64_t seed, const uint64_t* seed_dev, int layer, float* gS, float* gEl, float* gW1,
-                      float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st);
+                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
+                      float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st);
 
 // NGCF_B200_DENSE=ffma forces the exact-fp32 FFMA kernels (A/B comparisons); default: tensor cores where eligible
 bool ngcf_use_tensor_cores() {
@@ -455,7 +457,7 @@ extern "C" int ngcf_pack_weights(const float* W1, const float* b1, const float* 
 
 extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
                               const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
-                              const uint64_t* seed_dev, int layer, float* E_out, void* stream) {
+                              const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, void* stream) {
     NGCF_REQUIRE(S && E && wcat && bias_eff && E_out, "dense_fwd: null pointer");
     NGCF_REQUIRE(d_in > 0 && d_in <= NGCF_MAX_WIDTH && d_out > 0 && d_out <= NGCF_MAX_WIDTH,
                  "dense_fwd: widths %d -> %d not in [1,%d]", d_in, d_out, NGCF_MAX_WIDTH);
@@ -465,9 +467,9 @@ extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, in
     if (ngcf_use_tensor_cores() && ngcf_dense_fwd_tc_eligible(d_in, d_out) && aligned16(S) && aligned16(E) &&
         aligned16(E_out) && (!mess_mult || aligned16(mess_mult)))
         return ngcf_dense_fwd_tc(S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev,
-                                 layer, E_out, as_stream(stream));
+                                 layer, row_offset, E_out, as_stream(stream));
     FwdArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
-              (2 * d_in + 3) & ~3, (int)ceil_div64(n_rows, FWD_R)};
+              (2 * d_in + 3) & ~3, (int)ceil_div64(n_rows, FWD_R), row_offset};
     const int ncg = d_out <= 64 ? 1 : 2;
     const size_t smem = sizeof(float) * ((size_t)a.KP * 64 * ncg + (size_t)FWD_R * (a.KP + 4) + 64 * ncg);
     const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
@@ -488,8 +490,8 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
                               int col_off, const float* E_out, const float* S, const float* E, int64_t n_rows,
                               int d_in, int d_out, const float* W1, const float* W2, float slope,
                               const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                              float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch,
-                              void* stream) {
+                              int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
+                              float* gM_scratch, void* stream) {
     NGCF_REQUIRE(E_out && S && E && W1 && W2 && gS && gEl && gW1 && gb1 && gW2 && gb2, "dense_bwd: null pointer");
     NGCF_REQUIRE(!slot || gsum, "dense_bwd: slot given without gsum");
     NGCF_REQUIRE(d_in > 0 && d_in <= NGCF_MAX_WIDTH && d_out > 0 && d_out <= NGCF_MAX_WIDTH,
@@ -500,10 +502,10 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
     if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out) && aligned16(S) &&
         aligned16(E) && aligned16(gS) && aligned16(gEl) && aligned16(gM_scratch))
         return ngcf_dense_bwd_tc(gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2,
-                                 slope, mess_mult, mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2,
-                                 gM_scratch, as_stream(stream));
+                                 slope, mess_mult, mess_p, seed, seed_dev, layer, row_offset, gS, gEl, gW1, gb1, gW2,
+                                 gb2, gM_scratch, as_stream(stream));
     BwdArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-              mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0};
+              mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0, row_offset};
     int rc;
     if (d_in <= 64 && d_out <= 64) {
         constexpr int DC = 64, R = 64, T = 256;

@@ -42,6 +42,7 @@ struct FwdTcArgs {
     int layer;
     float* E_out;
     int n_tiles;
+    int64_t row_off;          // global index of local row 0 (RNG keys only)
 };
 
 struct Bars {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                         o[t] = m > 0.f ? m : a.slope * m;                               // LeakyReLU, NGCF.py:140
                     }
                     if (!a.mess_mult && a.mess_p > 0.f) {
-                        const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)(my_row * d_out + c * 32 + j) >> 2);
+                        const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
                         o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
                     }
                     st_f4(st + lane * FW_STAGE_PITCH + j, make_float4(o[0], o[1], o[2], o[3]));
@@ -297,6 +298,7 @@ struct BwdTcArgs {
     float* gb1;
     float* gb2;
     int n_tiles;
+    int64_t row_off;
 };
 
 struct BwdBars {
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                     float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (in) {
                         if (a.mess_mult) mult = ld_f4(a.mess_mult + row * d_out + c0);
-                        else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)(row * d_out + c0) >> 2);
+                        else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
                     }
                     g.x *= mult.x * (e[j].x > 0.f ? 1.f : a.slope);       // dropout + LeakyReLU backward
                     g.y *= mult.y * (e[j].y > 0.f ? 1.f : a.slope);
@@ -710,9 +712,9 @@ bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out) {
 
 int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
                       const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
-                      const uint64_t* seed_dev, int layer, float* E_out, cudaStream_t st) {
+                      const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, cudaStream_t st) {
     FwdTcArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
-                (int)ceil_div64(n_rows, TC_ROWS)};
+                (int)ceil_div64(n_rows, TC_ROWS), row_offset};
     const int KB = 2 * d_in / 32;
     const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) +
                         TC_EPI_WARPS * 32 * FW_STAGE_PITCH * sizeof(float) + sizeof(Bars);
@@ -732,10 +734,11 @@ bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out) { return d_in == 64 && (d_o
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
-                      uint64_t seed, const uint64_t* seed_dev, int layer, float* gS, float* gEl, float* gW1,
-                      float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st) {
+                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
+                      float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st) {
     BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-                mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS)};
+                mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS),
+                row_offset};
     const int KBo = d_out / 32;
     const size_t smem = 1024 + (size_t)6 * KBo * TC_A_BLOCK + TC_EPI_WARPS * 32 * BW_STAGE_PITCH * sizeof(float) +
                         sizeof(BwdBars);

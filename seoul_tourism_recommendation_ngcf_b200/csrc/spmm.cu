@@ -40,6 +40,7 @@ struct SpmmArgs {
     const uint64_t* seed_dev;
     int layer;
     int transposed;
+    uint32_t row_off;
 };
 
 struct CtaSync {
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
-    DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed};
+    DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
+                a.row_off};
     stage_tile<SP_THREADS>(ti, a.rowptr, a.ent, a.row_key, dr, rp_s, ent_s, tid, CtaSync());
 
     const int nr = ti.r1 - ti.r0;
@@ -138,8 +140,8 @@ int ngcf_check_csr(const ngcf_csr* g, const char* who) {
 
 extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
                          const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial, float drop_p,
-                         uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, float* Y, int64_t ldy,
-                         void* stream) {
+                         uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
+                         float* Y, int64_t ldy, void* stream) {
     int rc = ngcf_check_csr(g, "spmm");
     if (rc != NGCF_OK) return rc;
     NGCF_REQUIRE(X && Y, "spmm: null pointer");
@@ -147,6 +149,7 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     NGCF_REQUIRE(ldx >= d && ldy >= d && ldx < ((int64_t)1 << 31), "spmm: bad leading dimension");
     NGCF_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "spmm: drop_p %f not in [0,1)", drop_p);
     NGCF_REQUIRE(layer >= 0 && layer < NGCF_MAX_LAYERS, "spmm: layer %d", layer);
+    NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "spmm: row_offset %lld", (long long)row_offset);
     NGCF_REQUIRE(!slot || gsum, "spmm: slot given without gsum");
     NGCF_REQUIRE(g->n_hub == 0 || hub_partial, "spmm: hub_partial scratch missing");
     NGCF_REQUIRE(g->n_tiles == 0 || g->tiles, "spmm: SpMM tiles missing");
@@ -160,11 +163,11 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
         SpmmArgs h{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
                    reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, nullptr, nullptr, nullptr, X,
                    (uint32_t)ldx, d, nullptr, 0, nullptr, nullptr, 0, hub_partial, d, drop_p, seed, seed_dev, layer,
-                   transposed};
+                   transposed, (uint32_t)row_offset};
         if ((rc = launch_any(h, g->n_chunk_tiles, vec, st, "spmm_tile_kernel(hub chunks)")) != NGCF_OK) return rc;
     }
     SpmmArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
                g->n_hub > 0 ? g->hub_of_row : nullptr, g->hub_chunk_ptr, hub_partial, X, (uint32_t)ldx, d, addend,
-               ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed};
+               ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed, (uint32_t)row_offset};
     return launch_any(a, g->n_tiles, vec, st, "spmm_tile_kernel(rows)");
 }

@@ -33,6 +33,7 @@ struct DropArgs {
     uint64_t seed;      // already combined with the device counter
     int layer;
     int transposed;     // the CSR holds L^T: entry (row, col) here is entry (col, row) of L
+    uint32_t row_off;   // global index of local row 0 (row-sharded runs key the RNG on global coordinates)
 };
 
 // Stages one tile: rp_s[0 .. nr] = rowptr[r0 .. r1] - e0 (tile-relative), ent_s[0 .. cnt) = entries with node
@@ -53,7 +54,7 @@ __device__ __forceinline__ void stage_tile(const TileInfo ti, const int32_t* __r
                 const int mid = (lo + hi + 1) >> 1;
                 if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
             }
-            const uint32_t r = (uint32_t)(row_key ? row_key[ti.r0 + lo] : ti.r0 + lo);
+            const uint32_t r = (uint32_t)(row_key ? row_key[ti.r0 + lo] : ti.r0 + lo) + dr.row_off;
             const uint32_t r0 = dr.transposed ? (uint32_t)e.x : r;
             const uint32_t c0 = dr.transposed ? r : (uint32_t)e.x;
             if (!node_keep(dr.p, dr.seed, dr.layer, r0, c0)) e.y = 0;
@@ -67,29 +68,53 @@ __device__ __forceinline__ void stage_tile(const TileInfo ti, const int32_t* __r
 
 // ---- vector path: d % 4 == 0, 16-byte aligned rows.  A warp is cut into 32/G groups of G lanes; lane l of a
 // group owns columns [4l, 4l+4) and a group fetches one gathered row per LDG.128. ------------------------------
+// The issue rate, not memory, bounds this loop once the entries sit in shared memory (ncu: 67 % issue-active with a
+// fully predicated body), so whole batches of NG*UNROLL entries run without any predicate: one LDS.64 with an
+// immediate offset, one IMAD.WIDE, one LDG.128 and four FFMA per gathered row; only the remainder is predicated.
 template <int G>
 __device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b, const float* __restrict__ X,
                                                  uint32_t ldx, int d, int lane) {
     constexpr int NG = 32 / G;
+    constexpr int TAIL = 4;
     const int g = lane / G, l = lane % G;
-    const bool active = (l * 4) < d;
-    const float* xl = X + l * 4;
+    // byte addressing: one IMAD.WIDE.U32 (col * row_bytes + base) per gathered row
+    const char* xl = reinterpret_cast<const char*>(X + ((l * 4) < d ? l * 4 : 0));   // lanes past the width re-read column 0
+    const uint32_t row_bytes = ldx * 4u;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j0 = a; j0 < b; j0 += NG * UNROLL) {
+    int j0 = a;
+    for (; j0 + NG * UNROLL <= b; j0 += NG * UNROLL) {
+        const int2* p = ent_s + j0 + g;
+        int2 e[UNROLL];
         float4 x[UNROLL];
-        float w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) e[u] = p[u * NG];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)(uint32_t)e[u].x * row_bytes));
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
+            const float w = __int_as_float(e[u].y);
+            acc.x = fmaf(w, x[u].x, acc.x);
+            acc.y = fmaf(w, x[u].y, acc.y);
+            acc.z = fmaf(w, x[u].z, acc.z);
+            acc.w = fmaf(w, x[u].w, acc.w);
+        }
+    }
+    for (; j0 < b; j0 += NG * TAIL) {
+        float4 x[TAIL];
+        float w[TAIL];
+#pragma unroll
+        for (int u = 0; u < TAIL; ++u) {
             const int idx = j0 + u * NG + g;
-            const bool ok = (idx < b) && active;
+            const bool ok = idx < b;
             int2 e = make_int2(0, 0);
             if (ok) e = ent_s[idx];
             w[u] = __int_as_float(e.y);
             x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) x[u] = ld_f4(xl + (uint64_t)(uint32_t)e.x * ldx);
+            if (ok) x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)(uint32_t)e.x * row_bytes));
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
+        for (int u = 0; u < TAIL; ++u) {
             acc.x = fmaf(w[u], x[u].x, acc.x);
             acc.y = fmaf(w[u], x[u].y, acc.y);
             acc.z = fmaf(w[u], x[u].z, acc.z);

@@ -139,7 +139,10 @@ class CsrSide:
 
 
 class LaplacianPlan:
-    def __init__(self, L: torch.Tensor, device):
+    """Execution plan of one ``lap_list`` element; ``shard`` (a sharded.RowShards) restricts it to this rank's row
+    block of L and of L^T (``rows x N_pad`` matrices whose column ids stay global)."""
+
+    def __init__(self, L: torch.Tensor, device, shard=None):
         if not (L.is_sparse and L.dim() == 2 and L.shape[0] == L.shape[1]):
             raise ValueError("lap_list entries must be square torch.sparse_coo tensors (matrix.py:79-83)")
         device = torch.device(device)
@@ -148,33 +151,49 @@ class LaplacianPlan:
         lib = _lib.load()
         self.src = L
         self.N = int(L.shape[0])
+        self.shard = shard
         idx = L._indices().to(device=device, dtype=torch.int64).contiguous()
         self.coo_val = L._values().to(device=device, dtype=torch.float32).contiguous()
         self.nnz = int(self.coo_val.numel())
         if self.nnz and (int(idx.min()) < 0 or int(idx.max()) >= self.N):
             raise ValueError("Laplacian indices out of range")
-        row, col = idx[0].contiguous(), idx[1].contiguous()
-        need = C.c_size_t(0)
-        _lib.check(lib.ngcf_coo_to_csr_workspace(self.nnz, self.N, C.byref(need)), "coo_to_csr_workspace")
-        ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+        if shard is None:
+            n_rows = n_cols = self.N
+            pos = torch.arange(self.nnz, device=device)
+            parts = [(idx[0], idx[1], pos), (idx[1], idx[0], pos)]            # L, L^T
+        else:
+            from .sharded import shard_coo
+            if shard.N != self.N:
+                raise ValueError("shard descriptor and Laplacian disagree on N")
+            n_rows, n_cols = shard.rows, shard.N_pad
+            Ld = torch.sparse_coo_tensor(idx, self.coo_val, L.shape, is_coalesced=False, check_invariants=False)
+            parts = list(shard_coo(Ld, shard))
         sides = []
-        for transpose in (0, 1):
-            rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=device)
-            colidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)
-            perm = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=device)
-            _lib.check(lib.ngcf_coo_to_csr(row.data_ptr(), col.data_ptr(), self.nnz, self.N, self.N, transpose,
+        for row, col, pos in parts:
+            nnz = int(row.numel())
+            row, col = row.contiguous(), col.contiguous()
+            need = C.c_size_t(0)
+            _lib.check(lib.ngcf_coo_to_csr_workspace(nnz, n_rows, C.byref(need)), "coo_to_csr_workspace")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+            rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=device)
+            colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
+            perm = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
+            _lib.check(lib.ngcf_coo_to_csr(row.data_ptr(), col.data_ptr(), nnz, n_rows, n_cols, 0,
                                            rowptr.data_ptr(), colidx.data_ptr(), perm.data_ptr(), ws.data_ptr(),
                                            need.value, _stream()), "coo_to_csr")
-            side = CsrSide(rowptr, colidx, perm, self.N, self.nnz)
+            # perm indexes this side's entry list; compose with `pos` so it addresses the ORIGINAL COO order
+            perm = pos[perm[:nnz].to(torch.int64)].to(torch.int32) if nnz else perm
+            side = CsrSide(rowptr, colidx, perm, n_rows, nnz)
             side.ent = self.entries(side, None)
             sides.append(side)
-        torch.cuda.current_stream().synchronize()
-        del ws
+            torch.cuda.current_stream().synchronize()
+            del ws
         self.fwd, self.bwd = sides
         # L = D^-1/2 A D^-1/2 is symmetric (matrix.py:48-62): then L^T's layout is L's, and sharing the arrays
         # halves the distinct bytes a training step touches.  Node dropout breaks the symmetry per step, which
         # is handled by giving the two directions separate masked entry arrays.
-        self.symmetric = bool(torch.equal(self.fwd.rowptr, self.bwd.rowptr) and torch.equal(self.fwd.ent, self.bwd.ent))
+        self.symmetric = bool(self.fwd.nnz == self.bwd.nnz and torch.equal(self.fwd.rowptr, self.bwd.rowptr) and
+                              torch.equal(self.fwd.ent, self.bwd.ent))
 
     def side(self, transposed: bool, masked: bool) -> CsrSide:
         if transposed and not (self.symmetric and not masked):
@@ -185,14 +204,14 @@ class LaplacianPlan:
         """Entry pairs in execution order, optionally with an explicit COO-order node-dropout mask folded in
         (NGCF.py:93-100).  Two trailing pad pairs keep vector reads in bounds."""
         lib = _lib.load()
-        out = torch.zeros(self.nnz + 2, 2, dtype=torch.int32, device=self.coo_val.device)
+        out = torch.zeros(side.nnz + 2, 2, dtype=torch.int32, device=self.coo_val.device)
         _lib.check(lib.ngcf_edge_entries(side.colidx.data_ptr(), self.coo_val.data_ptr(), side.perm.data_ptr(),
-                                         _lib.ptr(keep_mask), out.data_ptr(), self.nnz, _stream()), "edge_entries")
+                                         _lib.ptr(keep_mask), out.data_ptr(), side.nnz, _stream()), "edge_entries")
         return out
 
 
 def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=None, drop_p: float = 0.0,
-         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False):
+         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0):
     """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout."""
     lib = _lib.load()
     if out is None:
@@ -202,5 +221,5 @@ def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=N
                              _lib.ptr(slot), _lib.ptr(gsum), gsum.stride(0) if gsum is not None else 0,
                              _lib.ptr(side.hub_partial(d)),
                              float(drop_p), int(seed) & (2 ** 64 - 1), _lib.ptr(seed_dev), int(layer), int(transposed),
-                             out.data_ptr(), out.stride(0), _stream()), "spmm")
+                             int(row_offset), out.data_ptr(), out.stride(0), _stream()), "spmm")
     return out

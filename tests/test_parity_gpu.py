@@ -380,7 +380,7 @@ def _dense_fwd(S, E, W1, b1, W2, b2, mess_mult=None):
                                      wcat.data_ptr(), bias.data_ptr(), st))
     out = torch.empty(N, d_out, device=DEV)
     _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E.data_ptr(), N, d_in, d_out, wcat.data_ptr(), bias.data_ptr(), 0.2,
-                                  _lib.ptr(mess_mult), 0.0, 0, None, 0, out.data_ptr(), st), "dense_fwd")
+                                  _lib.ptr(mess_mult), 0.0, 0, None, 0, 0, out.data_ptr(), st), "dense_fwd")
     torch.cuda.synchronize()
     return out
 
@@ -436,7 +436,7 @@ def test_dense_backward_vs_float64(N, d_in, d_out):
         _lib.check(lib.ngcf_dense_bwd(d["gE_next"].data_ptr() if use_next else None, d["slot"].data_ptr(),
                                       d["gsum"].data_ptr(), D, col_off, d["E_out"].data_ptr(), d["S"].data_ptr(),
                                       d["E"].data_ptr(), N, d_in, d_out, d["W1"].data_ptr(), d["W2"].data_ptr(), 0.2,
-                                      d["mult"].data_ptr() if use_mult else None, 0.0, 0, None, 0, gS.data_ptr(),
+                                      d["mult"].data_ptr() if use_mult else None, 0.0, 0, None, 0, 0, gS.data_ptr(),
                                       gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(),
                                       scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "dense_bwd")
         torch.cuda.synchronize()
@@ -453,3 +453,43 @@ def test_dense_backward_vs_float64(N, d_in, d_out):
         got = dict(gS=gS, gEl=gEl, gW1=gW1, gW2=gW2, gb1=gb1, gb2=gb2)
         for k in want:
             assert rel_err(got[k].cpu().numpy(), want[k].numpy()) <= 2e-5, (k, use_next)
+
+
+def test_row_sharded_path_single_rank_equals_unsharded():
+    """The row-sharded code path (sharded.py; all-gathers, shard plans, global RNG keys) with a one-rank NCCL group
+    must reproduce the unsharded step exactly, dropout included.  (tools/mgpu_check.py runs the same comparison
+    under torchrun on 2+ GPUs.)"""
+    import torch.distributed as dist
+    own = not dist.is_initialized()
+    if own:
+        import os
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        n_user, n_item, B = 900, 700, 256
+        u, i, r = synth.powerlaw_bipartite(n_user, n_item, 40000, seed=5)
+        L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+        nd = synth.num_dict_for(n_user, n_item)
+        b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=6).items()}
+        res = []
+        for sharded in (False, True):
+            torch.manual_seed(0)
+            m = pkg.NGCF(64, [64, 64, 32], 0.3, [0.1] * 3, 1.0, [L, L], nd, B, torch.device(DEV)).to(DEV)
+            if sharded:
+                m.shard()
+            m.train()
+            torch.manual_seed(11)
+            uu, pp, nn_ = _call(m, b, True)
+            loss = pkg.BPR(0.025, B)(uu, pp, nn_)
+            loss.backward()
+            res.append((uu.detach().clone(), float(loss), {k: p.grad.clone() for k, p in m.named_parameters()
+                                                           if p.grad is not None}, m.all_items_emb.clone()))
+        (u0, l0, g0, a0), (u1, l1, g1, a1) = res
+        assert torch.equal(u0, u1) and abs(l0 - l1) <= 1e-6 * abs(l0) and torch.equal(a0, a1)   # loss: atomic sum order
+        assert g0.keys() == g1.keys()
+        for k in g0:
+            assert rel_err(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-6, k      # weight grads: atomics order
+    finally:
+        if own:
+            dist.destroy_process_group()
