@@ -173,15 +173,36 @@ def run_ours(args):
     from seoul_tourism_recommendation_ngcf_b200 import _lib
     from seoul_tourism_recommendation_ngcf_b200.plan import spmm
 
-    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        raise SystemExit("multi-GPU row-sharded bench is not wired up yet in this revision")
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks: launch with python -m torch.distributed.run "
+                         f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
-    dev = torch.device("cuda:0")
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl")
     lib = _lib.load()
     L, batches, info = make_workload(args.shape)
     model = make_model(info, L, dev).to(dev)
+    if world > 1:
+        model.shard()          # row partition + per-layer all-gather (sharded.py); every rank steps the same batches
     model.train()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     crit = pkg.BPR(WEIGHT_DECAY, BATCH)
     dbatches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in batches]
     hbatches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
@@ -200,60 +221,60 @@ def run_ours(args):
         b["year"] = b["year"].cpu()
     for j in range(max(args.warmup, 3)):
         step(dbatches[j % len(dbatches)])
-    torch.cuda.synchronize()
+    fence()
 
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local)
     sampler.start()
     windows = []
 
     # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps -----------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = lib.ngcf_launch_count()
-    torch.cuda.synchronize()
+    fence()
     w0 = time.time()
     for j in range(args.steps):
         flush.zero_()
         ev[j][0].record()
         step(dbatches[j % len(dbatches)])
         ev[j][1].record()
-    torch.cuda.synchronize()
+    fence()
     windows.append((w0, time.time()))
     launches = (lib.ngcf_launch_count() - launches0) / args.steps
     times = [a.elapsed_time(b) for a, b in ev]
-    ms_per_step = sum(times) / len(times)
+    ms_per_step = max_over_ranks(sum(times)) / len(times)
 
     # ---- warm variant (no flush, back-to-back) — reported as context only -------------------------------------
-    torch.cuda.synchronize()
+    fence()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
     for j in range(args.steps):
         step(dbatches[j % len(dbatches)])
     e1.record()
-    torch.cuda.synchronize()
+    fence()
     windows.append((w0, time.time()))
-    ms_warm = e0.elapsed_time(e1) / args.steps
+    ms_warm = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---- e2e: host (pinned) inputs -> H2D inside the timed region -> step -> loss read back ---------------------
     h2d = sum(v.numel() * v.element_size() for k, v in hbatches[0].items() if k != "year")
     for j in range(3):
         b = hbatches[j % len(hbatches)]
-        float(step({k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}))
-    torch.cuda.synchronize()
+        float(step({k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}).detach())
+    fence()
     w0 = time.time()
     e0.record()
     for j in range(args.steps):
         b = hbatches[j % len(hbatches)]
         db = {k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}
-        loss_val = float(step(db))                          # device -> host read of the step's result
+        loss_val = float(step(db).detach())                 # device -> host read of the step's result
     e1.record()
-    torch.cuda.synchronize()
+    fence()
     windows.append((w0, time.time()))
-    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---- roofline of the dominant kernel: the propagation SpMM, timed alone, cold L2 ----------------------------
-    plan = model._last.plan
-    N, nnz, d = plan.N, plan.nnz, info["emb"]
+    plan = model._last.plan                       # this rank's row shard when world > 1
+    N, nnz, d = plan.fwd.n_rows, plan.fwd.nnz, info["emb"]
     X = model._packed_table()
     Y = torch.empty(N, d, device=dev)
     reps = 20
@@ -281,7 +302,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.shape)
-    roofline = {"kernel": "spmm_rows_vec_kernel<16> (+ spmm_hub_vec_kernel) = one ngcf_spmm call, layer 0",
+    roofline = {"kernel": "spmm_tile_kernel<16> x2 (hub-chunk pass + row pass) = one ngcf_spmm call, layer 0"
+                          + (f", row shard of rank 0 of {world}" if world > 1 else ""),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "kernel_ms": round(k_ms, 5), "peak_source": peak_src, "timing": "CUDA events, cold L2 (flushed)"}
@@ -303,15 +325,22 @@ def run_ours(args):
 
     # ---- CPU baseline beside it ------------------------------------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cpu = time_oracle(L, batches, info, max_steps=3, warmup=1, budget_s=40.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
 
     spe = info["steps_per_epoch"]
     out = {
-        "metric": METRIC, "value": round(ms_per_step * spe / 1e3, 6), "unit": "s/epoch", "n_gpus": 1,
+        "metric": METRIC, "value": round(ms_per_step * spe / 1e3, 6), "unit": "s/epoch", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
-        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": nnz, "N": N,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": int(L._nnz()), "N": int(L.shape[0]),
+                   "parallelism": "single GPU" if world == 1 else
+                   f"row-sharded x{world} (equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads)",
                    "rng": "device (Philox, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                    "api": "drop-in NGCF.forward + BPR + loss.backward(), eager"},
         "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),

@@ -266,9 +266,9 @@ class NGCF(nn.Module):
             n_rows = self._shard.N_pad if self._shard is not None else self.n_user + self.n_item
             table = torch.zeros(n_rows, d, dtype=torch.float32, device=u.device)   # rows past N: shard padding
             table[:self.n_user].copy_(u.data)
-            table[self.n_user:].copy_(i.data)
+            table[self.n_user:self.n_user + self.n_item].copy_(i.data)
             u.data = table[:self.n_user]
-            i.data = table[self.n_user:]
+            i.data = table[self.n_user:self.n_user + self.n_item]
             self._table = table
         return self._table if self._shard is None else self._table   # [N_pad, d] when sharded (pad rows are zero)
 
