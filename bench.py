@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="gowalla")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager drop-in path only (no CUDA graph)")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
     return ap.parse_args()
 
@@ -227,21 +228,66 @@ def run_ours(args):
     sampler.start()
     windows = []
 
-    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps -----------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def timed_resident(fn):
+        """K steps on device-resident batches, per-step CUDA events, L2 flushed between steps; max over ranks."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        fence()
+        w0 = time.time()
+        for j in range(args.steps):
+            flush.zero_()
+            ev[j][0].record()
+            fn(dbatches[j % len(dbatches)])
+            ev[j][1].record()
+        fence()
+        windows.append((w0, time.time()))
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / args.steps
+
+    def timed_e2e(fn, to_dev):
+        """K steps from pinned host batches: H2D copy + step + loss read back inside the timed region."""
+        for j in range(3):
+            b = hbatches[j % len(hbatches)]
+            float(fn({k: (v if (k == "year" or not to_dev) else v.to(dev, non_blocking=True)) for k, v in b.items()}).detach())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        w0 = time.time()
+        e0.record()
+        last = 0.0
+        for j in range(args.steps):
+            b = hbatches[j % len(hbatches)]
+            db = {k: (v if (k == "year" or not to_dev) else v.to(dev, non_blocking=True)) for k, v in b.items()}
+            last = float(fn(db).detach())                       # device -> host read of the step's result
+        e1.record()
+        fence()
+        windows.append((w0, time.time()))
+        return max_over_ranks(e0.elapsed_time(e1)) / args.steps, last
+
+    # ---- the eager drop-in path first (before any graph capture touches the allocator) ---------------------------
+    h2d = sum(v.numel() * v.element_size() for k, v in hbatches[0].items() if k != "year")
     launches0 = lib.ngcf_launch_count()
-    fence()
-    w0 = time.time()
-    for j in range(args.steps):
-        flush.zero_()
-        ev[j][0].record()
-        step(dbatches[j % len(dbatches)])
-        ev[j][1].record()
-    fence()
-    windows.append((w0, time.time()))
-    launches = (lib.ngcf_launch_count() - launches0) / args.steps
-    times = [a.elapsed_time(b) for a, b in ev]
-    ms_per_step = max_over_ranks(sum(times)) / len(times)
+    ms_eager = timed_resident(step)
+    launches_eager = (lib.ngcf_launch_count() - launches0) / args.steps
+    ms_e2e_eager, loss_eager = timed_e2e(step, to_dev=True)
+
+    # the same three calls captured once as a CUDA graph (graph.GraphedStep): the repo's fast public path
+    gstep, api = None, "drop-in NGCF.forward + BPR + loss.backward(), eager"
+    if not args.eager and world > 1:
+        log("[bench] row-sharded run: NCCL collectives are issued eagerly (graph capture across ranks is not enabled)")
+    if not args.eager and world == 1:
+        try:
+            gstep = pkg.GraphedStep(model, crit, BATCH, node_flag=True)
+            for j in range(max(args.warmup, 3)):
+                gstep(dbatches[j % len(dbatches)])
+            fence()
+            api = "GraphedStep = drop-in NGCF.forward + BPR + loss.backward() captured once as a CUDA graph, replayed per step"
+        except Exception as e:                                   # e.g. a collective that cannot be captured
+            log(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); measuring the eager path")
+            gstep = None
+            model._seed_dev = None
+    run = gstep if gstep is not None else step
+
+    # ---- value: device-resident inputs ------------------------------------------------------------------------
+    ms_per_step = timed_resident(run) if gstep is not None else ms_eager
+    launches = gstep.launches_per_step if gstep is not None else launches_eager
 
     # ---- warm variant (no flush, back-to-back) — reported as context only -------------------------------------
     fence()
@@ -249,28 +295,17 @@ def run_ours(args):
     w0 = time.time()
     e0.record()
     for j in range(args.steps):
-        step(dbatches[j % len(dbatches)])
+        run(dbatches[j % len(dbatches)])
     e1.record()
     fence()
     windows.append((w0, time.time()))
     ms_warm = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---- e2e: host (pinned) inputs -> H2D inside the timed region -> step -> loss read back ---------------------
-    h2d = sum(v.numel() * v.element_size() for k, v in hbatches[0].items() if k != "year")
-    for j in range(3):
-        b = hbatches[j % len(hbatches)]
-        float(step({k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}).detach())
-    fence()
-    w0 = time.time()
-    e0.record()
-    for j in range(args.steps):
-        b = hbatches[j % len(hbatches)]
-        db = {k: (v if k == "year" else v.to(dev, non_blocking=True)) for k, v in b.items()}
-        loss_val = float(step(db).detach())                 # device -> host read of the step's result
-    e1.record()
-    fence()
-    windows.append((w0, time.time()))
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    if gstep is not None:
+        ms_e2e, loss_val = timed_e2e(run, to_dev=False)          # GraphedStep copies the host batch itself (one H2D)
+    else:
+        ms_e2e, loss_val = ms_e2e_eager, loss_eager
 
     # ---- roofline of the dominant kernel: the propagation SpMM, timed alone, cold L2 ----------------------------
     plan = model._last.plan                       # this rank's row shard when world > 1
@@ -342,11 +377,14 @@ def run_ours(args):
                    "parallelism": "single GPU" if world == 1 else
                    f"row-sharded x{world} (equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads)",
                    "rng": "device (Philox, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
-                   "api": "drop-in NGCF.forward + BPR + loss.backward(), eager"},
+                   "api": api},
         "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_val},
         "warm_ms_per_step": round(ms_warm, 5),
+        "eager": {"ms_per_step": round(ms_eager, 5), "e2e_ms_per_step": round(ms_e2e_eager, 5),
+                  "api": "drop-in NGCF.forward + BPR + loss.backward() issued eagerly from Python"},
         "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
+        "gpu_launches_note": "library kernels per step (captured once, replayed per step under GraphedStep)",
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
     if breakdown:

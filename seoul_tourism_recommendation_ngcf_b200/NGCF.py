@@ -28,7 +28,7 @@ def _stream() -> int:
 
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
-    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "masked", "drop_p",
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p",
                  "rows", "offsets", "W1", "W2")
 
 
@@ -55,7 +55,8 @@ class _Propagate(torch.autograd.Function):
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
-            S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, layer=k, row_offset=r0)  # NGCF.py:124-130
+            S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
+                     row_offset=r0)                                                          # NGCF.py:124-130
             wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
             bias = torch.empty(d_out, dtype=torch.float32, device=dev)
             _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
@@ -70,7 +71,8 @@ class _Propagate(torch.autograd.Function):
             E_loc = st.E[k][r0:r0 + nloc]
             _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E_loc.data_ptr(), nv, d_in, d_out, wcat.data_ptr(),
                                           bias.data_ptr(), LEAKY_SLOPE, _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
-                                          float(st.mess_p[k]), st.seed, None, k, r0, En.data_ptr(), _stream()),
+                                          float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, En.data_ptr(),
+                                          _stream()),
                        "dense_fwd")                                                          # NGCF.py:131-142
             if sh is not None:
                 all_gather_rows(Xn, En, mod._group)                    # every rank needs all of E_{k+1}
@@ -133,7 +135,8 @@ class _Propagate(torch.autograd.Function):
                                           st.E[k][r0:r0 + nloc].data_ptr(), nv, d_in, d_out,
                                           st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE,
                                           _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
-                                          float(st.mess_p[k]), st.seed, None, k, r0, gS.data_ptr(), gEl.data_ptr(),
+                                          float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, gS.data_ptr(),
+                                          gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           gM_scratch.data_ptr(), _stream()), "dense_bwd")
             if sh is not None:                                        # L^T gS needs every rank's rows of gS
@@ -144,7 +147,7 @@ class _Propagate(torch.autograd.Function):
             vals = st.vals_b[k] if st.vals_b is not None else None
             last = (k == 0)
             gE_next = spmm(side, vals, gS_all, d_in, addend=gEl, slot=slot_loc if last else None,
-                           gsum=gsum if last else None, drop_p=st.drop_p, seed=st.seed, layer=k,
+                           gsum=gsum if last else None, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
                            transposed=True, row_offset=r0)            # gE_k = gEl + L^T gS (+ layer-0 row grads)
             if mod._trace is not None:                                # debugging aid: per-layer backward tensors
                 mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
@@ -207,6 +210,7 @@ class NGCF(nn.Module):
         self._winner = None
         self._last = None
         self._all_E = None
+        self._seed_dev = None    # device uint64 added to the Philox key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
@@ -357,6 +361,8 @@ class NGCF(nn.Module):
         # a device-RNG stream is live and only after the reference-mode mask draws, whose RNG stream it must not shift
         need_seed = st.drop_p > 0 or any(p > 0 for p in st.mess_p)
         st.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0
+        # CUDA-graph mode (graph.GraphedStep): the launches are frozen, so the per-step key comes from a device counter
+        st.seed_dev = self._seed_dev if need_seed else None
         if masks is not None:
             st.vals_f = [plan.entries(plan.fwd, masks[k]) for k in range(K)]
             st.vals_b = [plan.entries(plan.bwd, masks[k]) for k in range(K)]

@@ -1,6 +1,7 @@
 """B200-native NGCF embedding-propagation hot path behind the reference's NGCF / BPR API."""
 from .NGCF import NGCF
 from .bprloss import BPR
+from .graph import GraphedStep
 from .scoring import score_topk
 
-__all__ = ["NGCF", "BPR", "score_topk"]
+__all__ = ["NGCF", "BPR", "GraphedStep", "score_topk"]

@@ -1,0 +1,91 @@
+"""Whole-step CUDA graph around the drop-in modules.
+
+One reference training step (experiment.py:45-57: ``model(...)``, ``criterion(u, pos, neg)``, ``loss.backward()``)
+is ~35 kernel launches of 5-70 us each; issued eagerly from Python the host is the bottleneck (and, row-sharded over
+several GPUs, so are the NCCL launches).  ``GraphedStep`` captures exactly those three calls once — same modules,
+same kernels, same collectives — and replays them: per step the host does one pinned H2D copy of the index batch
+and one graph launch.  Gradients land in ``param.grad`` like after ``zero_grad(); loss.backward()``.
+
+Dropout stays fresh on every replay: the Philox key of a step is ``seed + *seed_dev`` (include/ngcf_b200.h) and the
+graph bumps the device counter ``seed_dev`` itself.
+"""
+from __future__ import annotations
+
+import torch
+
+FIELDS = ("u_id", "age", "sex", "month", "day", "dow", "pos_item", "neg_item")
+
+
+class GraphedStep:
+    """``step = GraphedStep(model, criterion, batch_size); loss = step(batch)`` with ``batch`` a dict of int64
+    tensors (host or device) holding ``year`` plus the eight index fields of ``TourDataset`` (utils.py:167-275).
+    ``year`` must be a host tensor (it selects ``lap_list[year.min() % 18]`` on the host, NGCF.py:117); one graph is
+    kept per selected Laplacian.  ``node_flag`` / train-vs-eval mode are frozen at capture time."""
+
+    def __init__(self, model, criterion, batch_size: int, node_flag: bool = True, warmup: int = 1):
+        dev = model.user_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedStep needs the model on a CUDA device")
+        self.model, self.criterion, self.node_flag, self.warmup = model, criterion, bool(node_flag), int(warmup)
+        self.B = int(batch_size)
+        self.static_idx = torch.zeros(len(FIELDS), self.B, dtype=torch.int64, device=dev)
+        self.stage = torch.zeros(len(FIELDS), self.B, dtype=torch.int64).pin_memory()
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graphs = {}
+        self.launches_per_step = None
+
+    def _run(self, year):
+        m = self.model
+        f = {k: self.static_idx[i] for i, k in enumerate(FIELDS)}
+        u, p, n = m(year=year, u_id=f["u_id"], age=f["age"], sex=f["sex"], month=f["month"], day=f["day"], dow=f["dow"],
+                    pos_item=f["pos_item"], neg_item=f["neg_item"], node_flag=self.node_flag)
+        loss = self.criterion(u, p, n)
+        loss.backward()
+        self.seed_dev.add_(0x9E3779B97F4A7C15 & (2 ** 62 - 1))        # next step: a different Philox key
+        return loss
+
+    def _capture(self, year):
+        from . import _lib
+        m = self.model
+        m._seed_dev = self.seed_dev
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                                    # warm-up outside the graph (plans, buffers)
+            for _ in range(self.warmup):
+                m.zero_grad(set_to_none=True)
+                self._run(year)
+        torch.cuda.current_stream().wait_stream(s)
+        m.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.load().ngcf_launch_count()
+        with torch.cuda.graph(g):
+            loss = self._run(year)
+        self.launches_per_step = int(_lib.load().ngcf_launch_count() - n0)
+        grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+        return g, loss, grads, m._last
+
+    def __call__(self, batch):
+        year = batch["year"]
+        if year.device.type != "cpu":
+            raise ValueError("GraphedStep: pass `year` as a host tensor (it is only used to pick lap_list[year % 18])")
+        for i, k in enumerate(FIELDS):
+            t = batch[k]
+            if t.numel() != self.B:
+                raise ValueError(f"GraphedStep was built for batches of {self.B} rows, got {t.numel()} for {k}")
+            if t.device.type == "cpu":
+                self.stage[i].copy_(t)
+            else:
+                self.static_idx[i].copy_(t, non_blocking=True)
+        if batch["u_id"].device.type == "cpu":
+            self.static_idx.copy_(self.stage, non_blocking=True)      # one pinned H2D copy for the whole batch
+        key = int(year.min()) % 18
+        entry = self.graphs.get(key)
+        if entry is None:                                             # first batch of this Laplacian: `warmup` eager
+            entry = self.graphs[key] = self._capture(year)            # steps on it (no parameter changes), then capture
+        g, loss, grads, last = entry
+        g.replay()
+        self.model._last, self.model._all_E = last, None              # all_users_emb / all_items_emb: rebuild on read
+        for k, p in self.model.named_parameters():                    # survive an optimizer.zero_grad(set_to_none=True)
+            if k in grads and p.grad is not grads[k]:
+                p.grad = grads[k]
+        return loss
