@@ -21,7 +21,7 @@ class NgcfCsr(C.Structure):
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
                 ("chunk_row", _vp), ("chunk_tiles", _vp),
                 ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
-                ("n_chunk_tiles", _i32), ("reserved", _i32)]
+                ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
 
 
 _csr_p = C.POINTER(NgcfCsr)
@@ -42,7 +42,8 @@ SIGNATURES = {
                          _vp, _vp],
     "ngcf_spmm_split_threshold": [],
     "ngcf_spmm": [_csr_p, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _i64,
-                  _vp, _i64, _vp],
+                  _vp, _vp, _i64, _vp],
+    "ngcf_node_dropout_bits": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp, _vp],
     "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
     "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32, _u64, _vp, C.c_int, _i64, _vp,
                        _vp],

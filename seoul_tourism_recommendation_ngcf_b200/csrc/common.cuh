@@ -115,6 +115,23 @@ __device__ __forceinline__ bool node_keep(float p, uint64_t seed, int layer, uin
     return keep;
 }
 
+// the same decisions for layers 0 .. n_layers-1 at once: bit k = the entry survives layer k (cumulative)
+__device__ __forceinline__ uint32_t node_keep_bits(float p, uint64_t seed, int n_layers, uint32_t row, uint32_t col) {
+    const uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t bits = 0;
+    bool keep = true;
+    for (int g = 0; g * 4 < n_layers && keep; ++g) {
+        const uint4 r = philox4x32_10(make_uint4(row, col, (uint32_t)g, NGCF_STREAM_NODE), k);
+        const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            keep = keep && (u01_from_bits(u[j]) >= p);
+            if (keep && g * 4 + j < n_layers) bits |= 1u << (g * 4 + j);
+        }
+    }
+    return bits;
+}
+
 // inverted-dropout multipliers of message dropout (NGCF.py:142) in device-RNG mode: one Philox call covers the four
 // consecutive elements 4*quad .. 4*quad+3 of the flattened [N, d_out] layer output
 __device__ __forceinline__ float4 mess_multiplier4(float p, uint64_t seed, int layer, uint64_t quad) {

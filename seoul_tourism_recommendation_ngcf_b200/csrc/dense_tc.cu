@@ -207,40 +207,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int64_t row0 = (int64_t)tile * TC_ROWS;
-            for (int hh = 0; hh < KBH; ++hh) {
-                const int kb1 = hh, kb2 = KBH + hh;
-                float4 s[4], e[4];
+            float4 s[2][4], e[2][4];                                      // both 32-column halves in flight at once
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {                             // 128 rows x 8 chunks = 4 per thread
                     const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
                     const int64_t row = row0 + r;
-                    s[q] = e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < a.n_rows) {
-                        s[q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
-                        e[q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
+                    s[hh][q] = e[hh][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < a.n_rows && hh < KBH) {
+                        s[hh][q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
+                        e[hh][q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
                     }
                 }
-                mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
-                mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
+            }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
-                    const uint32_t off = sw128_offset(r, c);
-                    const float4 x1 = make_float4(s[q].x + e[q].x, s[q].y + e[q].y, s[q].z + e[q].z, s[q].w + e[q].w);
-                    const float4 x2 = make_float4(s[q].x * e[q].x, s[q].y * e[q].y, s[q].z * e[q].z, s[q].w * e[q].w);
-                    float4 hi, lo;
-                    split_tf32(x1, hi, lo);
-                    *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
-                    *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
-                    split_tf32(x2, hi, lo);
-                    *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
-                    *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bars->full[kb1]);
-                    mbar_arrive(&bars->full[kb2]);
+            for (int hh = 0; hh < 2; ++hh) {
+                if (hh < KBH) {
+                    const int kb1 = hh, kb2 = KBH + hh;
+                    mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
+                    mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
+                        const uint32_t off = sw128_offset(r, c);
+                        const float4 sv = s[hh][q], ev = e[hh][q];
+                        const float4 x1 = make_float4(sv.x + ev.x, sv.y + ev.y, sv.z + ev.z, sv.w + ev.w);
+                        const float4 x2 = make_float4(sv.x * ev.x, sv.y * ev.y, sv.z * ev.z, sv.w * ev.w);
+                        float4 hi, lo;
+                        split_tf32(x1, hi, lo);
+                        *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
+                        *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
+                        split_tf32(x2, hi, lo);
+                        *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
+                        *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars->full[kb1]);
+                        mbar_arrive(&bars->full[kb2]);
+                    }
                 }
             }
         }
@@ -455,7 +462,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
         const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
         float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
         constexpr int PAIRS = TC_ROWS / (2 * TC_LOAD_WARPS);              // row pairs per warp per tile
-        constexpr int PB = 4;                                             // row pairs in flight
+        constexpr int PB = 4;                                             // row pairs in flight (register budget: 13 warps
+                                                                          // put 4 on one SM sub-partition -> 128 regs/thread)
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int buf = it & 1;

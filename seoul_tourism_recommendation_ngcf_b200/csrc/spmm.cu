@@ -41,6 +41,7 @@ struct SpmmArgs {
     int layer;
     int transposed;
     uint32_t row_off;
+    const uint8_t* bits;
 };
 
 struct CtaSync {
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
     DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
-                a.row_off};
+                a.row_off, a.bits};
     stage_tile<SP_THREADS>(ti, a.rowptr, a.ent, a.row_key, dr, rp_s, ent_s, tid, CtaSync());
 
     const int nr = ti.r1 - ti.r0;
@@ -101,6 +102,45 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     }
 }
 
+// Node-dropout decisions of one step for every entry of a tile list, all layers at once (bit k = survives layer k).
+// out_f: keyed on (row, col) = this CSR read as L; out_t: keyed on (col, row) = the same CSR read as L^T (a
+// symmetric L shares one CSR for both directions).  Either may be NULL.
+struct BitsArgs {
+    const TileInfo* tiles;
+    const int32_t* rowptr;
+    const int2* ent;
+    const int32_t* row_key;
+    float p;
+    uint64_t seed;
+    const uint64_t* seed_dev;
+    int n_layers;
+    uint32_t row_off;
+    uint8_t* out_f;
+    uint8_t* out_t;
+};
+
+__global__ void __launch_bounds__(SP_THREADS) dropout_bits_kernel(BitsArgs a) {
+    __shared__ int rp_s[SP_TILE_ROWS + 1];
+    const int tid = threadIdx.x;
+    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
+    const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
+    const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
+    for (int i = tid; i <= nr; i += SP_THREADS) rp_s[i] = a.rowptr[ti.r0 + i] - ti.e0;
+    __syncthreads();
+    const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
+    for (int i = tid; i < cnt; i += SP_THREADS) {
+        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + ti.e0 + i).x;
+        int lo = 0, hi = nr - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
+        if (a.out_f) a.out_f[ti.e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, r, c);
+        if (a.out_t) a.out_t[ti.e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, c, r);
+    }
+}
+
 template <int G>
 int launch(const SpmmArgs& a, int n_tiles, cudaStream_t st, const char* what) {
     if (n_tiles <= 0) return NGCF_OK;
@@ -141,7 +181,7 @@ int ngcf_check_csr(const ngcf_csr* g, const char* who) {
 extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
                          const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial, float drop_p,
                          uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
-                         float* Y, int64_t ldy, void* stream) {
+                         const uint8_t* keep_bits, float* Y, int64_t ldy, void* stream) {
     int rc = ngcf_check_csr(g, "spmm");
     if (rc != NGCF_OK) return rc;
     NGCF_REQUIRE(X && Y, "spmm: null pointer");
@@ -163,11 +203,39 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
         SpmmArgs h{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
                    reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, nullptr, nullptr, nullptr, X,
                    (uint32_t)ldx, d, nullptr, 0, nullptr, nullptr, 0, hub_partial, d, drop_p, seed, seed_dev, layer,
-                   transposed, (uint32_t)row_offset};
+                   transposed, (uint32_t)row_offset, keep_bits ? keep_bits + g->rowptr_nnz : nullptr};
         if ((rc = launch_any(h, g->n_chunk_tiles, vec, st, "spmm_tile_kernel(hub chunks)")) != NGCF_OK) return rc;
     }
     SpmmArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
                g->n_hub > 0 ? g->hub_of_row : nullptr, g->hub_chunk_ptr, hub_partial, X, (uint32_t)ldx, d, addend,
-               ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed, (uint32_t)row_offset};
+               ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed, (uint32_t)row_offset,
+               keep_bits};
     return launch_any(a, g->n_tiles, vec, st, "spmm_tile_kernel(rows)");
+}
+
+extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                      int n_layers, int64_t row_offset, uint8_t* bits_as_L, uint8_t* bits_as_Lt,
+                                      void* stream) {
+    int rc = ngcf_check_csr(g, "node_dropout_bits");
+    if (rc != NGCF_OK) return rc;
+    NGCF_REQUIRE(drop_p > 0.f && drop_p < 1.f, "node_dropout_bits: drop_p %f not in (0,1)", drop_p);
+    NGCF_REQUIRE(n_layers >= 1 && n_layers <= NGCF_MAX_LAYERS, "node_dropout_bits: n_layers %d", n_layers);
+    NGCF_REQUIRE(bits_as_L || bits_as_Lt, "node_dropout_bits: no output");
+    NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "node_dropout_bits: row_offset");
+    cudaStream_t st = as_stream(stream);
+    if (g->n_tiles > 0) {
+        BitsArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
+                   drop_p, seed, seed_dev, n_layers, (uint32_t)row_offset, bits_as_L, bits_as_Lt};
+        dropout_bits_kernel<<<(unsigned)g->n_tiles, SP_THREADS, 0, st>>>(a);
+        NGCF_LAUNCH_OK("dropout_bits_kernel(rows)");
+    }
+    if (g->n_hub > 0 && g->n_chunk_tiles > 0) {
+        BitsArgs a{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
+                   reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, drop_p, seed, seed_dev, n_layers,
+                   (uint32_t)row_offset, bits_as_L ? bits_as_L + g->rowptr_nnz : nullptr,
+                   bits_as_Lt ? bits_as_Lt + g->rowptr_nnz : nullptr};
+        dropout_bits_kernel<<<(unsigned)g->n_chunk_tiles, SP_THREADS, 0, st>>>(a);
+        NGCF_LAUNCH_OK("dropout_bits_kernel(hub chunks)");
+    }
+    return NGCF_OK;
 }

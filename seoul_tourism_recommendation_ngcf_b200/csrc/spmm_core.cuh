@@ -34,6 +34,7 @@ struct DropArgs {
     int layer;
     int transposed;     // the CSR holds L^T: entry (row, col) here is entry (col, row) of L
     uint32_t row_off;   // global index of local row 0 (row-sharded runs key the RNG on global coordinates)
+    const uint8_t* bits;    // optional precomputed decisions (ngcf_node_dropout_bits), indexed like `ent`; bit = layer
 };
 
 // Stages one tile: rp_s[0 .. nr] = rowptr[r0 .. r1] - e0 (tile-relative), ent_s[0 .. cnt) = entries with node
@@ -45,7 +46,13 @@ __device__ __forceinline__ void stage_tile(const TileInfo ti, const int32_t* __r
                                            const DropArgs& dr, int* rp_s, int2* ent_s, int tid, Sync sync) {
     const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
     for (int i = tid; i <= nr; i += NTHREADS) rp_s[i] = rowptr[ti.r0 + i] - ti.e0;
-    if (dr.p > 0.f) {
+    if (dr.bits) {                                                // decisions drawn once per step: one byte per entry
+        for (int i = tid; i < cnt; i += NTHREADS) {
+            int2 e = ld_stream_i2(ent + ti.e0 + i);
+            if (!((dr.bits[ti.e0 + i] >> dr.layer) & 1)) e.y = 0;
+            ent_s[i] = e;
+        }
+    } else if (dr.p > 0.f) {
         sync();                                                   // rp_s visible: entries need their row
         for (int i = tid; i < cnt; i += NTHREADS) {
             int2 e = ld_stream_i2(ent + ti.e0 + i);

@@ -125,6 +125,7 @@ class CsrSide:
             s.n_hub = self.n_hub
             s.n_chunks = self.n_chunks
             s.n_chunk_tiles = int(self.chunk_tiles.shape[0]) if self.chunk_tiles is not None else 0
+            s.rowptr_nnz = self.nnz_short
             self._struct_cache[key] = s
         return s
 
@@ -210,8 +211,22 @@ class LaplacianPlan:
         return out
 
 
+def node_dropout_bits(side: CsrSide, drop_p: float, seed: int, seed_dev, n_layers: int, row_offset: int = 0,
+                      as_L: bool = True, as_Lt: bool = False):
+    """One step's node-dropout decisions for every entry of ``side`` (uint8 per entry, bit k = survives layer k),
+    for the CSR read as L and/or as L^T.  Returns (bits_as_L or None, bits_as_Lt or None)."""
+    lib = _lib.load()
+    dev = side.rowptr.device
+    bl = torch.empty(side.nnz, dtype=torch.uint8, device=dev) if as_L else None
+    bt = torch.empty(side.nnz, dtype=torch.uint8, device=dev) if as_Lt else None
+    _lib.check(lib.ngcf_node_dropout_bits(C.byref(side.descriptor(None)), float(drop_p), int(seed) & (2 ** 64 - 1),
+                                          _lib.ptr(seed_dev), int(n_layers), int(row_offset), _lib.ptr(bl), _lib.ptr(bt),
+                                          _stream()), "node_dropout_bits")
+    return bl, bt
+
+
 def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=None, drop_p: float = 0.0,
-         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0):
+         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0, keep_bits=None):
     """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout."""
     lib = _lib.load()
     if out is None:
@@ -221,5 +236,5 @@ def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=N
                              _lib.ptr(slot), _lib.ptr(gsum), gsum.stride(0) if gsum is not None else 0,
                              _lib.ptr(side.hub_partial(d)),
                              float(drop_p), int(seed) & (2 ** 64 - 1), _lib.ptr(seed_dev), int(layer), int(transposed),
-                             int(row_offset), out.data_ptr(), out.stride(0), _stream()), "spmm")
+                             int(row_offset), _lib.ptr(keep_bits), out.data_ptr(), out.stride(0), _stream()), "spmm")
     return out

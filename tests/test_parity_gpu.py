@@ -260,6 +260,14 @@ def test_device_rng_dropout_statistics_and_consistency():
     for side in (ps.bwd, ps.fwd):                                # L^T from its own CSR, and from L's (symmetric L)
         mt = spmm(side, None, eye, 128, drop_p=0.3, seed=1234, layer=0, transposed=True)
         assert torch.equal(mt, m0.T)
+    # the per-step precomputed decision bytes (ngcf_node_dropout_bits) are the same decisions
+    from seoul_tourism_recommendation_ngcf_b200.plan import node_dropout_bits
+    bl, bt = node_dropout_bits(ps.fwd, 0.3, 1234, None, 3, as_L=True, as_Lt=True)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, layer=0, keep_bits=bl), m0)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, layer=2, keep_bits=bl), m2)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, layer=0, transposed=True, keep_bits=bt), m0.T)
+    _, bt2 = node_dropout_bits(ps.bwd, 0.3, 1234, None, 3, as_L=False, as_Lt=True)
+    assert torch.equal(spmm(ps.bwd, None, eye, 128, layer=0, transposed=True, keep_bits=bt2), m0.T)
     m0b = spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=99, layer=0)
     assert not torch.equal(m0b, m0)
     sd = torch.tensor([1234 - 99], dtype=torch.int64, device=DEV)   # device-side seed offset (graph replay path)
