@@ -143,11 +143,18 @@ int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const f
 /* E_out = Dropout(LeakyReLU_slope((S+E)·W1^T + (S*E)·W2^T + bias_eff)).
  *   mess_mult : optional [n_rows, d_out] multipliers standing in for nn.Dropout (mask injection);
  *   mess_p>0  : device-RNG inverted dropout keyed on (seed + *seed_dev, layer, element); ignored with mess_mult.
+ *   mess_bits : optional output of ngcf_mess_dropout_bits for this layer (the same decisions, drawn once per step
+ *               by a full-GPU pass instead of inside the 4 epilogue warps of each CTA); needs mess_p for 1/(1-p).
  *   row_offset: global index of row 0 (RNG keys only; 0 unless the rows are a shard of the full table). */
 int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* wcat, const float* bias_eff, float slope,
-                   const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                   int64_t row_offset, float* E_out, void* stream);
+                   const float* mess_mult, const uint32_t* mess_bits, float mess_p, uint64_t seed,
+                   const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, void* stream);
+
+/* Message-dropout decisions of one layer for a whole step: bits[row, col >> 5] bit (col & 31) = keep, for a
+ * [n_rows, ceil(d_out/32)] uint32 array; same Philox stream as the in-kernel path (keyed on global rows). */
+int ngcf_mess_dropout_bits(int64_t n_rows, int d_out, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
+                           int64_t row_offset, uint32_t* bits, void* stream);
 
 /* ---- output rows: NGCF.py:144-156 -------------------------------------------------------------------
  * out[b,:] = [ E0[r,:] | E1[r,:]/max(||E1[r,:]||,1e-12) | ... | EK[r,:]/max(...) ],  r = rows[b]+row_offset
@@ -191,9 +198,9 @@ int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_h
 int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,
-                   const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                   int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
-                   float* gM_scratch, void* stream);
+                   const float* mess_mult, const uint32_t* mess_bits, float mess_p, uint64_t seed,
+                   const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl, float* gW1,
+                   float* gb1, float* gW2, float* gb2, float* gM_scratch, void* stream);
 
 /* ---- scoring: demo.py:234-235, experiment.py:93,104,109 ----------------------------------------------
  * scores = U·I^T without materialising them; per user row the k largest (descending; ties by lower item

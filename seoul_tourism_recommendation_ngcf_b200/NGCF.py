@@ -28,7 +28,7 @@ def _stream() -> int:
 
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
-    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b",
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "mess_bits",
                  "rows", "offsets", "W1", "W2")
 
 
@@ -60,6 +60,17 @@ class _Propagate(torch.autograd.Function):
             st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
             if shared:
                 st.bits_b = bt
+        # message dropout (NGCF.py:142): optionally this step's decisions for every layer, one bit per element, drawn
+        # by a full-GPU pass instead of inside the dense kernels (measured slower at Gowalla shape: off by default)
+        self_uses_mess_bits = mod._mess_bits
+        st.mess_bits = [None] * K
+        for k in range(K):
+            if self_uses_mess_bits and st.mess_mult is None and st.mess_p[k] > 0 and st.dims[k + 1] % 4 == 0:
+                bits = torch.empty(nloc * ((st.dims[k + 1] + 31) // 32), dtype=torch.int32, device=dev)
+                _lib.check(lib.ngcf_mess_dropout_bits(nv, st.dims[k + 1], float(st.mess_p[k]), st.seed,
+                                                      _lib.ptr(st.seed_dev), k, r0, bits.data_ptr(), _stream()),
+                           "mess_dropout_bits")
+                st.mess_bits[k] = bits
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
@@ -79,7 +90,7 @@ class _Propagate(torch.autograd.Function):
             E_loc = st.E[k][r0:r0 + nloc]
             _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E_loc.data_ptr(), nv, d_in, d_out, wcat.data_ptr(),
                                           bias.data_ptr(), LEAKY_SLOPE, _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
-                                          float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, En.data_ptr(),
+                                          _lib.ptr(st.mess_bits[k]), float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, En.data_ptr(),
                                           _stream()),
                        "dense_fwd")                                                          # NGCF.py:131-142
             if sh is not None:
@@ -145,7 +156,8 @@ class _Propagate(torch.autograd.Function):
                                           st.E[k][r0:r0 + nloc].data_ptr(), nv, d_in, d_out,
                                           st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE,
                                           _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
-                                          float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, gS.data_ptr(),
+                                          _lib.ptr(st.mess_bits[k]), float(st.mess_p[k]), st.seed,
+                                          _lib.ptr(st.seed_dev), k, r0, gS.data_ptr(),
                                           gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           gM_scratch.data_ptr(), _stream()), "dense_bwd")
@@ -220,6 +232,7 @@ class NGCF(nn.Module):
         self._winner = None
         self._last = None
         self._all_E = None
+        self._mess_bits = False  # precompute message-dropout bits per step (ngcf_mess_dropout_bits)
         self._seed_dev = None    # device uint64 added to the Philox key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None

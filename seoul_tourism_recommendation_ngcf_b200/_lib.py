@@ -45,14 +45,15 @@ SIGNATURES = {
                   _vp, _vp, _i64, _vp],
     "ngcf_node_dropout_bits": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp, _vp],
     "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
-    "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32, _u64, _vp, C.c_int, _i64, _vp,
+    "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32, _u64, _vp, C.c_int, _i64, _vp,
                        _vp],
+    "ngcf_mess_dropout_bits": [_i64, C.c_int, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp],
     "ngcf_gather_concat": [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, _vp, _i64, _i64, _vp, _i64, _vp],
     "ngcf_bpr_fwd_bwd": [_vp, _vp, _vp, _i64, C.c_int, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "ngcf_rowgrad_scatter": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64), C.c_int, C.c_int, _vp,
                              _vp, _vp],
     "ngcf_rowgrad_reset": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, _vp, _vp],
-    "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _f32,
+    "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32,
                        _u64, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.POINTER(_sz)],
     "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],

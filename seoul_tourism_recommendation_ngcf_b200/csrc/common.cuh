@@ -147,3 +147,10 @@ __device__ __forceinline__ float mess_multiplier(float p, uint64_t seed, int lay
     const int j = (int)(elem & 3);
     return j == 0 ? m.x : j == 1 ? m.y : j == 2 ? m.z : m.w;
 }
+
+// message-dropout decisions precomputed per step (ngcf_mess_dropout_bits): bit (col & 31) of word
+// [row, col >> 5] of a [n_rows, ceil(d_out/32)] array = keep; same Philox stream as mess_multiplier4
+__device__ __forceinline__ float mess_multiplier_bits(const uint32_t* bits, float p, int64_t row, int d_out, int col) {
+    const uint32_t w = bits[row * ((d_out + 31) >> 5) + (col >> 5)];
+    return (w >> (col & 31)) & 1u ? 1.0f / (1.0f - p) : 0.0f;
+}

@@ -40,6 +40,7 @@ struct FwdArgs {
     const float* bias_eff;
     float slope;
     const float* mess_mult;
+    const uint32_t* mess_bits;
     float mess_p;
     uint64_t seed;
     const uint64_t* seed_dev;
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(FWD_THREADS) dense_fwd_kernel(FwdArgs a) {
                     const int col = c0 + c;
                     if (col < d_out) {
                         if (a.mess_mult) v *= a.mess_mult[row * d_out + col];
+                        else if (a.mess_bits) v *= mess_multiplier_bits(a.mess_bits, a.mess_p, row, d_out, col);
                         else if (a.mess_p > 0.f) v *= mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + col));
                     }
                     o[c] = v;
@@ -186,6 +188,7 @@ struct BwdArgs {
     const float* W2;
     float slope;
     const float* mess_mult;
+    const uint32_t* mess_bits;
     float mess_p;
     uint64_t seed;
     const uint64_t* seed_dev;
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(THREADS) dense_bwd_kernel(BwdArgs a) {
                     if (s >= 0) g += (gh[q] - (e[q] / n) * dot) / n;     // normalize backward
                     float mult = 1.f;
                     if (a.mess_mult) mult = a.mess_mult[row * d_out + c];
+                    else if (a.mess_bits) mult = mess_multiplier_bits(a.mess_bits, a.mess_p, row, d_out, c);
                     else if (a.mess_p > 0.f) mult = mess_multiplier(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c));
                     g *= mult * (e[q] > 0.f ? 1.f : a.slope);            // dropout + LeakyReLU backward
                 }
@@ -429,13 +433,15 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // dense_tc.cu: tcgen05 / TMEM versions (3xTF32) of the dense parts, used whenever the widths allow
 bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out);
 int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
-                      const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
+                      const float* bias_eff, float slope, const float* mess_mult, const uint32_t* mess_bits, float mess_p,
+                      uint64_t seed,
                       const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, cudaStream_t st);
 
 bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out);
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
-                      const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
+                      const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
+                      float mess_p,
                       uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
                       float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st);
 
@@ -456,7 +462,8 @@ extern "C" int ngcf_pack_weights(const float* W1, const float* b1, const float* 
 }
 
 extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
-                              const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
+                              const float* bias_eff, float slope, const float* mess_mult, const uint32_t* mess_bits, float mess_p,
+                      uint64_t seed,
                               const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, void* stream) {
     NGCF_REQUIRE(S && E && wcat && bias_eff && E_out, "dense_fwd: null pointer");
     NGCF_REQUIRE(d_in > 0 && d_in <= NGCF_MAX_WIDTH && d_out > 0 && d_out <= NGCF_MAX_WIDTH,
@@ -466,9 +473,9 @@ extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, in
     if (n_rows == 0) return NGCF_OK;
     if (ngcf_use_tensor_cores() && ngcf_dense_fwd_tc_eligible(d_in, d_out) && aligned16(S) && aligned16(E) &&
         aligned16(E_out) && (!mess_mult || aligned16(mess_mult)))
-        return ngcf_dense_fwd_tc(S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev,
+        return ngcf_dense_fwd_tc(S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev,
                                  layer, row_offset, E_out, as_stream(stream));
-    FwdArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
+    FwdArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, E_out,
               (2 * d_in + 3) & ~3, (int)ceil_div64(n_rows, FWD_R), row_offset};
     const int ncg = d_out <= 64 ? 1 : 2;
     const size_t smem = sizeof(float) * ((size_t)a.KP * 64 * ncg + (size_t)FWD_R * (a.KP + 4) + 64 * ncg);
@@ -489,8 +496,8 @@ extern "C" int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, in
 extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum,
                               int col_off, const float* E_out, const float* S, const float* E, int64_t n_rows,
                               int d_in, int d_out, const float* W1, const float* W2, float slope,
-                              const float* mess_mult, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
-                              int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
+                              const float* mess_mult, const uint32_t* mess_bits, float mess_p, uint64_t seed,
+                              const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
                               float* gM_scratch, void* stream) {
     NGCF_REQUIRE(E_out && S && E && W1 && W2 && gS && gEl && gW1 && gb1 && gW2 && gb2, "dense_bwd: null pointer");
     NGCF_REQUIRE(!slot || gsum, "dense_bwd: slot given without gsum");
@@ -502,10 +509,10 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
     if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out) && aligned16(S) &&
         aligned16(E) && aligned16(gS) && aligned16(gEl) && aligned16(gM_scratch))
         return ngcf_dense_bwd_tc(gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2,
-                                 slope, mess_mult, mess_p, seed, seed_dev, layer, row_offset, gS, gEl, gW1, gb1, gW2,
+                                 slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, row_offset, gS, gEl, gW1, gb1, gW2,
                                  gb2, gM_scratch, as_stream(stream));
     BwdArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-              mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0, row_offset};
+              mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0, row_offset};
     int rc;
     if (d_in <= 64 && d_out <= 64) {
         constexpr int DC = 64, R = 64, T = 256;
@@ -523,5 +530,43 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
         dense_bwd_kernel<DC, R, T><<<grid, T, smem, as_stream(stream)>>>(a);
     }
     NGCF_LAUNCH_OK("dense_bwd_kernel");
+    return NGCF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// message-dropout decisions for a whole layer, one 32-column word per thread
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void mess_bits_kernel(int64_t n_rows, int d_out, int words, float p, uint64_t seed0, const uint64_t* seed_dev,
+                                 int layer, int64_t row_off, uint32_t* __restrict__ bits) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows * words) return;
+    const int64_t row = i / words;
+    const int w = (int)(i % words);
+    const uint64_t seed = ngcf_seed(seed0, seed_dev);
+    uint32_t out = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int col = w * 32 + q * 4;
+        if (col < d_out) {
+            const float4 m = mess_multiplier4(p, seed, layer, (uint64_t)((row + row_off) * d_out + col) >> 2);
+            out |= (m.x != 0.f ? 1u : 0u) << (q * 4) | (m.y != 0.f ? 2u : 0u) << (q * 4) | (m.z != 0.f ? 4u : 0u) << (q * 4) |
+                   (m.w != 0.f ? 8u : 0u) << (q * 4);
+        }
+    }
+    bits[i] = out;
+}
+}  // namespace
+
+extern "C" int ngcf_mess_dropout_bits(int64_t n_rows, int d_out, float mess_p, uint64_t seed, const uint64_t* seed_dev,
+                                      int layer, int64_t row_offset, uint32_t* bits, void* stream) {
+    NGCF_REQUIRE(bits && n_rows >= 0, "mess_dropout_bits: null pointer");
+    NGCF_REQUIRE(d_out > 0 && d_out <= NGCF_MAX_WIDTH && d_out % 4 == 0, "mess_dropout_bits: width %d", d_out);
+    NGCF_REQUIRE(mess_p > 0.f && mess_p < 1.f, "mess_dropout_bits: mess_p %f not in (0,1)", mess_p);
+    if (n_rows == 0) return NGCF_OK;
+    const int words = (d_out + 31) / 32;
+    mess_bits_kernel<<<(unsigned)ceil_div64(n_rows * words, 256), 256, 0, as_stream(stream)>>>(
+        n_rows, d_out, words, mess_p, seed, seed_dev, layer, row_offset, bits);
+    NGCF_LAUNCH_OK("mess_bits_kernel");
     return NGCF_OK;
 }

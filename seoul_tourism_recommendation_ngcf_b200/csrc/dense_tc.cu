@@ -36,6 +36,7 @@ struct FwdTcArgs {
     const float* bias_eff;    // [d_out]
     float slope;
     const float* mess_mult;
+    const uint32_t* mess_bits;
     float mess_p;
     uint64_t seed;
     const uint64_t* seed_dev;
@@ -129,6 +130,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
                 }
                 const int64_t my_row = row_base + lane;
+                uint32_t keep = 0xffffffffu;                              // this row's 32 dropout decisions of the chunk
+                if (a.mess_bits && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
+                const float inv_keep = 1.0f / (1.0f - a.mess_p);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float o[4];
@@ -137,7 +141,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                         const float m = v[j + t] + bias_s[c * 32 + j + t];
                         o[t] = m > 0.f ? m : a.slope * m;                               // LeakyReLU, NGCF.py:140
                     }
-                    if (!a.mess_mult && a.mess_p > 0.f) {
+                    if (a.mess_bits) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) o[t] = (keep >> (j + t)) & 1u ? o[t] * inv_keep : 0.f;
+                    } else if (!a.mess_mult && a.mess_p > 0.f) {
                         const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
                         o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
                     }
@@ -295,6 +302,7 @@ struct BwdTcArgs {
     const float* W2;
     float slope;
     const float* mess_mult;
+    const uint32_t* mess_bits;
     float mess_p;
     uint64_t seed;
     const uint64_t* seed_dev;
@@ -520,7 +528,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                     float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (in) {
                         if (a.mess_mult) mult = ld_f4(a.mess_mult + row * d_out + c0);
-                        else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
+                        else if (a.mess_bits) {
+                            const uint32_t w = a.mess_bits[row * ((d_out + 31) >> 5) + (c0 >> 5)] >> (c0 & 31);
+                            const float inv = 1.0f / (1.0f - a.mess_p);
+                            mult = make_float4(w & 1u ? inv : 0.f, w & 2u ? inv : 0.f, w & 4u ? inv : 0.f, w & 8u ? inv : 0.f);
+                        } else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
                     }
                     g.x *= mult.x * (e[j].x > 0.f ? 1.f : a.slope);       // dropout + LeakyReLU backward
                     g.y *= mult.y * (e[j].y > 0.f ? 1.f : a.slope);
@@ -719,9 +731,10 @@ bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out) {
 }
 
 int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
-                      const float* bias_eff, float slope, const float* mess_mult, float mess_p, uint64_t seed,
-                      const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, cudaStream_t st) {
-    FwdTcArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_p, seed, seed_dev, layer, E_out,
+                      const float* bias_eff, float slope, const float* mess_mult, const uint32_t* mess_bits, float mess_p,
+                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out,
+                      cudaStream_t st) {
+    FwdTcArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, E_out,
                 (int)ceil_div64(n_rows, TC_ROWS), row_offset};
     const int KB = 2 * d_in / 32;
     const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) +
@@ -741,11 +754,11 @@ bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out) { return d_in == 64 && (d_o
 
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
-                      const float* W1, const float* W2, float slope, const float* mess_mult, float mess_p,
-                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
+                      const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
+                      float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
                       float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st) {
     BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-                mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS),
+                mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS),
                 row_offset};
     const int KBo = d_out / 32;
     const size_t smem = 1024 + (size_t)6 * KBo * TC_A_BLOCK + TC_EPI_WARPS * 32 * BW_STAGE_PITCH * sizeof(float) +

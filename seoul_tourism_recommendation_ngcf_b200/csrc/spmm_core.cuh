@@ -82,7 +82,7 @@ template <int G>
 __device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b, const float* __restrict__ X,
                                                  uint32_t ldx, int d, int lane) {
     constexpr int NG = 32 / G;
-    constexpr int TAIL = 4;
+    constexpr int TAIL = 4;           // (one predicated batch of UNROLL for the whole remainder measured slower)
     const int g = lane / G, l = lane % G;
     // byte addressing: one IMAD.WIDE.U32 (col * row_bytes + base) per gathered row
     const char* xl = reinterpret_cast<const char*>(X + ((l * 4) < d ? l * 4 : 0));   // lanes past the width re-read column 0

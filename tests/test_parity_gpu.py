@@ -388,7 +388,7 @@ def _dense_fwd(S, E, W1, b1, W2, b2, mess_mult=None):
                                      wcat.data_ptr(), bias.data_ptr(), st))
     out = torch.empty(N, d_out, device=DEV)
     _lib.check(lib.ngcf_dense_fwd(S.data_ptr(), E.data_ptr(), N, d_in, d_out, wcat.data_ptr(), bias.data_ptr(), 0.2,
-                                  _lib.ptr(mess_mult), 0.0, 0, None, 0, 0, out.data_ptr(), st), "dense_fwd")
+                                  _lib.ptr(mess_mult), None, 0.0, 0, None, 0, 0, out.data_ptr(), st), "dense_fwd")
     torch.cuda.synchronize()
     return out
 
@@ -444,7 +444,7 @@ def test_dense_backward_vs_float64(N, d_in, d_out):
         _lib.check(lib.ngcf_dense_bwd(d["gE_next"].data_ptr() if use_next else None, d["slot"].data_ptr(),
                                       d["gsum"].data_ptr(), D, col_off, d["E_out"].data_ptr(), d["S"].data_ptr(),
                                       d["E"].data_ptr(), N, d_in, d_out, d["W1"].data_ptr(), d["W2"].data_ptr(), 0.2,
-                                      d["mult"].data_ptr() if use_mult else None, 0.0, 0, None, 0, 0, gS.data_ptr(),
+                                      d["mult"].data_ptr() if use_mult else None, None, 0.0, 0, None, 0, 0, gS.data_ptr(),
                                       gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(),
                                       scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "dense_bwd")
         torch.cuda.synchronize()
@@ -535,3 +535,26 @@ def test_graphed_step_matches_eager_and_redraws_dropout():
     losses = [float(step_t(batches[0])) for _ in range(4)]
     assert all(np.isfinite(losses)) and len(set(losses)) == 4         # same batch, fresh dropout masks each replay
     assert max(losses) - min(losses) < 0.2 * abs(losses[0])
+
+
+def test_precomputed_message_dropout_bits_equal_in_kernel_decisions():
+    """ngcf_mess_dropout_bits draws the same message-dropout decisions as the in-kernel Philox path: a training
+    step with the bits precomputed must reproduce the default step bit for bit (forward) / to rounding (grads)."""
+    n_user, n_item, B = 800, 600, 128
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, 30000, seed=12)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    nd = synth.num_dict_for(n_user, n_item)
+    b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=13).items()}
+    res = []
+    for use_bits in (False, True):
+        torch.manual_seed(0)
+        m = pkg.NGCF(64, [64, 32, 65], 0.2, [0.3, 0.2, 0.1], 1.0, [L, L], nd, B, torch.device(DEV)).to(DEV)
+        m._mess_bits = use_bits
+        m.train()
+        torch.manual_seed(5)
+        uu, pp, nn_ = _call(m, b, True)
+        pkg.BPR(0.025, B)(uu, pp, nn_).backward()
+        res.append((uu.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0])
+    for k in res[0][1]:
+        assert rel_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) <= 1e-6, k
