@@ -270,9 +270,7 @@ def run_ours(args):
 
     # the same three calls captured once as a CUDA graph (graph.GraphedStep): the repo's fast public path
     gstep, api = None, "drop-in NGCF.forward + BPR + loss.backward(), eager"
-    if not args.eager and world > 1:
-        log("[bench] row-sharded run: NCCL collectives are issued eagerly (graph capture across ranks is not enabled)")
-    if not args.eager and world == 1:
+    if not args.eager:
         try:
             gstep = pkg.GraphedStep(model, crit, BATCH, node_flag=True)
             for j in range(max(args.warmup, 3)):
@@ -364,9 +362,12 @@ def run_ours(args):
         cpu = time_oracle(L, batches, info, max_steps=3, warmup=1, budget_s=40.0)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
         if rank != 0:
-            return
+            # no destroy_process_group(): tearing the communicator down while captured CUDA graphs still hold NCCL
+            # kernels blocks (observed: hangs until killed); the process simply exits after the final barrier
+            sys.stdout.flush()
+            os._exit(0)
 
     spe = info["steps_per_epoch"]
     out = {
@@ -390,6 +391,9 @@ def run_ours(args):
     if breakdown:
         out["breakdown"] = breakdown
     print(json.dumps(out), flush=True)
+    if world > 1:
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------------------

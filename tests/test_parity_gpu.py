@@ -319,7 +319,7 @@ def test_device_rng_dropout_statistics_and_consistency():
             assert rel_err(dict(m.named_parameters())[k].grad.cpu().numpy(), gr.numpy()) <= TOL, k
 
 
-@pytest.mark.parametrize("shape", ["seoul", "gowalla"])
+@pytest.mark.parametrize("shape", ["seoul", "gowalla", "yelp2018", "amazon-book"])
 def test_full_size_step_vs_oracle(shape):
     """BASELINE.json configs 1-2 at full size against the CPU oracle (the reference's torch.sparse path):
     Seoul shape = width 65 (scalar kernels, item rows of ~4000 entries -> hub split), Gowalla shape = width 64."""
