@@ -377,7 +377,7 @@ def run_ours(args):
         "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": int(L._nnz()), "N": int(L.shape[0]),
                    "parallelism": "single GPU" if world == 1 else
                    f"row-sharded x{world} (equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads)",
-                   "rng": "device (Philox, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "rng": "device (counter-based hash, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                    "api": api},
         "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_val},

@@ -112,7 +112,7 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
  *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
  *               (the IndexBackward scatter of NGCF.py:151-155 folded into the last backward SpMM).
  *   drop_p > 0: device-RNG node dropout (NGCF.py:93-100,124-126) evaluated in-kernel: entry (r,c) of L survives
- *               layer `layer` iff its Philox draws keyed on (seed + *seed_dev, r, c) for layers 0..layer are all
+ *               layer `layer` iff its counter-based draws keyed on (seed + *seed_dev, r, c) for layers 0..layer are all
  *               >= drop_p (cumulative over layers, unscaled — the reference's semantics).  `transposed` != 0 says
  *               this CSR holds L^T, so both directions drop the same entries of L.
  *               seed_dev: optional device uint64 added to seed (graph-replay safe).
@@ -129,7 +129,7 @@ int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
 /* One step's node-dropout decisions for every entry and every layer at once (bit k of a byte = the entry survives
  * layer k; cumulative).  Entry order = ent then hub_ent.  bits_as_L: this CSR read as L (keys (row, col));
  * bits_as_Lt: the same CSR read as L^T (keys (col, row)) — a symmetric L shares one CSR for both directions.
- * Passing the result to ngcf_spmm as keep_bits replaces its in-kernel Philox evaluation by one byte load per
+ * Passing the result to ngcf_spmm as keep_bits replaces its in-kernel hash evaluation by one byte load per
  * entry (same decisions, ~10 us less per product at Gowalla shape). */
 int ngcf_node_dropout_bits(const ngcf_csr* csr_host, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                            int n_layers, int64_t row_offset, uint8_t* bits_as_L, uint8_t* bits_as_Lt, void* stream);
@@ -152,7 +152,7 @@ int ngcf_dense_fwd(const float* S, const float* E, int64_t n_rows, int d_in, int
                    const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, void* stream);
 
 /* Message-dropout decisions of one layer for a whole step: bits[row, col >> 5] bit (col & 31) = keep, for a
- * [n_rows, ceil(d_out/32)] uint32 array; same Philox stream as the in-kernel path (keyed on global rows). */
+ * [n_rows, ceil(d_out/32)] uint32 array; same RNG stream as the in-kernel path (keyed on global rows). */
 int ngcf_mess_dropout_bits(int64_t n_rows, int d_out, float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer,
                            int64_t row_offset, uint32_t* bits, void* stream);
 

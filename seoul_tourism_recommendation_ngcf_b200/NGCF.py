@@ -54,7 +54,7 @@ class _Propagate(torch.autograd.Function):
         side = st.plan.fwd
         st.bits_f = st.bits_b = None
         if st.drop_p > 0:
-            # this step's node-dropout decisions for all K layers, drawn once (one byte per entry) instead of a Philox
+            # this step's node-dropout decisions for all K layers, drawn once (one byte per entry) instead of a hash
             # evaluation per entry in each of the 2K products; a symmetric L serves both directions from one pass
             shared = st.plan.side(True, False) is side
             st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
@@ -188,7 +188,7 @@ class _Propagate(torch.autograd.Function):
 class NGCF(nn.Module):
     """Same surface as the reference ``NGCF`` (NGCF.py:8-17).  Extra keyword-only knobs:
 
-    rng : "device" (default) draws node- and message-dropout decisions in-kernel from a Philox stream keyed
+    rng : "device" (default) draws node- and message-dropout decisions in-kernel from a counter-based hash stream keyed
           on a per-forward seed taken from torch's CPU generator;  "reference" reproduces the reference's host
           float64 ``nn.Dropout`` node mask bit for bit (NGCF.py:94) at its host cost.
     """
@@ -233,7 +233,7 @@ class NGCF(nn.Module):
         self._last = None
         self._all_E = None
         self._mess_bits = False  # precompute message-dropout bits per step (ngcf_mess_dropout_bits)
-        self._seed_dev = None    # device uint64 added to the Philox key (set by graph.GraphedStep)
+        self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
@@ -267,7 +267,7 @@ class NGCF(nn.Module):
     def shard(self, group=None):
         """Row-partitions the propagation over the ranks of ``group`` (default process group): this rank then
         computes rows [rank*rows, (rank+1)*rows) of every layer (sharded.py).  Parameters stay replicated; every
-        rank must call forward with the same batch and the same torch CPU RNG state (the per-step Philox key is drawn
+        rank must call forward with the same batch and the same torch CPU RNG state (the per-step RNG key is drawn
         from it).  Explicit-mask node dropout (rng="reference") is not available in this mode."""
         if not dist.is_initialized():
             raise RuntimeError("NGCF.shard() needs an initialised torch.distributed process group")
@@ -380,7 +380,7 @@ class NGCF(nn.Module):
             st.mess_mult = [m.to(device=dev, dtype=torch.float32).contiguous() for m in inj["mess_mult"]]
         elif self.training and self.mess_dropout is not None:
             st.mess_p = [float(p) for p in self.mess_dropout[:K]]
-        # per-forward Philox key from torch's CPU generator (reproducible under torch.manual_seed); drawn only when
+        # per-forward RNG key from torch's CPU generator (reproducible under torch.manual_seed); drawn only when
         # a device-RNG stream is live and only after the reference-mode mask draws, whose RNG stream it must not shift
         need_seed = st.drop_p > 0 or any(p > 0 for p in st.mess_p)
         st.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0

@@ -4,9 +4,9 @@
 // resident in shared memory for the whole (persistent) kernel, fp32 accumulator in TMEM, 3xTF32 (tc.cuh).
 //
 // Warp roles (416 threads, one CTA per SM):
-//   warps 0-3   epilogue: tcgen05.ld the accumulator (TMEM lane = tile row), bias + LeakyReLU + dropout, store
-//   warp  4     TMEM allocation; lane 0 issues every tcgen05.mma / tcgen05.commit
-//   warps 5-12  loaders: coalesced 128-bit reads of S and E, split into TF32 hi/lo, written straight into the
+//   warps 0-7   epilogue: tcgen05.ld the accumulator (TMEM lane = tile row), bias + LeakyReLU + dropout, store
+//   warp  8     TMEM allocation; lane 0 issues every tcgen05.mma / tcgen05.commit
+//   warps 9-12  loaders: coalesced 128-bit reads of S and E, split into TF32 hi/lo, written straight into the
 //               128-byte-swizzled K-major operand layout
 // A is pipelined per 32-wide K block: block kb of the next tile is refilled as soon as the MMAs that read it have
 // completed (tcgen05.commit -> empty[kb]); the accumulator is double buffered in TMEM so the epilogue of tile t
@@ -25,7 +25,6 @@ constexpr int TC_LOAD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_LOAD_WARPS) * 32;
 constexpr int TC_MAX_KB = 4;                 // K blocks of 32 TF32 (128 bytes): 2*d_in/32 <= 4  ->  d_in <= 64
 constexpr int TC_A_BLOCK = TC_ROWS * 128;    // bytes of one K block of A (hi or lo)
-constexpr int FW_STAGE_PITCH = 36;           // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
 
 struct FwdTcArgs {
     const float* S;
@@ -54,6 +53,17 @@ struct Bars {
     uint32_t tmem_base;
 };
 
+// Forward roles: warps 0-7 epilogue (warp w: TMEM lane quarter w & 3, 32-column chunk w >> 2), warp 8 MMA issuer,
+// warps 9-12 loaders.  (ncu, first version with 4 epilogue + 8 loader warps: the loaders sat idle 59 % of the time
+// waiting for the epilogue — bias/LeakyReLU/dropout RNG for 128 x 64 outputs per tile in 4 warps was the critical path.)
+constexpr int FW_EPI_WARPS = 8;
+constexpr int FW_LOAD_WARPS = 4;
+constexpr int FW_MMA_WARP = FW_EPI_WARPS;
+static_assert((FW_EPI_WARPS + 1 + FW_LOAD_WARPS) * 32 == TC_THREADS, "forward roles must fill the CTA");
+
+// 32 x 32 fp32 transposition buffer without padding: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
+__device__ __forceinline__ int stage_off(int r, int c) { return r * 32 + ((c ^ (r & 7)) << 2); }
+
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // operand tiles need 1024-byte alignment
@@ -66,24 +76,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     uint8_t* B_hi = A_lo + KB * TC_A_BLOCK;
     uint8_t* B_lo = B_hi + KB * b_block;
     float* bias_s = reinterpret_cast<float*>(B_lo + KB * b_block);
-    float* stage = bias_s + 64;                                           // [4 warps][32][FW_STAGE_PITCH]
-    Bars* bars = reinterpret_cast<Bars*>(stage + TC_EPI_WARPS * 32 * FW_STAGE_PITCH);
+    float* stage = bias_s + 64;                                           // [8 warps][32 x 32]
+    Bars* bars = reinterpret_cast<Bars*>(stage + FW_EPI_WARPS * 32 * 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-off setup: barriers, TMEM, weights ----------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < TC_MAX_KB; ++i) {
-            mbar_init(&bars->full[i], TC_LOAD_WARPS);
+            mbar_init(&bars->full[i], FW_LOAD_WARPS);
             mbar_init(&bars->empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tmem_full[i], 1);
-            mbar_init(&bars->tmem_empty[i], TC_EPI_WARPS);
+            mbar_init(&bars->tmem_empty[i], FW_EPI_WARPS);
         }
         fence_mbar_init();
     }
-    if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 128);          // 2 accumulators x 64 fp32 columns
+    if (warp == FW_MMA_WARP) tmem_alloc(&bars->tmem_base, 128);           // 2 accumulators x 64 fp32 columns
     // B[n][k] = wcat[k][n], split and swizzled (row n of K block kb: 32 values of k)
     for (int i = tid; i < d_out * KB * 8; i += TC_THREADS) {
         const int c = i & 7, n = (i >> 3) % d_out, kb = (i >> 3) / d_out;
@@ -105,73 +115,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
 
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-    if (warp < TC_EPI_WARPS) {
+    if (warp < FW_EPI_WARPS) {
         // ======================= epilogue =======================================================================
-        // TMEM lane = tile row, so a thread holds one row; bias + LeakyReLU + dropout are applied in that layout, then
-        // the 32x32 block goes through a per-warp transposition buffer so the global stores are coalesced.
+        // TMEM lane = tile row, so a thread holds one row of its chunk; bias + LeakyReLU + dropout are applied in that
+        // layout, then the 32x32 block goes through a per-warp transposition buffer so the stores are coalesced.
         const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
-        float* st = stage + warp * 32 * FW_STAGE_PITCH;
+        float* st = stage + warp * 32 * 32;
+        const int quarter = warp & 3, c = warp >> 2;                      // TMEM lanes 32*quarter.., columns 32*c..
         const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
+        const bool has_chunk = c * 32 < d_out;
+        const float inv_keep = 1.0f / (1.0f - a.mess_p);
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int buf = it & 1;
             mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 64;
-            const int64_t row_base = (int64_t)tile * TC_ROWS + warp * 32;
-            const int n_chunks = d_out / 32 + (d_out % 32 != 0);
-#pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c) {
-                float v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                if (c == n_chunks - 1) {                                  // accumulator drained: next tile may reuse it
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+            float v[32];
+            if (has_chunk) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 64 + c * 32, v);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);           // accumulator drained: next tile may reuse it
+            if (!has_chunk) continue;
+            const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
+            const int64_t my_row = row_base + lane;
+            uint32_t keep = 0xffffffffu;                                  // this row's 32 dropout decisions of the chunk
+            if (a.mess_bits && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float m = v[j + t] + bias_s[c * 32 + j + t];
+                    o[t] = m > 0.f ? m : a.slope * m;                                   // LeakyReLU, NGCF.py:140
                 }
-                const int64_t my_row = row_base + lane;
-                uint32_t keep = 0xffffffffu;                              // this row's 32 dropout decisions of the chunk
-                if (a.mess_bits && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
-                const float inv_keep = 1.0f / (1.0f - a.mess_p);
+                if (a.mess_bits) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float m = v[j + t] + bias_s[c * 32 + j + t];
-                        o[t] = m > 0.f ? m : a.slope * m;                               // LeakyReLU, NGCF.py:140
-                    }
-                    if (a.mess_bits) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) o[t] = (keep >> (j + t)) & 1u ? o[t] * inv_keep : 0.f;
-                    } else if (!a.mess_mult && a.mess_p > 0.f) {
-                        const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
-                        o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
-                    }
-                    st_f4(st + lane * FW_STAGE_PITCH + j, make_float4(o[0], o[1], o[2], o[3]));
+                    for (int t = 0; t < 4; ++t) o[t] = (keep >> (j + t)) & 1u ? o[t] * inv_keep : 0.f;
+                } else if (!a.mess_mult && a.mess_p > 0.f) {
+                    const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
+                    o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
                 }
-                __syncwarp();
-                float4 r4[8];
+                st_f4(st + stage_off(lane, j >> 2), make_float4(o[0], o[1], o[2], o[3]));
+            }
+            __syncwarp();
+            float4 r4[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + (i * 4 + rr) * FW_STAGE_PITCH + c4 * 4);
-                __syncwarp();
-                const int col = c * 32 + c4 * 4;
-                if (col < d_out) {
+            for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + stage_off(i * 4 + rr, c4));
+            __syncwarp();
+            const int col = c * 32 + c4 * 4;
+            if (col < d_out) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int64_t row = row_base + i * 4 + rr;
-                        if (row < a.n_rows) {
-                            if (a.mess_mult) {
-                                const float4 mm = ld_f4(a.mess_mult + row * d_out + col);
-                                r4[i].x *= mm.x; r4[i].y *= mm.y; r4[i].z *= mm.z; r4[i].w *= mm.w;
-                            }
-                            st_f4(a.E_out + row * d_out + col, r4[i]);
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t row = row_base + i * 4 + rr;
+                    if (row < a.n_rows) {
+                        if (a.mess_mult) {
+                            const float4 mm = ld_f4(a.mess_mult + row * d_out + col);
+                            r4[i].x *= mm.x; r4[i].y *= mm.y; r4[i].z *= mm.z; r4[i].w *= mm.w;
                         }
+                        st_f4(a.E_out + row * d_out + col, r4[i]);
                     }
                 }
             }
         }
-    } else if (warp == TC_EPI_WARPS) {
+    } else if (warp == FW_MMA_WARP) {
         // ======================= MMA issuer =====================================================================
         const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 0, 0);
         for (int it = 0; it < n_my; ++it) {
@@ -209,52 +215,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         }
     } else {
         // ======================= loaders ========================================================================
-        const int lt = tid - (TC_EPI_WARPS + 1) * 32;                     // 0 .. 255
-        constexpr int LT = TC_LOAD_WARPS * 32;
+        const int lt = tid - (FW_EPI_WARPS + 1) * 32;                     // 0 .. 127
+        constexpr int LT = FW_LOAD_WARPS * 32;
+        constexpr int Q = TC_ROWS * 8 / LT;                               // 16-byte chunks per thread per 32-column half
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int64_t row0 = (int64_t)tile * TC_ROWS;
-            float4 s[2][4], e[2][4];                                      // both 32-column halves in flight at once
+            for (int hh = 0; hh < KBH; ++hh) {
+                const int kb1 = hh, kb2 = KBH + hh;
+                float4 s[Q], e[Q];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {                             // 128 rows x 8 chunks = 4 per thread
+                for (int q = 0; q < Q; ++q) {
                     const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
                     const int64_t row = row0 + r;
-                    s[hh][q] = e[hh][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < a.n_rows && hh < KBH) {
-                        s[hh][q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
-                        e[hh][q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
+                    s[q] = e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < a.n_rows) {
+                        s[q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
+                        e[q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
                     }
                 }
-            }
+                mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
+                mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                if (hh < KBH) {
-                    const int kb1 = hh, kb2 = KBH + hh;
-                    mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
-                    mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
-                        const uint32_t off = sw128_offset(r, c);
-                        const float4 sv = s[hh][q], ev = e[hh][q];
-                        const float4 x1 = make_float4(sv.x + ev.x, sv.y + ev.y, sv.z + ev.z, sv.w + ev.w);
-                        const float4 x2 = make_float4(sv.x * ev.x, sv.y * ev.y, sv.z * ev.z, sv.w * ev.w);
-                        float4 hi, lo;
-                        split_tf32(x1, hi, lo);
-                        *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
-                        *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
-                        split_tf32(x2, hi, lo);
-                        *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
-                        *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&bars->full[kb1]);
-                        mbar_arrive(&bars->full[kb2]);
-                    }
+                for (int q = 0; q < Q; ++q) {
+                    const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
+                    const uint32_t off = sw128_offset(r, c);
+                    const float4 x1 = make_float4(s[q].x + e[q].x, s[q].y + e[q].y, s[q].z + e[q].z, s[q].w + e[q].w);
+                    const float4 x2 = make_float4(s[q].x * e[q].x, s[q].y * e[q].y, s[q].z * e[q].z, s[q].w * e[q].w);
+                    float4 hi, lo;
+                    split_tf32(x1, hi, lo);
+                    *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
+                    *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
+                    split_tf32(x2, hi, lo);
+                    *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
+                    *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->full[kb1]);
+                    mbar_arrive(&bars->full[kb2]);
                 }
             }
         }
@@ -262,12 +262,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) {
+    if (warp == FW_MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 128);
     }
 }
 
+}  // namespace
+namespace {
 
 // ====================================================================================================================
 // Backward of the same layer (row-local part), d_in = 64, as two kernels:
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
         }
     } else {
         // ======================= loaders: gM rows ====================================================================
-        // half a warp per row: lane owns the four columns 4*(lane & 15) .. +3 (one Philox call = exactly its four
+        // half a warp per row: lane owns the four columns 4*(lane & 15) .. +3 (one RNG call = exactly its four
         // dropout decisions, 128-bit loads and shared-memory stores); 8 row pairs in flight per warp
         const int lw = warp - (TC_EPI_WARPS + 1);                         // 0 .. 7
         const int hl = lane & 15, hsel = lane >> 4;
@@ -738,7 +740,7 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                 (int)ceil_div64(n_rows, TC_ROWS), row_offset};
     const int KB = 2 * d_in / 32;
     const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) +
-                        TC_EPI_WARPS * 32 * FW_STAGE_PITCH * sizeof(float) + sizeof(Bars);
+                        FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
     static bool attr_set = false;
     if (!attr_set) {
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

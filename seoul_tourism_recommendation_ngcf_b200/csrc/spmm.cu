@@ -119,25 +119,30 @@ struct BitsArgs {
     uint8_t* out_t;
 };
 
-__global__ void __launch_bounds__(SP_THREADS) dropout_bits_kernel(BitsArgs a) {
-    __shared__ int rp_s[SP_TILE_ROWS + 1];
+// One CTA covers BITS_TILES consecutive tiles (= one contiguous row range and one contiguous entry range): with a
+// CTA per 512-entry tile the pass was bound by the tile-info -> rowptr -> entries latency chain of ~6000 tiny CTAs.
+constexpr int BITS_THREADS = 256;
+constexpr int BITS_TILES = 8;
+__global__ void __launch_bounds__(BITS_THREADS) dropout_bits_kernel(BitsArgs a, int n_tiles) {
+    __shared__ int rp_s[BITS_TILES * SP_TILE_ROWS + 1];
     const int tid = threadIdx.x;
-    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
-    const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
-    const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
-    for (int i = tid; i <= nr; i += SP_THREADS) rp_s[i] = a.rowptr[ti.r0 + i] - ti.e0;
+    const int t0 = blockIdx.x * BITS_TILES, t1 = min(t0 + BITS_TILES, n_tiles) - 1;
+    const int4 first = *reinterpret_cast<const int4*>(a.tiles + t0);
+    const int4 last = *reinterpret_cast<const int4*>(a.tiles + t1);
+    const int r0 = first.x, nr = last.y - first.x, e0 = first.z, cnt = last.w - first.z;
+    for (int i = tid; i <= nr; i += BITS_THREADS) rp_s[i] = a.rowptr[r0 + i] - e0;
     __syncthreads();
     const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
-    for (int i = tid; i < cnt; i += SP_THREADS) {
-        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + ti.e0 + i).x;
+    for (int i = tid; i < cnt; i += BITS_THREADS) {
+        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + e0 + i).x;
         int lo = 0, hi = nr - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
         }
-        const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
-        if (a.out_f) a.out_f[ti.e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, r, c);
-        if (a.out_t) a.out_t[ti.e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, c, r);
+        const uint32_t r = (uint32_t)(a.row_key ? a.row_key[r0 + lo] : r0 + lo) + a.row_off;
+        if (a.out_f) a.out_f[e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, r, c);
+        if (a.out_t) a.out_t[e0 + i] = (uint8_t)node_keep_bits(a.p, seed, a.n_layers, c, r);
     }
 }
 
@@ -226,7 +231,7 @@ extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t 
     if (g->n_tiles > 0) {
         BitsArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
                    drop_p, seed, seed_dev, n_layers, (uint32_t)row_offset, bits_as_L, bits_as_Lt};
-        dropout_bits_kernel<<<(unsigned)g->n_tiles, SP_THREADS, 0, st>>>(a);
+        dropout_bits_kernel<<<(unsigned)ceil_div64(g->n_tiles, BITS_TILES), BITS_THREADS, 0, st>>>(a, g->n_tiles);
         NGCF_LAUNCH_OK("dropout_bits_kernel(rows)");
     }
     if (g->n_hub > 0 && g->n_chunk_tiles > 0) {
@@ -234,7 +239,7 @@ extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t 
                    reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, drop_p, seed, seed_dev, n_layers,
                    (uint32_t)row_offset, bits_as_L ? bits_as_L + g->rowptr_nnz : nullptr,
                    bits_as_Lt ? bits_as_Lt + g->rowptr_nnz : nullptr};
-        dropout_bits_kernel<<<(unsigned)g->n_chunk_tiles, SP_THREADS, 0, st>>>(a);
+        dropout_bits_kernel<<<(unsigned)ceil_div64(g->n_chunk_tiles, BITS_TILES), BITS_THREADS, 0, st>>>(a, g->n_chunk_tiles);
         NGCF_LAUNCH_OK("dropout_bits_kernel(hub chunks)");
     }
     return NGCF_OK;

@@ -6,7 +6,7 @@ several GPUs, so are the NCCL launches).  ``GraphedStep`` captures exactly those
 same kernels, same collectives — and replays them: per step the host does one pinned H2D copy of the index batch
 and one graph launch.  Gradients land in ``param.grad`` like after ``zero_grad(); loss.backward()``.
 
-Dropout stays fresh on every replay: the Philox key of a step is ``seed + *seed_dev`` (include/ngcf_b200.h) and the
+Dropout stays fresh on every replay: the RNG key of a step is ``seed + *seed_dev`` (include/ngcf_b200.h) and the
 graph bumps the device counter ``seed_dev`` itself.
 """
 from __future__ import annotations
@@ -41,7 +41,7 @@ class GraphedStep:
                     pos_item=f["pos_item"], neg_item=f["neg_item"], node_flag=self.node_flag)
         loss = self.criterion(u, p, n)
         loss.backward()
-        self.seed_dev.add_(0x9E3779B97F4A7C15 & (2 ** 62 - 1))        # next step: a different Philox key
+        self.seed_dev.add_(0x9E3779B97F4A7C15 & (2 ** 62 - 1))        # next step: a different RNG key
         return loss
 
     def _capture(self, year):
