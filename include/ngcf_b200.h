@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NGCF_B200_ABI_VERSION 2
+#define NGCF_B200_ABI_VERSION 3
 #define NGCF_MAX_LAYERS 8
 #define NGCF_MAX_WIDTH 128          /* widest embedding / layer size the kernels accept */
 
@@ -117,6 +117,9 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
  *               this CSR holds L^T, so both directions drop the same entries of L.
  *               seed_dev: optional device uint64 added to seed (graph-replay safe).
  *   keep_bits : optional output of ngcf_node_dropout_bits for this direction; when given, drop_p/seed are unused.
+ *   c_ent/c_trp: optional output of ngcf_node_dropout_compact for this direction AND layer (the step's surviving
+ *               entries, compacted per tile); when given, keep_bits/drop_p/seed are unused and only survivors are
+ *               staged and gathered.
  *   row_offset: global index of row 0 of this CSR.  RNG keys use global coordinates, so a row shard (rows
  *               [row_offset, row_offset + n_rows) of L, all columns) draws exactly the single-GPU decisions. */
 int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
@@ -124,7 +127,8 @@ int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
               const int32_t* slot, const float* gsum, int64_t ld_gsum,
               float* hub_partial,
               float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
-              const uint8_t* keep_bits, float* Y, int64_t ldy, void* stream);
+              const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_trp,
+              float* Y, int64_t ldy, void* stream);
 
 /* One step's node-dropout decisions for every entry and every layer at once (bit k of a byte = the entry survives
  * layer k; cumulative).  Entry order = ent then hub_ent.  bits_as_L: this CSR read as L (keys (row, col));
@@ -133,6 +137,18 @@ int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
  * entry (same decisions, ~10 us less per product at Gowalla shape). */
 int ngcf_node_dropout_bits(const ngcf_csr* csr_host, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                            int n_layers, int64_t row_offset, uint8_t* bits_as_L, uint8_t* bits_as_Lt, void* stream);
+
+/* The same decisions applied the way the reference applies them (NGCF.sparse_dropout, NGCF.py:93-100, DELETES the
+ * dropped entries, cumulatively over the layers): one pass per step writes, for every layer k and for the CSR read
+ * as L and/or as L^T, the surviving (col, value) pairs of each SpMM tile {r0,r1,e0,e1} compacted in their original
+ * order at [e0, e0 + kept) of ent_*[k] (int32[2*nnz], indexed like ent then hub_ent) and the tile-relative row
+ * pointers trp_*[k][tile * (ngcf_spmm_tile_rows()+1) + i], i = 0..r1-r0 (tiles first, then chunk_tiles).
+ * ent_*_host / trp_*_host are HOST arrays of n_layers device pointers; pass NULL for a direction that is not needed.
+ * Products given these arrays gather only the survivors: (1-p)^(k+1) of the entries at layer k. */
+int ngcf_node_dropout_compact(const ngcf_csr* csr_host, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                              int n_layers, int64_t row_offset,
+                              int32_t* const* ent_as_L_host, int32_t* const* trp_as_L_host,
+                              int32_t* const* ent_as_Lt_host, int32_t* const* trp_as_Lt_host, void* stream);
 
 /* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
  * pack:  wcat[k, o] = W1[o,k] (k < d_in), W2[o,k-d_in] (k >= d_in);  bias_eff = 2*b1 + b2

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.distributed as dist
 
 from . import _lib
-from .plan import LaplacianPlan, node_dropout_bits, spmm
+from .plan import LaplacianPlan, node_dropout_bits, node_dropout_compact, spmm
 from .sharded import RowShards, all_gather_rows
 
 LEAKY_SLOPE = 0.2   # NGCF.py:140
@@ -28,7 +28,7 @@ def _stream() -> int:
 
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
-    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "mess_bits",
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
                  "rows", "offsets", "W1", "W2")
 
 
@@ -52,14 +52,20 @@ class _Propagate(torch.autograd.Function):
         X0 = mod._packed_table()                                       # [N(_pad), d0] = cat(user, item), NGCF.py:120
         st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
-        st.bits_f = st.bits_b = None
+        st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
         if st.drop_p > 0:
-            # this step's node-dropout decisions for all K layers, drawn once (one byte per entry) instead of a hash
-            # evaluation per entry in each of the 2K products; a symmetric L serves both directions from one pass
+            # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
+            # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
+            # deletes the dropped entries like NGCF.sparse_dropout does, so layer k gathers (1-p)^(k+1) of the rows
             shared = st.plan.side(True, False) is side
-            st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
-            if shared:
-                st.bits_b = bt
+            if mod._node_mode == "compact":
+                st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
+                if shared:
+                    st.comp_b = ct
+            elif mod._node_mode == "bits":
+                st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
+                if shared:
+                    st.bits_b = bt
         # message dropout (NGCF.py:142): optionally this step's decisions for every layer, one bit per element, drawn
         # by a full-GPU pass instead of inside the dense kernels (measured slower at Gowalla shape: off by default)
         self_uses_mess_bits = mod._mess_bits
@@ -75,7 +81,8 @@ class _Propagate(torch.autograd.Function):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
             S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
-                     row_offset=r0, keep_bits=st.bits_f)                                     # NGCF.py:124-130
+                     row_offset=r0, keep_bits=st.bits_f,
+                     compact=st.comp_f[k] if st.comp_f is not None else None)               # NGCF.py:124-130
             wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
             bias = torch.empty(d_out, dtype=torch.float32, device=dev)
             _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
@@ -140,7 +147,9 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
-        if st.drop_p > 0 and st.bits_b is None:
+        if st.drop_p > 0 and mod._node_mode == "compact" and st.comp_b is None:
+            _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
+        if st.drop_p > 0 and mod._node_mode == "bits" and st.bits_b is None:
             _, st.bits_b = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         gE_next = None
         col_off = D
@@ -170,7 +179,8 @@ class _Propagate(torch.autograd.Function):
             last = (k == 0)
             gE_next = spmm(side, vals, gS_all, d_in, addend=gEl, slot=slot_loc if last else None,
                            gsum=gsum if last else None, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
-                           transposed=True, row_offset=r0, keep_bits=st.bits_b)   # gE_k = gEl + L^T gS (+ row grads)
+                           transposed=True, row_offset=r0, keep_bits=st.bits_b,
+                           compact=st.comp_b[k] if st.comp_b is not None else None)   # gE_k = gEl + L^T gS (+ row grads)
             if mod._trace is not None:                                # debugging aid: per-layer backward tensors
                 mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
@@ -233,6 +243,7 @@ class NGCF(nn.Module):
         self._last = None
         self._all_E = None
         self._mess_bits = False  # precompute message-dropout bits per step (ngcf_mess_dropout_bits)
+        self._node_mode = "compact"   # device-RNG node dropout: "compact" (survivors only), "bits", or "inkernel"
         self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None

@@ -42,7 +42,9 @@ SIGNATURES = {
                          _vp, _vp],
     "ngcf_spmm_split_threshold": [],
     "ngcf_spmm": [_csr_p, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _i64,
-                  _vp, _vp, _i64, _vp],
+                  _vp, _vp, _vp, _vp, _i64, _vp],
+    "ngcf_node_dropout_compact": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                  C.POINTER(_vp), _vp],
     "ngcf_node_dropout_bits": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp, _vp],
     "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
     "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32, _u64, _vp, C.c_int, _i64, _vp,

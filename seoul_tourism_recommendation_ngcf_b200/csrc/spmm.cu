@@ -42,6 +42,8 @@ struct SpmmArgs {
     int transposed;
     uint32_t row_off;
     const uint8_t* bits;
+    const int2* cent;               // optional: this layer's compacted entries (ngcf_node_dropout_compact), tile t at e0
+    const int32_t* ctrp;            // ... and its tile-relative row pointers [n_tiles][SP_TILE_ROWS + 1]
 };
 
 struct CtaSync {
@@ -58,9 +60,18 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
     DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
                 a.row_off, a.bits};
-    stage_tile<SP_THREADS>(ti, a.rowptr, a.ent, a.row_key, dr, rp_s, ent_s, tid, CtaSync());
-
     const int nr = ti.r1 - ti.r0;
+    if (a.ctrp) {
+        // node dropout already applied for this step and layer: the tile's surviving entries sit compacted at e0
+        const int32_t* trp = a.ctrp + (size_t)blockIdx.x * (SP_TILE_ROWS + 1);
+        for (int i = tid; i <= nr; i += SP_THREADS) rp_s[i] = trp[i];
+        const int cnt = trp[nr];
+        for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(a.cent + ti.e0 + i);
+        __syncthreads();
+    } else {
+        stage_tile<SP_THREADS>(ti, a.rowptr, a.ent, a.row_key, dr, rp_s, ent_s, tid, CtaSync());
+    }
+
     for (int i = warp; i < nr; i += SP_WARPS) {
         const int64_t row = ti.r0 + i;
         const int h = a.hub_of_row ? a.hub_of_row[row] : -1;
@@ -146,6 +157,120 @@ __global__ void __launch_bounds__(BITS_THREADS) dropout_bits_kernel(BitsArgs a, 
     }
 }
 
+// ---- per-step node-dropout compaction -----------------------------------------------------------------------------
+// The reference's sparse_dropout (NGCF.py:93-100) DELETES the dropped entries, cumulatively over the layers, so its
+// layer-k product walks only (1-p)^(k+1) of the Laplacian.  One pass per step does the same for every layer and both
+// directions at once: the surviving entries of tile t are written, in their original order, to the front of the
+// tile's own slot range [e0, e1) of a per-(direction, layer) entry array, with the tile-relative row pointers next to
+// them.  The products then stage and gather the survivors only (same sums bit for bit: a dropped entry contributed
+// +0.0), which at p = 0.3 halves the gathered bytes of a 3-layer step.
+struct CompactArgs {
+    const TileInfo* tiles;
+    const int32_t* rowptr;
+    const int2* ent;
+    const int32_t* row_key;
+    float p;
+    uint64_t seed;
+    const uint64_t* seed_dev;
+    int n_layers;
+    uint32_t row_off;
+    int2* out_ent[2][NGCF_MAX_LAYERS];       // [0] keyed (row, col) = this CSR read as L, [1] keyed (col, row) = as L^T
+    int32_t* out_trp[2][NGCF_MAX_LAYERS];    // NULL: direction/layer not wanted
+};
+
+constexpr int CP_THREADS = 128;
+constexpr int CP_PER = SP_TILE_ENT / CP_THREADS;     // consecutive entries per thread
+static_assert(CP_PER * CP_THREADS == SP_TILE_ENT, "tile entries must split evenly over the compaction CTA");
+
+// combo c = dir * n_layers + layer keeps a 16-bit counter in word c >> 2 at bit 16 * (c & 3) (counts <= 512)
+template <int NW>
+__global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
+    __shared__ int rp_s[SP_TILE_ROWS + 1];
+    __shared__ uint64_t pre_s[NW][SP_TILE_ENT + 1];  // kept entries before entry i, per combo
+    __shared__ uint64_t wtot_s[NW][CP_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
+    const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
+    const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
+    const int K = a.n_layers;
+    for (int i = tid; i <= nr; i += CP_THREADS) rp_s[i] = a.rowptr[ti.r0 + i] - ti.e0;
+    const int base = tid * CP_PER;
+    int2 e[CP_PER];
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+        e[q] = make_int2(0, 0);
+        if (base + q < cnt) e[q] = ld_stream_i2(a.ent + ti.e0 + base + q);
+    }
+    __syncthreads();
+    const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
+    const bool want_l = a.out_ent[0][0] != nullptr, want_t = a.out_ent[1][0] != nullptr;
+    uint32_t keep[CP_PER];                            // bits [0, K): as L, bits [K, 2K): as L^T  (= combo index)
+    uint64_t mine[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mine[w] = 0;
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+        keep[q] = 0;
+        const int i = base + q;
+        if (i < cnt) {
+            int lo = 0, hi = nr - 1;                  // last row with rp_s[row] <= i
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
+            const uint32_t c = (uint32_t)e[q].x;
+            if (want_l) keep[q] = node_keep_bits(a.p, seed, K, r, c);
+            if (want_t) keep[q] |= node_keep_bits(a.p, seed, K, c, r) << K;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            for (uint32_t m = (keep[q] >> (4 * w)) & 0xfu; m; m &= m - 1) mine[w] += 1ull << (16 * (__ffs(m) - 1));
+    }
+    uint64_t run[NW];                                 // exclusive prefix of this thread's first entry
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        uint64_t inc = mine[w];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint64_t v = __shfl_up_sync(FULL_MASK, inc, off);
+            if (lane >= off) inc += v;
+        }
+        if (lane == 31) wtot_s[w][warp] = inc;
+        run[w] = inc - mine[w];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        for (int j = 0; j < warp; ++j) run[w] += wtot_s[w][j];
+#pragma unroll
+    for (int q = 0; q < CP_PER; ++q) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) pre_s[w][base + q] = run[w];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            for (uint32_t m = (keep[q] >> (4 * w)) & 0xfu; m; m &= m - 1) {
+                const int c4 = __ffs(m) - 1, c = 4 * w + c4;
+                const int dir = c >= K, layer = dir ? c - K : c;
+                const int pos = (int)((run[w] >> (16 * c4)) & 0xffffu);
+                a.out_ent[dir][layer][ti.e0 + pos] = e[q];
+                run[w] += 1ull << (16 * c4);
+            }
+    }
+    if (tid == CP_THREADS - 1) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) pre_s[w][SP_TILE_ENT] = run[w];
+    }
+    __syncthreads();
+    const int n_combo = 2 * K;
+    for (int j = tid; j < (nr + 1) * n_combo; j += CP_THREADS) {
+        const int c = j / (nr + 1), i = j - c * (nr + 1);
+        const int dir = c >= K, layer = dir ? c - K : c;
+        int32_t* trp = a.out_trp[dir][layer];
+        if (trp) trp[(size_t)blockIdx.x * (SP_TILE_ROWS + 1) + i] = (int)((pre_s[c >> 2][rp_s[i]] >> (16 * (c & 3))) & 0xffffu);
+    }
+}
+
 template <int G>
 int launch(const SpmmArgs& a, int n_tiles, cudaStream_t st, const char* what) {
     if (n_tiles <= 0) return NGCF_OK;
@@ -186,7 +311,8 @@ int ngcf_check_csr(const ngcf_csr* g, const char* who) {
 extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
                          const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial, float drop_p,
                          uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
-                         const uint8_t* keep_bits, float* Y, int64_t ldy, void* stream) {
+                         const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_trp, float* Y, int64_t ldy,
+                         void* stream) {
     int rc = ngcf_check_csr(g, "spmm");
     if (rc != NGCF_OK) return rc;
     NGCF_REQUIRE(X && Y, "spmm: null pointer");
@@ -196,6 +322,7 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     NGCF_REQUIRE(layer >= 0 && layer < NGCF_MAX_LAYERS, "spmm: layer %d", layer);
     NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "spmm: row_offset %lld", (long long)row_offset);
     NGCF_REQUIRE(!slot || gsum, "spmm: slot given without gsum");
+    NGCF_REQUIRE((c_ent == nullptr) == (c_trp == nullptr), "spmm: c_ent and c_trp go together");
     NGCF_REQUIRE(g->n_hub == 0 || hub_partial, "spmm: hub_partial scratch missing");
     NGCF_REQUIRE(g->n_tiles == 0 || g->tiles, "spmm: SpMM tiles missing");
     NGCF_REQUIRE(g->n_chunk_tiles == 0 || g->chunk_tiles, "spmm: chunk tiles missing");
@@ -208,13 +335,15 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
         SpmmArgs h{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
                    reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, nullptr, nullptr, nullptr, X,
                    (uint32_t)ldx, d, nullptr, 0, nullptr, nullptr, 0, hub_partial, d, drop_p, seed, seed_dev, layer,
-                   transposed, (uint32_t)row_offset, keep_bits ? keep_bits + g->rowptr_nnz : nullptr};
+                   transposed, (uint32_t)row_offset, keep_bits ? keep_bits + g->rowptr_nnz : nullptr,
+                   c_ent ? reinterpret_cast<const int2*>(c_ent) + g->rowptr_nnz : nullptr,
+                   c_trp ? c_trp + (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : nullptr};
         if ((rc = launch_any(h, g->n_chunk_tiles, vec, st, "spmm_tile_kernel(hub chunks)")) != NGCF_OK) return rc;
     }
     SpmmArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
                g->n_hub > 0 ? g->hub_of_row : nullptr, g->hub_chunk_ptr, hub_partial, X, (uint32_t)ldx, d, addend,
                ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed, (uint32_t)row_offset,
-               keep_bits};
+               keep_bits, reinterpret_cast<const int2*>(c_ent), c_trp};
     return launch_any(a, g->n_tiles, vec, st, "spmm_tile_kernel(rows)");
 }
 
@@ -241,6 +370,53 @@ extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t 
                    bits_as_Lt ? bits_as_Lt + g->rowptr_nnz : nullptr};
         dropout_bits_kernel<<<(unsigned)ceil_div64(g->n_chunk_tiles, BITS_TILES), BITS_THREADS, 0, st>>>(a, g->n_chunk_tiles);
         NGCF_LAUNCH_OK("dropout_bits_kernel(hub chunks)");
+    }
+    return NGCF_OK;
+}
+
+extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                         int n_layers, int64_t row_offset, int32_t* const* ent_as_L_host,
+                                         int32_t* const* trp_as_L_host, int32_t* const* ent_as_Lt_host,
+                                         int32_t* const* trp_as_Lt_host, void* stream) {
+    int rc = ngcf_check_csr(g, "node_dropout_compact");
+    if (rc != NGCF_OK) return rc;
+    NGCF_REQUIRE(drop_p > 0.f && drop_p < 1.f, "node_dropout_compact: drop_p %f not in (0,1)", drop_p);
+    NGCF_REQUIRE(n_layers >= 1 && n_layers <= NGCF_MAX_LAYERS, "node_dropout_compact: n_layers %d", n_layers);
+    NGCF_REQUIRE((ent_as_L_host && trp_as_L_host) || (ent_as_Lt_host && trp_as_Lt_host), "node_dropout_compact: no output");
+    NGCF_REQUIRE((ent_as_L_host == nullptr) == (trp_as_L_host == nullptr) &&
+                 (ent_as_Lt_host == nullptr) == (trp_as_Lt_host == nullptr), "node_dropout_compact: ent/trp go together");
+    NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "node_dropout_compact: row_offset");
+    for (int k = 0; k < n_layers; ++k) {
+        NGCF_REQUIRE(!ent_as_L_host || (ent_as_L_host[k] && trp_as_L_host[k]), "node_dropout_compact: null L output %d", k);
+        NGCF_REQUIRE(!ent_as_Lt_host || (ent_as_Lt_host[k] && trp_as_Lt_host[k]), "node_dropout_compact: null L^T output %d", k);
+    }
+    cudaStream_t st = as_stream(stream);
+    // pass 0: ordinary rows; pass 1: hub chunks (entry arrays continue after rowptr_nnz, tile arrays after n_tiles)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n_tiles = pass ? g->n_chunk_tiles : g->n_tiles;
+        if (n_tiles <= 0 || (pass && g->n_hub == 0)) continue;
+        CompactArgs a{};
+        a.tiles = reinterpret_cast<const TileInfo*>(pass ? g->chunk_tiles : g->tiles);
+        a.rowptr = pass ? g->chunk_ptr : g->rowptr;
+        a.ent = reinterpret_cast<const int2*>(pass ? g->hub_ent : g->ent);
+        a.row_key = pass ? g->chunk_row : nullptr;
+        a.p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.n_layers = n_layers; a.row_off = (uint32_t)row_offset;
+        const size_t e_off = pass ? (size_t)g->rowptr_nnz : 0, t_off = pass ? (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : 0;
+        for (int k = 0; k < n_layers; ++k) {
+            if (ent_as_L_host) {
+                a.out_ent[0][k] = reinterpret_cast<int2*>(ent_as_L_host[k]) + e_off;
+                a.out_trp[0][k] = trp_as_L_host[k] + t_off;
+            }
+            if (ent_as_Lt_host) {
+                a.out_ent[1][k] = reinterpret_cast<int2*>(ent_as_Lt_host[k]) + e_off;
+                a.out_trp[1][k] = trp_as_Lt_host[k] + t_off;
+            }
+        }
+        const int nw = (2 * n_layers + 3) / 4;
+        if (nw <= 1) compact_kernel<1><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        else if (nw == 2) compact_kernel<2><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        else compact_kernel<4><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        NGCF_LAUNCH_OK(pass ? "compact_kernel(hub chunks)" : "compact_kernel(rows)");
     }
     return NGCF_OK;
 }

@@ -225,9 +225,41 @@ def node_dropout_bits(side: CsrSide, drop_p: float, seed: int, seed_dev, n_layer
     return bl, bt
 
 
+def node_dropout_compact(side: CsrSide, drop_p: float, seed: int, seed_dev, n_layers: int, row_offset: int = 0,
+                         as_L: bool = True, as_Lt: bool = False):
+    """One step's node dropout applied like the reference does it (entries deleted, cumulatively per layer,
+    NGCF.py:93-100): per layer the surviving entries of every SpMM tile, compacted, for ``side`` read as L and/or as
+    L^T.  Returns (per-layer list of (ent, trp) or None, same for L^T); pass one pair to ``spmm(compact=...)``."""
+    lib = _lib.load()
+    dev = side.rowptr.device
+    n_t = int(side.tiles.shape[0]) + (int(side.chunk_tiles.shape[0]) if side.chunk_tiles is not None else 0)
+    per = lib.ngcf_spmm_tile_rows() + 1
+
+    def alloc():
+        return [(torch.empty(side.nnz + 2, 2, dtype=torch.int32, device=dev),
+                 torch.empty(n_t * per, dtype=torch.int32, device=dev)) for _ in range(n_layers)]
+
+    cl = alloc() if as_L else None
+    ct = alloc() if as_Lt else None
+
+    def arrs(c):
+        if c is None:
+            return None, None
+        return _lib.ptr_array([e for e, _ in c]), _lib.ptr_array([t for _, t in c])
+
+    el, tl = arrs(cl)
+    et, tt = arrs(ct)
+    _lib.check(lib.ngcf_node_dropout_compact(C.byref(side.descriptor(None)), float(drop_p), int(seed) & (2 ** 64 - 1),
+                                             _lib.ptr(seed_dev), int(n_layers), int(row_offset), el, tl, et, tt,
+                                             _stream()), "node_dropout_compact")
+    return cl, ct
+
+
 def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=None, drop_p: float = 0.0,
-         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0, keep_bits=None):
-    """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout."""
+         seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0, keep_bits=None,
+         compact=None):
+    """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout;
+    compact = this layer's (ent, trp) pair from node_dropout_compact."""
     lib = _lib.load()
     if out is None:
         out = torch.empty(side.n_rows, d, dtype=torch.float32, device=X.device)
@@ -236,5 +268,8 @@ def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=N
                              _lib.ptr(slot), _lib.ptr(gsum), gsum.stride(0) if gsum is not None else 0,
                              _lib.ptr(side.hub_partial(d)),
                              float(drop_p), int(seed) & (2 ** 64 - 1), _lib.ptr(seed_dev), int(layer), int(transposed),
-                             int(row_offset), _lib.ptr(keep_bits), out.data_ptr(), out.stride(0), _stream()), "spmm")
+                             int(row_offset), _lib.ptr(keep_bits),
+                             _lib.ptr(compact[0]) if compact is not None else None,
+                             _lib.ptr(compact[1]) if compact is not None else None,
+                             out.data_ptr(), out.stride(0), _stream()), "spmm")
     return out

@@ -268,6 +268,28 @@ def test_device_rng_dropout_statistics_and_consistency():
     assert torch.equal(spmm(ps.fwd, None, eye, 128, layer=0, transposed=True, keep_bits=bt), m0.T)
     _, bt2 = node_dropout_bits(ps.bwd, 0.3, 1234, None, 3, as_L=False, as_Lt=True)
     assert torch.equal(spmm(ps.bwd, None, eye, 128, layer=0, transposed=True, keep_bits=bt2), m0.T)
+    # ... and so are the per-step compacted survivors (ngcf_node_dropout_compact): only they are staged and gathered
+    from seoul_tourism_recommendation_ngcf_b200.plan import node_dropout_compact
+    cl, ct = node_dropout_compact(ps.fwd, 0.3, 1234, None, 3, as_L=True, as_Lt=True)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, compact=cl[0]), m0)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, compact=cl[2]), m2)
+    assert torch.equal(spmm(ps.fwd, None, eye, 128, transposed=True, compact=ct[0]), m0.T)
+    _, ct2 = node_dropout_compact(ps.bwd, 0.3, 1234, None, 3, as_L=False, as_Lt=True)
+    assert torch.equal(spmm(ps.bwd, None, eye, 128, transposed=True, compact=ct2[2]), m2.T)
+    from seoul_tourism_recommendation_ngcf_b200 import _lib
+    per = _lib.load().ngcf_spmm_tile_rows() + 1
+    tiles = ps.fwd.tiles.cpu().numpy()
+    for k, frac in ((0, 0.7), (2, 0.343)):                       # survivors per tile = what the bits say, in order
+        trp = cl[k][1].cpu().numpy().reshape(-1, per)
+        ent_c, ent_o = cl[k][0].cpu().numpy(), ps.fwd.ent.cpu().numpy()
+        keep = ((bl.cpu().numpy() >> k) & 1).astype(bool)
+        kept = 0
+        for t, (r0, r1, e0, e1) in enumerate(tiles):
+            n = trp[t, r1 - r0]
+            assert trp[t, 0] == 0 and (np.diff(trp[t, :r1 - r0 + 1]) >= 0).all() and n == keep[e0:e1].sum()
+            assert (ent_c[e0:e0 + n] == ent_o[e0:e1][keep[e0:e1]]).all()
+            kept += n
+        assert abs(kept / max(1, tiles[-1][3]) - frac) < 0.05
     m0b = spmm(ps.fwd, None, eye, 128, drop_p=0.3, seed=99, layer=0)
     assert not torch.equal(m0b, m0)
     sd = torch.tensor([1234 - 99], dtype=torch.int64, device=DEV)   # device-side seed offset (graph replay path)
@@ -558,3 +580,32 @@ def test_precomputed_message_dropout_bits_equal_in_kernel_decisions():
     assert torch.equal(res[0][0], res[1][0])
     for k in res[0][1]:
         assert rel_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) <= 1e-6, k
+
+
+def test_node_dropout_modes_agree():
+    """Device-RNG node dropout evaluated in-kernel, from per-step decision bytes, or as per-step compacted survivor
+    lists (the default): one set of decisions, identical sums (hub rows included), forward and backward."""
+    n_user, n_item, B = 900, 600, 256
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, 40000, seed=3)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    nd = synth.num_dict_for(n_user, n_item)
+    b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=4).items()}
+    res = {}
+    for mode in ("inkernel", "bits", "compact"):
+        torch.manual_seed(0)
+        m = pkg.NGCF(64, [64, 64, 64], 0.3, [0.1] * 3, 1.0, [L, L], nd, B, torch.device("cpu")).to(DEV)
+        m._node_mode = mode
+        m.train()
+        torch.manual_seed(5)
+        uu, pp, nn_ = _call(m, b, True)
+        assert m._last.plan.fwd.n_hub > 0
+        loss = pkg.BPR(0.025, B)(uu, pp, nn_)
+        loss.backward()
+        res[mode] = [uu.detach().clone(), pp.detach().clone(), loss.detach().clone()] + \
+                    [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    for a, b_ in zip(res["bits"], res["inkernel"]):
+        assert torch.equal(a, b_)
+    # compaction shifts an entry's position inside its row, hence its lane group in the row sum: same terms,
+    # different fp32 summation tree
+    for a, b_ in zip(res["compact"], res["inkernel"]):
+        assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) <= 2e-6

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from seoul_tourism_recommendation_ngcf_b200 import _lib
-from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, node_dropout_bits, spmm
+from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, node_dropout_bits, node_dropout_compact, spmm
 
 shape = sys.argv[1] if len(sys.argv) > 1 else "gowalla"
 L, batches, info = bench.make_workload(shape)
@@ -45,6 +45,11 @@ t("spmm (no dropout)", lambda: spmm(plan.fwd, None, X, d, out=Y))
 t("spmm (in-kernel Philox dropout)", lambda: spmm(plan.fwd, None, X, d, out=Y, drop_p=0.3, seed=1, layer=1))
 t("spmm (precomputed dropout bits)", lambda: spmm(plan.fwd, None, X, d, out=Y, layer=1, keep_bits=bl))
 t("spmm transposed + addend (bits)", lambda: spmm(plan.fwd, None, X, d, out=Y, addend=S, layer=1, transposed=True, keep_bits=bt))
+cl, ct = node_dropout_compact(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True)
+for k in range(3):
+    t(f"spmm (compacted survivors, layer {k})", lambda: spmm(plan.fwd, None, X, d, out=Y, compact=cl[k]))
+t("spmm transposed + addend (compacted, layer 1)", lambda: spmm(plan.fwd, None, X, d, out=Y, addend=S, transposed=True, compact=ct[1]))
+t("node_dropout_compact (L and L^T, 3 layers)", lambda: node_dropout_compact(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True))
 t("node_dropout_bits (L and L^T)", lambda: node_dropout_bits(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True))
 t("dense_fwd (mess_p 0.1)", lambda: lib.ngcf_dense_fwd(S.data_ptr(), X.data_ptr(), N, d, d, wcat.data_ptr(), bias.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, Y.data_ptr(), st))
 t("dense_fwd (no dropout)", lambda: lib.ngcf_dense_fwd(S.data_ptr(), X.data_ptr(), N, d, d, wcat.data_ptr(), bias.data_ptr(), 0.2, None, None, 0.0, 1, None, 0, 0, Y.data_ptr(), st))
