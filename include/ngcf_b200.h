@@ -198,13 +198,23 @@ int ngcf_bpr_fwd_bwd(const float* u, const float* p, const float* n, int64_t bat
 int ngcf_rowgrad_scatter(const int64_t* const* rows_host, const int64_t* offsets_host,
                          const float* const* g_host, const int64_t* batch_host, int n_sets, int D,
                          int32_t* slot, float* gsum, void* stream);
+/* In place, for every distinct row r of the sets (its slot s = slot[r]) and every block k >= 1 of the output row
+ * (widths dims_host[k], layer k's stored E'_k in layers_host[k], as in ngcf_gather_concat):
+ *   gsum[s, block k] <- (gH - H (H.gH)) / n,   n = max(||E'_k[r]||, 1e-12), H = E'_k[r] / n
+ * i.e. the backward of F.normalize (NGCF.py:144) for the <= 3B rows that have an output-row gradient at all, done once
+ * instead of inside every row tile of ngcf_dense_bwd (which is then called with gh_normalized = 1). */
+int ngcf_rowgrad_normalize(const int64_t* const* rows_host, const int64_t* offsets_host,
+                           const int64_t* batch_host, int n_sets, const float* const* layers_host,
+                           const int* dims_host, int n_layers_plus1, const int32_t* slot, float* gsum, int D,
+                           void* stream);
 int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_host,
                        const int64_t* batch_host, int n_sets, int32_t* slot, void* stream);
 
 /* ---- row-local backward of one layer (AddmmBackward/LeakyReluBackward/normalize backward) -----------
  * With gH = gsum[slot[i], col_off .. col_off+d_out) (0 when slot[i] < 0), n = max(||E_out[i]||,1e-12),
  * H = E_out[i]/n:
- *   gE' = gE_next[i] (0 if NULL) + (gH - H (H.gH)) / n
+ *   gE' = gE_next[i] (0 if NULL) + (gH - H (H.gH)) / n       (gh_normalized != 0: + gH as it is, see
+ *                                                            ngcf_rowgrad_normalize)
  *   gM  = gE' * mess_mult * (E_out > 0 ? 1 : slope)         (sign(E_out) = sign(M); dropped -> 0)
  *   gS[i]  = gM·W1 + (gM·W2) * E[i]      gEl[i] = gM·W1 + (gM·W2) * S[i]
  *   gW1 += gM^T (S+E)   gb1 += 2 colsum(gM)   gW2 += gM^T (S*E)   gb2 += colsum(gM)   (atomic accumulate
@@ -215,8 +225,8 @@ int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,
                    const float* mess_mult, const uint32_t* mess_bits, float mess_p, uint64_t seed,
-                   const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl, float* gW1,
-                   float* gb1, float* gW2, float* gb2, float* gM_scratch, void* stream);
+                   const uint64_t* seed_dev, int layer, int64_t row_offset, int gh_normalized, float* gS, float* gEl,
+                   float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, void* stream);
 
 /* ---- scoring: demo.py:234-235, experiment.py:93,104,109 ----------------------------------------------
  * scores = U·I^T without materialising them; per user row the k largest (descending; ties by lower item

@@ -8,6 +8,7 @@ Everything numerical runs in libngcf_b200.so; there is no PyTorch/CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -135,6 +136,9 @@ class _Propagate(torch.autograd.Function):
         gsum = torch.empty(sum(batch), D, dtype=torch.float32, device=dev)
         _lib.check(lib.ngcf_rowgrad_scatter(rows_h, offs_h, g_h, batch_h, n_sets, D, slot.data_ptr(),
                                             gsum.data_ptr(), _stream()), "rowgrad_scatter")
+        # F.normalize's backward (NGCF.py:144) for the <= 3B rows that carry an output-row gradient, once, in place
+        _lib.check(lib.ngcf_rowgrad_normalize(rows_h, offs_h, batch_h, n_sets, _lib.ptr_array(st.E), _lib.int_array(dims),
+                                              K + 1, slot.data_ptr(), gsum.data_ptr(), D, _stream()), "rowgrad_normalize")
         slot_loc = slot[r0:r0 + nloc]
         sizes = [dims[k + 1] * dims[k] for k in range(K)]
         flat = torch.zeros(2 * sum(sizes) + 2 * sum(dims[1:]), dtype=torch.float32, device=dev)
@@ -166,7 +170,7 @@ class _Propagate(torch.autograd.Function):
                                           st.W1[k].data_ptr(), st.W2[k].data_ptr(), LEAKY_SLOPE,
                                           _lib.ptr(mm[r0:r0 + nloc] if mm is not None else None),
                                           _lib.ptr(st.mess_bits[k]), float(st.mess_p[k]), st.seed,
-                                          _lib.ptr(st.seed_dev), k, r0, gS.data_ptr(),
+                                          _lib.ptr(st.seed_dev), k, r0, 1, gS.data_ptr(),
                                           gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           gM_scratch.data_ptr(), _stream()), "dense_bwd")
@@ -242,7 +246,7 @@ class NGCF(nn.Module):
         self._winner = None
         self._last = None
         self._all_E = None
-        self._mess_bits = False  # precompute message-dropout bits per step (ngcf_mess_dropout_bits)
+        self._mess_bits = os.environ.get("NGCF_B200_MESS_BITS", "0") == "1"   # precompute message-dropout bits per step
         self._node_mode = "compact"   # device-RNG node dropout: "compact" (survivors only), "bits", or "inkernel"
         self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called

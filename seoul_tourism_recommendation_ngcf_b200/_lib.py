@@ -56,7 +56,9 @@ SIGNATURES = {
                              _vp, _vp],
     "ngcf_rowgrad_reset": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, _vp, _vp],
     "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32,
-                       _u64, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                       _u64, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngcf_rowgrad_normalize": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, C.POINTER(_vp),
+                               C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, _vp],
     "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.POINTER(_sz)],
     "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],
 }

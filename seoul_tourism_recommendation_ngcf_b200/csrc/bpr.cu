@@ -133,6 +133,40 @@ __global__ void rowgrad_accum_kernel(RowSets s, int D, const int32_t* __restrict
     for (int c = lane; c < D; c += 32) atomicAdd(dst + c, g[c]);
 }
 
+// one warp per winning slot: blocks 1..K of its summed output-row gradient go through the backward of
+// H = E'/max(||E'||, 1e-12) (F.normalize, NGCF.py:144) in place; block 0 (the raw table row, NGCF.py:121) stays
+struct NormArgs {
+    const float* layer[NGCF_MAX_LAYERS + 1];
+    int dim[NGCF_MAX_LAYERS + 1];
+    int n;
+};
+__global__ void rowgrad_normalize_kernel(RowSets s, NormArgs L, int D, const int32_t* __restrict__ slot,
+                                         float* __restrict__ gsum) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    int j; int64_t b;
+    if (!locate(s, i, j, b)) return;
+    const int64_t row = s.rows[j][b] + s.offset[j];
+    if (slot[row] != (int32_t)i) return;                                  // a duplicate of the row: its winner does it
+    float* g = gsum + i * D;
+    int col = L.dim[0];
+    for (int k = 1; k < L.n; ++k) {
+        const int d = L.dim[k];
+        const float* e = L.layer[k] + row * d;
+        float nrm2 = 0.f, dot = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            nrm2 = fmaf(e[c], e[c], nrm2);
+            dot = fmaf(e[c], g[col + c], dot);
+        }
+        nrm2 = warp_sum(nrm2);
+        dot = warp_sum(dot);
+        const float n = fmaxf(sqrtf(nrm2), 1e-12f);
+        const float hd = dot / n;                                         // H . gH
+        for (int c = lane; c < d; c += 32) g[col + c] = (g[col + c] - (e[c] / n) * hd) / n;
+        col += d;
+    }
+}
+
 __global__ void rowgrad_reset_kernel(RowSets s, int32_t* __restrict__ slot) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int j; int64_t b;
@@ -215,6 +249,31 @@ extern "C" int ngcf_rowgrad_scatter(const int64_t* const* rows_host, const int64
     NGCF_LAUNCH_OK("rowgrad_claim_kernel");
     rowgrad_accum_kernel<<<(unsigned)ceil_div64(s.total * 32, 256), 256, 0, st>>>(s, D, slot, gsum);
     NGCF_LAUNCH_OK("rowgrad_accum_kernel");
+    return NGCF_OK;
+}
+
+extern "C" int ngcf_rowgrad_normalize(const int64_t* const* rows_host, const int64_t* offsets_host,
+                                      const int64_t* batch_host, int n_sets, const float* const* layers_host,
+                                      const int* dims_host, int n_layers_plus1, const int32_t* slot, float* gsum,
+                                      int D, void* stream) {
+    NGCF_REQUIRE(slot && gsum && layers_host && dims_host, "rowgrad_normalize: null pointer");
+    NGCF_REQUIRE(n_layers_plus1 >= 1 && n_layers_plus1 <= NGCF_MAX_LAYERS + 1, "rowgrad_normalize: %d blocks", n_layers_plus1);
+    RowSets s;
+    int rc = fill_sets(s, rows_host, offsets_host, nullptr, batch_host, n_sets);
+    if (rc != NGCF_OK) return rc;
+    NormArgs L;
+    int total = 0;
+    for (int k = 0; k < n_layers_plus1; ++k) {
+        NGCF_REQUIRE(layers_host[k] && dims_host[k] > 0 && dims_host[k] <= NGCF_MAX_WIDTH, "rowgrad_normalize: bad block %d", k);
+        L.layer[k] = layers_host[k];
+        L.dim[k] = dims_host[k];
+        total += dims_host[k];
+    }
+    L.n = n_layers_plus1;
+    NGCF_REQUIRE(total == D, "rowgrad_normalize: block widths sum to %d, D = %d", total, D);
+    if (s.total == 0 || n_layers_plus1 == 1) return NGCF_OK;
+    rowgrad_normalize_kernel<<<(unsigned)ceil_div64(s.total * 32, 256), 256, 0, as_stream(stream)>>>(s, L, D, slot, gsum);
+    NGCF_LAUNCH_OK("rowgrad_normalize_kernel");
     return NGCF_OK;
 }
 

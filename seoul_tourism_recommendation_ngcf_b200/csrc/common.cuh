@@ -123,6 +123,12 @@ __device__ __forceinline__ float4 mess_multiplier4(float p, uint64_t seed, int l
     return make_float4((r.x & 0xffffu) >= thr ? s : 0.f, (r.x >> 16) >= thr ? s : 0.f, (r.y & 0xffffu) >= thr ? s : 0.f,
                        (r.y >> 16) >= thr ? s : 0.f);
 }
+// the same decisions with the threshold and 1/(1-p) hoisted out of the caller's loop
+__device__ __forceinline__ float4 mess_multiplier4_pre(uint32_t thr, float s, uint64_t seed, int layer, uint64_t quad) {
+    const uint2 r = ngcf_hash64(seed, (uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)layer, NGCF_STREAM_MESS);
+    return make_float4((r.x & 0xffffu) >= thr ? s : 0.f, (r.x >> 16) >= thr ? s : 0.f, (r.y & 0xffffu) >= thr ? s : 0.f,
+                       (r.y >> 16) >= thr ? s : 0.f);
+}
 __device__ __forceinline__ float mess_multiplier(float p, uint64_t seed, int layer, uint64_t elem) {
     const float4 m = mess_multiplier4(p, seed, layer, elem >> 2);
     const int j = (int)(elem & 3);

@@ -201,6 +201,7 @@ struct BwdArgs {
     float* gb2;
     int n_tiles;
     int64_t row_off;
+    int gh_normalized;        // gsum already went through ngcf_rowgrad_normalize: add its slice as it is
 };
 
 template <int DC, int R, int THREADS>
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(THREADS) dense_bwd_kernel(BwdArgs a) {
                 float g = 0.f;
                 if (row < a.n_rows && c < d_out) {
                     g = a.gE_next ? a.gE_next[row * d_out + c] : 0.f;
-                    if (s >= 0) g += (gh[q] - (e[q] / n) * dot) / n;     // normalize backward
+                    if (s >= 0) g += a.gh_normalized ? gh[q] : (gh[q] - (e[q] / n) * dot) / n;   // normalize backward
                     float mult = 1.f;
                     if (a.mess_mult) mult = a.mess_mult[row * d_out + c];
                     else if (a.mess_bits) mult = mess_multiplier_bits(a.mess_bits, a.mess_p, row, d_out, c);
@@ -442,7 +443,7 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
                       float mess_p,
-                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
+                      uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, int gh_normalized, float* gS, float* gEl,
                       float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st);
 
 // NGCF_B200_DENSE=ffma forces the exact-fp32 FFMA kernels (A/B comparisons); default: tensor cores where eligible
@@ -497,8 +498,8 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
                               int col_off, const float* E_out, const float* S, const float* E, int64_t n_rows,
                               int d_in, int d_out, const float* W1, const float* W2, float slope,
                               const float* mess_mult, const uint32_t* mess_bits, float mess_p, uint64_t seed,
-                              const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
-                              float* gM_scratch, void* stream) {
+                              const uint64_t* seed_dev, int layer, int64_t row_offset, int gh_normalized, float* gS,
+                              float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, void* stream) {
     NGCF_REQUIRE(E_out && S && E && W1 && W2 && gS && gEl && gW1 && gb1 && gW2 && gb2, "dense_bwd: null pointer");
     NGCF_REQUIRE(!slot || gsum, "dense_bwd: slot given without gsum");
     NGCF_REQUIRE(d_in > 0 && d_in <= NGCF_MAX_WIDTH && d_out > 0 && d_out <= NGCF_MAX_WIDTH,
@@ -509,10 +510,10 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
     if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out) && aligned16(S) &&
         aligned16(E) && aligned16(gS) && aligned16(gEl) && aligned16(gM_scratch))
         return ngcf_dense_bwd_tc(gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2,
-                                 slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, row_offset, gS, gEl, gW1, gb1, gW2,
-                                 gb2, gM_scratch, as_stream(stream));
+                                 slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, row_offset, gh_normalized, gS,
+                                 gEl, gW1, gb1, gW2, gb2, gM_scratch, as_stream(stream));
     BwdArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-              mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0, row_offset};
+              mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gW1, gb1, gW2, gb2, 0, row_offset, gh_normalized};
     int rc;
     if (d_in <= 64 && d_out <= 64) {
         constexpr int DC = 64, R = 64, T = 256;

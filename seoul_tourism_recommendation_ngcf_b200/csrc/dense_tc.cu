@@ -64,6 +64,15 @@ static_assert((FW_EPI_WARPS + 1 + FW_LOAD_WARPS) * 32 == TC_THREADS, "forward ro
 // 32 x 32 fp32 transposition buffer without padding: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
 __device__ __forceinline__ int stage_off(int r, int c) { return r * 32 + ((c ^ (r & 7)) << 2); }
 
+// message-dropout source, a compile-time mode so the per-element code is branch-free and the unrolled chains interleave
+// (with run-time tests inside the loops the compiler kept every iteration a separate basic block: no overlap of
+// the ~45-deep integer hash chains, measured 1200 cycles per 4-element step in the backward's loader)
+enum { MM_NONE = 0, MM_MULT = 1, MM_BITS = 2, MM_HASH = 3 };
+static inline int mess_mode(const float* mess_mult, const uint32_t* mess_bits, float mess_p) {
+    return mess_mult ? MM_MULT : (mess_p > 0.f ? (mess_bits ? MM_BITS : MM_HASH) : MM_NONE);
+}
+
+template <int MM>
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // operand tiles need 1024-byte alignment
@@ -119,7 +128,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         // ======================= epilogue =======================================================================
         // TMEM lane = tile row, so a thread holds one row of its chunk; bias + LeakyReLU + dropout are applied in that
         // layout, then the 32x32 block goes through a per-warp transposition buffer so the stores are coalesced.
-        const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        const uint64_t seed = MM == MM_HASH ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        const uint32_t thr = ngcf_threshold16(a.mess_p);
         float* st = stage + warp * 32 * 32;
         const int quarter = warp & 3, c = warp >> 2;                      // TMEM lanes 32*quarter.., columns 32*c..
         const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
             const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
             const int64_t my_row = row_base + lane;
             uint32_t keep = 0xffffffffu;                                  // this row's 32 dropout decisions of the chunk
-            if (a.mess_bits && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
+            if (MM == MM_BITS && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float o[4];
@@ -148,11 +158,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                     const float m = v[j + t] + bias_s[c * 32 + j + t];
                     o[t] = m > 0.f ? m : a.slope * m;                                   // LeakyReLU, NGCF.py:140
                 }
-                if (a.mess_bits) {
+                if (MM == MM_BITS) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) o[t] = (keep >> (j + t)) & 1u ? o[t] * inv_keep : 0.f;
-                } else if (!a.mess_mult && a.mess_p > 0.f) {
-                    const float4 mm = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
+                } else if (MM == MM_HASH) {
+                    const float4 mm = mess_multiplier4_pre(thr, inv_keep, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
                     o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
                 }
                 st_f4(st + stage_off(lane, j >> 2), make_float4(o[0], o[1], o[2], o[3]));
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                 for (int i = 0; i < 8; ++i) {
                     const int64_t row = row_base + i * 4 + rr;
                     if (row < a.n_rows) {
-                        if (a.mess_mult) {
+                        if (MM == MM_MULT) {
                             const float4 mm = ld_f4(a.mess_mult + row * d_out + col);
                             r4[i].x *= mm.x; r4[i].y *= mm.y; r4[i].z *= mm.z; r4[i].w *= mm.w;
                         }
@@ -287,8 +297,6 @@ namespace {
 //   coalesced atomics.
 // gM is kept in two shared-memory buffers in the first kernel so the loaders run one tile ahead of the MMAs.
 // ====================================================================================================================
-constexpr int BW_STAGE_PITCH = 36;            // floats per staged row (32 + 4: keeps 16-byte alignment, no conflicts)
-
 struct BwdTcArgs {
     const float* gE_next;
     const int32_t* slot;
@@ -318,11 +326,33 @@ struct BwdTcArgs {
     int64_t row_off;
 };
 
+// optional per-role timeline of CTA 0 (tools/bwd_timeline.py): SM clock at the protocol points of each tile
+__device__ long long g_bwd_dbg[4][8][8];   // [3][tile][k] = loader warp 0 inside its tile: first half computed, next loads issued, second half, fence
+__device__ int g_bwd_dbg_on = 0;
+#define BWD_STAMP(role, it, k)                                                   \
+    do {                                                                         \
+        if (dbg && lane == 0 && (it) < 8) g_bwd_dbg[role][it][k] = clock64();    \
+    } while (0)
+
 struct BwdBars {
-    uint64_t full_gm[2], empty_gm[2], tmem_full[2], tmem_empty[2];
+    uint64_t full_gm, empty_gm, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
+    float colsum[64];         // CTA-level column sums of gM (bias gradients): one global atomic per column per CTA
 };
 
+// E / S tile of the epilogue in shared memory: 128 rows of 256 bytes (d_in = 64), the 16-byte chunk c of row r at
+// chunk position c ^ (r & 15): conflict-free both for "lane = row" accesses (the TMEM layout) and for row-contiguous
+// ones (coalesced global traffic)
+__device__ __forceinline__ uint32_t es_off(int r, int c) { return (uint32_t)r * 256u + (uint32_t)((c ^ (r & 15)) << 4); }
+
+// Roles (416 threads): warps 0-3 epilogue, warp 4 MMA issuer, warps 5-12 loaders.
+// The first version's epilogue fetched E and S from global memory after every TMEM read: ncu showed the four epilogue
+// warps as the critical path (60 % of their time waiting on those loads) and the loaders idle 74 % of the time.  Now
+// the loaders also bring the tile's E and S rows into shared memory (registers as the second pipeline stage, so the
+// global latency overlaps the previous tile's epilogue); the epilogue combines them with T in TMEM layout IN PLACE
+// (gS over E, gEl over S), then each warp streams its 32 rows out with coalesced 128-bit stores.
+// PRE: gsum went through ngcf_rowgrad_normalize, the loader adds its slice as it is (no reductions, no divisions)
+template <int MM, bool PRE>
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -330,25 +360,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     constexpr int d_in = 64;
     const int d_out = a.d_out;
     const int KBo = d_out / 32;                                           // 32-column blocks of gM
-    const int gm_buf = 2 * KBo * TC_A_BLOCK;                              // hi + lo of one gM buffer
-    uint8_t* GM = smem;                                                   // [2 buffers][hi | lo][KBo blocks]
-    uint8_t* BT_hi = GM + 2 * gm_buf;                                     // [n = 0..127][k = o], K blocks of 32 o
+    uint8_t* GM_hi = smem;                                                // [hi | lo][KBo blocks]
+    uint8_t* GM_lo = GM_hi + KBo * TC_A_BLOCK;
+    uint8_t* BT_hi = GM_lo + KBo * TC_A_BLOCK;                            // [n = 0..127][k = o], K blocks of 32 o
     uint8_t* BT_lo = BT_hi + KBo * TC_A_BLOCK;
-    float* stage = reinterpret_cast<float*>(BT_lo + KBo * TC_A_BLOCK);    // [4 warps][32][BW_STAGE_PITCH]
-    BwdBars* bars = reinterpret_cast<BwdBars*>(stage + TC_EPI_WARPS * 32 * BW_STAGE_PITCH);
+    uint8_t* E_s = BT_lo + KBo * TC_A_BLOCK;                              // [128][64] fp32, es_off layout
+    uint8_t* S_s = E_s + TC_ROWS * 256;
+    BwdBars* bars = reinterpret_cast<BwdBars*>(S_s + TC_ROWS * 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
+        mbar_init(&bars->full_gm, TC_LOAD_WARPS);
+        mbar_init(&bars->empty_gm, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->full_gm[i], TC_LOAD_WARPS);
-            mbar_init(&bars->empty_gm[i], 1);
             mbar_init(&bars->tmem_full[i], 1);
             mbar_init(&bars->tmem_empty[i], TC_EPI_WARPS);
         }
         fence_mbar_init();
     }
     if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // T x2 (128 columns each)
+    if (tid < 64) bars->colsum[tid] = 0.f;
     // BT[n][o] = W1[o][n] (n < 64), W2[o][n-64]; W1/W2 are [d_out, d_in] row-major
     for (int i = tid; i < 128 * KBo * 8; i += TC_THREADS) {
         const int c = i & 7, n = (i >> 3) & 127, kb = i >> 10;
@@ -368,79 +400,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool dbg = g_bwd_dbg_on && blockIdx.x == 0 && (warp == 0 || warp == TC_EPI_WARPS || warp == TC_EPI_WARPS + 1);
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();   // start of the steady state
 
     if (warp < TC_EPI_WARPS) {
         // ======================= epilogue: gS / gEl ==============================================================
-        float* st = stage + warp * 32 * BW_STAGE_PITCH;
-        const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
+        // Each warp owns tile rows [32 warp, 32 warp + 32): it brings their E and S into shared memory itself (two
+        // rounds of 8 row pairs; the first round of the NEXT tile is in flight while this tile streams out), combines
+        // them with T in TMEM layout in place, and streams the 32 rows out — warp-local, no CTA-level barrier.
+        const int r = warp * 32 + lane;                                   // TMEM lane = tile row
+        uint8_t* e_row = E_s + r * 256;
+        uint8_t* s_row = S_s + r * 256;
+        const int sw = r & 15;
+        const int c = lane & 15, hsel = lane >> 4;
+        // fill: this warp's 32 rows of E and S of a tile -> shared memory with cp.async (no registers held; rows past
+        // the end are zero-filled), issued right after the previous tile streamed out
+        const uint32_t e_s32 = smem_u32(E_s), s_s32 = smem_u32(S_s);
+        auto fill = [&](int tile) {
+            const int64_t row0 = (int64_t)tile * TC_ROWS;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int rl = warp * 32 + 2 * i + hsel;
+                const int64_t row = row0 + rl;
+                const bool ok = row < a.n_rows;
+                const int64_t src = (ok ? row : 0) * d_in + c * 4;
+                const uint32_t off = es_off(rl, c);
+                cp_async16(e_s32 + off, a.E + src, ok ? 16u : 0u);
+                cp_async16(s_s32 + off, a.S + src, ok ? 16u : 0u);
+            }
+        };
+        if (n_my > 0) fill(blockIdx.x);
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int buf = it & 1;
+            BWD_STAMP(0, it, 0);
+            cp_async_wait_all();
+            __syncwarp();
+            BWD_STAMP(0, it, 1);
             mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+            BWD_STAMP(0, it, 2);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 128;
-            const int64_t row_base = (int64_t)tile * TC_ROWS + warp * 32;
 #pragma unroll 1
-            for (int c = 0; c < d_in / 32; ++c) {
-                float4 t1[8], t2[8];
-                float v[32];
-                tmem_ld_32x32(taddr + c * 32, v);                         // T1[row = lane][32c .. 32c+32)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_f4(st + lane * BW_STAGE_PITCH + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t1[i] = ld_f4(st + (i * 4 + rr) * BW_STAGE_PITCH + c4 * 4);
-                __syncwarp();
-                tmem_ld_32x32(taddr + d_in + c * 32, v);                  // T2
-                if (c == d_in / 32 - 1) {                                 // accumulator fully read
+            for (int half = 0; half < d_in / 32; ++half) {
+                float v1[32], v2[32];
+                tmem_ld_32x32(taddr + half * 32, v1);                     // T1[row][32 half .. +32)
+                tmem_ld_32x32(taddr + d_in + half * 32, v2);              // T2
+                if (half == d_in / 32 - 1) {                              // accumulator fully read
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_f4(st + lane * BW_STAGE_PITCH + j * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t2[i] = ld_f4(st + (i * 4 + rr) * BW_STAGE_PITCH + c4 * 4);
-                __syncwarp();
-#pragma unroll
-                for (int ib = 0; ib < 8; ib += 4) {                       // 4 rows at a time: loads first, then math + stores
-                    float4 e4[4], s4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int64_t row = min(row_base + (ib + i) * 4 + rr, a.n_rows - 1);
-                        const int64_t o = row * d_in + c * 32 + c4 * 4;
-                        e4[i] = ld_f4(a.E + o);
-                        s4[i] = ld_f4(a.S + o);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int64_t row = row_base + (ib + i) * 4 + rr;
-                        if (row < a.n_rows) {
-                            const int64_t o = row * d_in + c * 32 + c4 * 4;
-                            const float4 x1 = t1[ib + i], x2 = t2[ib + i];
-                            st_f4(a.gS + o, make_float4(fmaf(x2.x, e4[i].x, x1.x), fmaf(x2.y, e4[i].y, x1.y),
-                                                        fmaf(x2.z, e4[i].z, x1.z), fmaf(x2.w, e4[i].w, x1.w)));
-                            st_f4(a.gEl + o, make_float4(fmaf(x2.x, s4[i].x, x1.x), fmaf(x2.y, s4[i].y, x1.y),
-                                                         fmaf(x2.z, s4[i].z, x1.z), fmaf(x2.w, s4[i].w, x1.w)));
-                        }
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = (uint32_t)(((half * 8 + j) ^ sw) << 4);
+                    const float4 e = *reinterpret_cast<const float4*>(e_row + off);
+                    const float4 s = *reinterpret_cast<const float4*>(s_row + off);
+                    *reinterpret_cast<float4*>(e_row + off) =              // gS = T1 + T2 * E
+                        make_float4(fmaf(v2[4 * j], e.x, v1[4 * j]), fmaf(v2[4 * j + 1], e.y, v1[4 * j + 1]),
+                                    fmaf(v2[4 * j + 2], e.z, v1[4 * j + 2]), fmaf(v2[4 * j + 3], e.w, v1[4 * j + 3]));
+                    *reinterpret_cast<float4*>(s_row + off) =              // gEl = T1 + T2 * S
+                        make_float4(fmaf(v2[4 * j], s.x, v1[4 * j]), fmaf(v2[4 * j + 1], s.y, v1[4 * j + 1]),
+                                    fmaf(v2[4 * j + 2], s.z, v1[4 * j + 2]), fmaf(v2[4 * j + 3], s.w, v1[4 * j + 3]));
                 }
             }
+            __syncwarp();
+            BWD_STAMP(0, it, 3);
+            // this warp's 32 rows, two rows per instruction: coalesced 128-bit stores
+            const int64_t row0 = (int64_t)tile * TC_ROWS;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int rl = warp * 32 + 2 * i + hsel;
+                const int64_t row = row0 + rl;
+                const uint32_t off = es_off(rl, c);
+                const float4 x = *reinterpret_cast<const float4*>(E_s + off);
+                const float4 y = *reinterpret_cast<const float4*>(S_s + off);
+                if (row < a.n_rows) {
+                    st_f4(a.gS + row * d_in + c * 4, x);
+                    st_f4(a.gEl + row * d_in + c * 4, y);
+                }
+            }
+            __syncwarp();
+            BWD_STAMP(0, it, 4);
+            if (it + 1 < n_my) fill(tile + gridDim.x);
         }
     } else if (warp == TC_EPI_WARPS) {
         // ======================= MMA issuer =====================================================================
         const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, 2 * d_in, 0, 0);
         for (int it = 0; it < n_my; ++it) {
-            const int buf = it & 1, ph = (it >> 1) & 1;
-            mbar_wait(&bars->full_gm[buf], ph);
-            mbar_wait(&bars->tmem_empty[buf], ph ^ 1);
+            const int buf = it & 1;
+            BWD_STAMP(1, it, 0);
+            mbar_wait(&bars->full_gm, it & 1);
+            BWD_STAMP(1, it, 1);
+            mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            BWD_STAMP(1, it, 2);
             tc_fence_after_sync();
             if (lane == 0) {
                 const uint32_t tmem_t = tmem_base + buf * 128;
-                const uint32_t gm_hi = smem_u32(GM + buf * gm_buf), gm_lo = gm_hi + KBo * TC_A_BLOCK;
+                const uint32_t gm_hi = smem_u32(GM_hi), gm_lo = smem_u32(GM_lo);
                 uint32_t acc1 = 0;
                 for (int kb = 0; kb < KBo; ++kb) {
 #pragma unroll
@@ -457,92 +514,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                     }
                 }
                 umma_commit(&bars->tmem_full[buf]);
-                umma_commit(&bars->empty_gm[buf]);
+                umma_commit(&bars->empty_gm);
             }
             __syncwarp();
+            BWD_STAMP(1, it, 3);
         }
     } else {
-        // ======================= loaders: gM rows ====================================================================
+        // ======================= loaders: gM rows =================================================================
         // half a warp per row: lane owns the four columns 4*(lane & 15) .. +3 (one RNG call = exactly its four
-        // dropout decisions, 128-bit loads and shared-memory stores); 8 row pairs in flight per warp
+        // dropout decisions, 128-bit loads and shared-memory stores).  Software-pipelined by half tiles (4 row pairs
+        // per warp): the loads of the next half are in flight while this half is computed, across tiles too.
         const int lw = warp - (TC_EPI_WARPS + 1);                         // 0 .. 7
         const int hl = lane & 15, hsel = lane >> 4;
         const int c0 = hl * 4;
         const bool col_ok = c0 < d_out;
-        const uint64_t seed = a.mess_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        const uint64_t seed = MM == MM_HASH ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+        const uint32_t thr = ngcf_threshold16(a.mess_p);
+        const float inv_keep = 1.0f / (1.0f - a.mess_p);
         float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        constexpr int PAIRS = TC_ROWS / (2 * TC_LOAD_WARPS);              // row pairs per warp per tile
-        constexpr int PB = 4;                                             // row pairs in flight (register budget: 13 warps
-                                                                          // put 4 on one SM sub-partition -> 128 regs/thread)
-        for (int it = 0; it < n_my; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int buf = it & 1;
+        constexpr int HP = TC_ROWS / (4 * TC_LOAD_WARPS);                 // row pairs per warp per half tile
+        struct Half {
+            float4 e[HP], gn[HP];
+            int sl[HP];
+        };
+        auto issue = [&](Half& h, int tile, int half) {
             const int64_t row0 = (int64_t)tile * TC_ROWS;
-            uint8_t* GM_hi = GM + buf * gm_buf;
-            uint8_t* GM_lo = GM_hi + KBo * TC_A_BLOCK;
-            mbar_wait(&bars->empty_gm[buf], ((it >> 1) & 1) ^ 1);
-#pragma unroll 1
-            for (int jb = 0; jb < PAIRS; jb += PB) {
-            float4 e[PB], gn[PB];
-            int sl[PB];
 #pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                const int64_t row = row0 + 2 * (lw + TC_LOAD_WARPS * (jb + j)) + hsel;
+            for (int j = 0; j < HP; ++j) {
+                const int64_t row = row0 + 2 * (lw + TC_LOAD_WARPS * (half * HP + j)) + hsel;
                 const bool ok = row < a.n_rows && col_ok;
-                e[j] = gn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                sl[j] = -1;
+                h.e[j] = h.gn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                h.sl[j] = -1;
                 if (ok) {
-                    e[j] = ld_f4(a.E_out + row * d_out + c0);
-                    if (a.gE_next) gn[j] = ld_f4(a.gE_next + row * d_out + c0);
-                    if (a.slot) sl[j] = a.slot[row];
+                    h.e[j] = ld_f4(a.E_out + row * d_out + c0);
+                    if (a.gE_next) h.gn[j] = ld_f4(a.gE_next + row * d_out + c0);
+                    if (a.slot) h.sl[j] = a.slot[row];
                 }
             }
+        };
+        auto compute = [&](Half& h, int tile, int half) {
+            const int64_t row0 = (int64_t)tile * TC_ROWS;
+            // (1) rows of the batch only (~4 % of all rows): their output-row gradient
+            if (PRE) {                                                    // already normalize-backwarded: predicated add
 #pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                const int r = 2 * (lw + TC_LOAD_WARPS * (jb + j)) + hsel;
-                const int64_t row = row0 + r;
-                const bool in = row < a.n_rows;
-                float4 g = gn[j];
-                const int s = sl[j];
-                if (__any_sync(FULL_MASK, s >= 0)) {                      // rows of the batch only (~4 % of all rows)
-                    float4 gh = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < HP; ++j) {
+                    const int s = h.sl[j];
                     if (s >= 0) {                                         // col_off need not be a multiple of 4 (width 65 first)
                         const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + c0;
-                        gh = make_float4(gp[0], gp[1], gp[2], gp[3]);
-                    }
-                    float nrm2 = e[j].x * e[j].x + e[j].y * e[j].y + e[j].z * e[j].z + e[j].w * e[j].w;
-                    float dot = e[j].x * gh.x + e[j].y * gh.y + e[j].z * gh.z + e[j].w * gh.w;
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) {                     // reduce over the 16 lanes of the row
-                        nrm2 += __shfl_xor_sync(FULL_MASK, nrm2, o);
-                        dot += __shfl_xor_sync(FULL_MASK, dot, o);
-                    }
-                    if (s >= 0) {
-                        const float n = fmaxf(sqrtf(nrm2), 1e-12f);       // F.normalize eps, NGCF.py:144
-                        const float hd = dot / n;                         // H . gH
-                        g.x += (gh.x - (e[j].x / n) * hd) / n;            // normalize backward
-                        g.y += (gh.y - (e[j].y / n) * hd) / n;
-                        g.z += (gh.z - (e[j].z / n) * hd) / n;
-                        g.w += (gh.w - (e[j].w / n) * hd) / n;
+                        h.gn[j].x += gp[0]; h.gn[j].y += gp[1]; h.gn[j].z += gp[2]; h.gn[j].w += gp[3];
                     }
                 }
-                if (col_ok) {
-                    float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (in) {
-                        if (a.mess_mult) mult = ld_f4(a.mess_mult + row * d_out + c0);
-                        else if (a.mess_bits) {
-                            const uint32_t w = a.mess_bits[row * ((d_out + 31) >> 5) + (c0 >> 5)] >> (c0 & 31);
-                            const float inv = 1.0f / (1.0f - a.mess_p);
-                            mult = make_float4(w & 1u ? inv : 0.f, w & 2u ? inv : 0.f, w & 4u ? inv : 0.f, w & 8u ? inv : 0.f);
-                        } else if (a.mess_p > 0.f) mult = mess_multiplier4(a.mess_p, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < HP; ++j) {
+                    const int s = h.sl[j];
+                    if (__any_sync(FULL_MASK, s >= 0)) {
+                        float4 gh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (s >= 0) {                                         // col_off need not be a multiple of 4 (width 65 first)
+                            const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + c0;
+                            gh = make_float4(gp[0], gp[1], gp[2], gp[3]);
+                        }
+                        const float4 e = h.e[j];
+                        float nrm2 = e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+                        float dot = e.x * gh.x + e.y * gh.y + e.z * gh.z + e.w * gh.w;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) {                     // reduce over the 16 lanes of the row
+                            nrm2 += __shfl_xor_sync(FULL_MASK, nrm2, o);
+                            dot += __shfl_xor_sync(FULL_MASK, dot, o);
+                        }
+                        if (s >= 0) {
+                            const float rn = 1.0f / fmaxf(sqrtf(nrm2), 1e-12f);   // F.normalize eps, NGCF.py:144
+                            const float hd = dot * rn;                        // H . gH
+                            h.gn[j].x += (gh.x - (e.x * rn) * hd) * rn;       // normalize backward
+                            h.gn[j].y += (gh.y - (e.y * rn) * hd) * rn;
+                            h.gn[j].z += (gh.z - (e.z * rn) * hd) * rn;
+                            h.gn[j].w += (gh.w - (e.w * rn) * hd) * rn;
+                        }
                     }
-                    g.x *= mult.x * (e[j].x > 0.f ? 1.f : a.slope);       // dropout + LeakyReLU backward
-                    g.y *= mult.y * (e[j].y > 0.f ? 1.f : a.slope);
-                    g.z *= mult.z * (e[j].z > 0.f ? 1.f : a.slope);
-                    g.w *= mult.w * (e[j].w > 0.f ? 1.f : a.slope);
-                    if (in) st_f4(a.gM + row * d_out + c0, g);
-                    else g = make_float4(0.f, 0.f, 0.f, 0.f);
-                    colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
+                }
+            }
+            // (2) every row, branch-free: dropout + LeakyReLU backward, gM out, TF32 split into the operand tile
+#pragma unroll
+            for (int j = 0; j < HP; ++j) {
+                const int r = 2 * (lw + TC_LOAD_WARPS * (half * HP + j)) + hsel;
+                const int64_t row = row0 + r;
+                const bool in = row < a.n_rows && col_ok;
+                const float4 e = h.e[j];
+                float4 g = h.gn[j];
+                float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (MM == MM_MULT) {
+                    if (in) mult = ld_f4(a.mess_mult + row * d_out + c0);
+                } else if (MM == MM_BITS) {
+                    uint32_t w = 0;
+                    if (in) w = a.mess_bits[row * ((d_out + 31) >> 5) + (c0 >> 5)] >> (c0 & 31);
+                    mult = make_float4(w & 1u ? inv_keep : 0.f, w & 2u ? inv_keep : 0.f, w & 4u ? inv_keep : 0.f,
+                                       w & 8u ? inv_keep : 0.f);
+                } else if (MM == MM_HASH) {
+                    mult = mess_multiplier4_pre(thr, inv_keep, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
+                }
+                g.x *= mult.x * (e.x > 0.f ? 1.f : a.slope);              // dropout + LeakyReLU backward
+                g.y *= mult.y * (e.y > 0.f ? 1.f : a.slope);
+                g.z *= mult.z * (e.z > 0.f ? 1.f : a.slope);
+                g.w *= mult.w * (e.w > 0.f ? 1.f : a.slope);
+                if (!in) g = make_float4(0.f, 0.f, 0.f, 0.f);             // rows past the end / unused columns
+                if (in) st_f4(a.gM + row * d_out + c0, g);
+                colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
+                if (col_ok) {
                     float4 hi, lo;
                     split_tf32(g, hi, lo);
                     const uint32_t off = (hl >> 3) * TC_A_BLOCK + sw128_offset(r, hl & 7);
@@ -550,27 +627,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                     *reinterpret_cast<float4*>(GM_lo + off) = lo;
                 }
             }
-            }
+        };
+        Half h0, h1;
+        if (n_my > 0) issue(h0, blockIdx.x, 0);
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            BWD_STAMP(2, it, 0);
+            issue(h1, tile, 1);
+            BWD_STAMP(2, it, 1);
+            mbar_wait(&bars->empty_gm, (it & 1) ^ 1);                     // the MMAs of the previous tile have read gM
+            BWD_STAMP(2, it, 2);
+            compute(h0, tile, 0);
+            BWD_STAMP(3, it, 0);
+            if (it + 1 < n_my) issue(h0, tile + gridDim.x, 0);
+            BWD_STAMP(3, it, 1);
+            compute(h1, tile, 1);
+            BWD_STAMP(3, it, 2);
             fence_proxy_async_smem();
+            BWD_STAMP(3, it, 3);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->full_gm[buf]);
+            if (lane == 0) mbar_arrive(&bars->full_gm);
+            BWD_STAMP(2, it, 3);
         }
         colsum.x += __shfl_xor_sync(FULL_MASK, colsum.x, 16);
         colsum.y += __shfl_xor_sync(FULL_MASK, colsum.y, 16);
         colsum.z += __shfl_xor_sync(FULL_MASK, colsum.z, 16);
         colsum.w += __shfl_xor_sync(FULL_MASK, colsum.w, 16);
+        // the 8 loader warps first reduce in shared memory: 148 x 8 warps hammering the same 128 global addresses
+        // with atomics (150 k of them on four cache lines) jammed the L2 slices behind them for tens of microseconds
         if (hsel == 0 && col_ok) {
-            const float cs[4] = {colsum.x, colsum.y, colsum.z, colsum.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                atomicAdd(a.gb2 + c0 + t, cs[t]);
-                atomicAdd(a.gb1 + c0 + t, 2.0f * cs[t]);                  // w1_list[i] is applied twice (NGCF.py:131,133)
-            }
+            atomicAdd(&bars->colsum[c0 + 0], colsum.x);
+            atomicAdd(&bars->colsum[c0 + 1], colsum.y);
+            atomicAdd(&bars->colsum[c0 + 2], colsum.z);
+            atomicAdd(&bars->colsum[c0 + 3], colsum.w);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_LOAD_WARPS * 32) : "memory");   // loader warps only
+        const int lt = tid - (TC_EPI_WARPS + 1) * 32;
+        if (lt < d_out) {
+            const float cs = bars->colsum[lt];
+            atomicAdd(a.gb2 + lt, cs);
+            atomicAdd(a.gb1 + lt, 2.0f * cs);                             // w1_list[i] is applied twice (NGCF.py:131,133)
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[1][7][7] = clock64();   // every role done
     if (warp == TC_EPI_WARPS) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 256);
@@ -743,11 +845,19 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                         FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
     static bool attr_set = false;
     if (!attr_set) {
-        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_MULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
-    dense_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    switch (mess_mode(mess_mult, mess_bits, mess_p)) {
+        case MM_NONE: dense_fwd_tc_kernel<MM_NONE><<<grid, TC_THREADS, smem, st>>>(a); break;
+        case MM_MULT: dense_fwd_tc_kernel<MM_MULT><<<grid, TC_THREADS, smem, st>>>(a); break;
+        case MM_BITS: dense_fwd_tc_kernel<MM_BITS><<<grid, TC_THREADS, smem, st>>>(a); break;
+        default: dense_fwd_tc_kernel<MM_HASH><<<grid, TC_THREADS, smem, st>>>(a); break;
+    }
     NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
     return NGCF_OK;
 }
@@ -757,22 +867,30 @@ bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out) { return d_in == 64 && (d_o
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
-                      float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* gS, float* gEl,
-                      float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch, cudaStream_t st) {
+                      float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, int gh_normalized,
+                      float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch,
+                      cudaStream_t st) {
     BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
                 mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS),
                 row_offset};
     const int KBo = d_out / 32;
-    const size_t smem = 1024 + (size_t)6 * KBo * TC_A_BLOCK + TC_EPI_WARPS * 32 * BW_STAGE_PITCH * sizeof(float) +
-                        sizeof(BwdBars);
+    const size_t smem = 1024 + (size_t)4 * KBo * TC_A_BLOCK + 2 * TC_ROWS * 256 + sizeof(BwdBars);
+    const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
+    void (*kern)(BwdTcArgs) = nullptr;
+    const bool pre = gh_normalized != 0;
+    switch (mess_mode(mess_mult, mess_bits, mess_p)) {
+        case MM_NONE: kern = pre ? dense_bwd_tc_kernel<MM_NONE, true> : dense_bwd_tc_kernel<MM_NONE, false>; break;
+        case MM_MULT: kern = pre ? dense_bwd_tc_kernel<MM_MULT, true> : dense_bwd_tc_kernel<MM_MULT, false>; break;
+        case MM_BITS: kern = pre ? dense_bwd_tc_kernel<MM_BITS, true> : dense_bwd_tc_kernel<MM_BITS, false>; break;
+        default: kern = pre ? dense_bwd_tc_kernel<MM_HASH, true> : dense_bwd_tc_kernel<MM_HASH, false>; break;
+    }
+    NGCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     static bool attr_set = false;
     if (!attr_set) {
-        NGCF_CUDA(cudaFuncSetAttribute(dense_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
-    dense_bwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    kern<<<grid, TC_THREADS, smem, st>>>(a);
     NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
 
     WgradArgs w{S, E, gM_scratch, n_rows, d_out, gW1, gW2, (int)ceil_div64(n_rows, WG_ROWS)};
@@ -780,5 +898,12 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
     const int grid2 = (int)min((int64_t)w.n_chunks, (int64_t)ngcf_num_sms());
     wgrad_tc_kernel<<<grid2, TC_THREADS, smem2, st>>>(w);
     NGCF_LAUNCH_OK("wgrad_tc_kernel");
+    return NGCF_OK;
+}
+
+// debugging aid (tools/bwd_timeline.py): switch the CTA-0 timeline of dense_bwd_tc_kernel on/off and read it back
+extern "C" int ngcf_debug_bwd_timeline(int enable, long long* out_host /*[4*8*8] or NULL*/) {
+    NGCF_CUDA(cudaMemcpyToSymbol(g_bwd_dbg_on, &enable, sizeof(int)));
+    if (out_host) NGCF_CUDA(cudaMemcpyFromSymbol(out_host, g_bwd_dbg, sizeof(long long) * 4 * 8 * 8));
     return NGCF_OK;
 }

@@ -28,7 +28,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
+#ifdef NGCF_MBAR_TEST_WAIT
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
@@ -38,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- cp.async (LDGSTS): 16 bytes global -> shared without a register stage; src_bytes < 16 zero-fills the rest ------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- tcgen05 ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -125,10 +135,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 // hi = x rounded to nearest TF32, lo = the exactly representable remainder rounded to TF32 as well, so the tensor
 // core's operand truncation changes neither.  Round-to-nearest keeps the split errors zero-mean: with a truncating
 // split they all share the sign of x and add up coherently over the ~10^5-row weight-gradient sums.
+// (cvt.rna.tf32.f32 is not a native sm_100a instruction: ptxas expands it to add / inf-test / select / mask.  For
+// finite inputs the add-half-ulp-and-mask below is the same round-to-nearest in two integer instructions; an
+// infinity stays an infinity, and the operands here are finite by construction.)
 __device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = rna_tf32(x);

@@ -456,9 +456,19 @@ def test_dense_backward_vs_float64(N, d_in, d_out):
     slot[rows] = torch.arange(n_slot, dtype=torch.int32)
     gsum = torch.randn(n_slot, D, generator=g)
     dev = lambda t: t.to(DEV).contiguous()
-    for use_next, use_mult in ((True, True), (False, False)):
+    for use_next, use_mult, pre in ((True, True, 0), (False, False, 0), (True, False, 1)):
         d = dict(S=dev(S), E=dev(E), W1=dev(W1), W2=dev(W2), E_out=dev(E_out), gE_next=dev(gE_next), mult=dev(mult),
                  slot=dev(slot), gsum=dev(gsum))
+        if pre:          # F.normalize's backward applied to gsum up front (ngcf_rowgrad_normalize), as the module does
+            rows_d = dev(rows.to(torch.int64))
+            blocks = [torch.zeros(N, col_off, device=DEV), d["E_out"]] + \
+                     ([torch.zeros(N, D - col_off - d_out, device=DEV)] if D - col_off - d_out > 0 else [])
+            before = d["gsum"].clone()
+            _lib.check(lib.ngcf_rowgrad_normalize(_lib.ptr_array([rows_d]), _lib.i64_array([0]), _lib.i64_array([n_slot]),
+                                                  1, _lib.ptr_array(blocks), _lib.int_array([b.shape[1] for b in blocks]),
+                                                  len(blocks), d["slot"].data_ptr(), d["gsum"].data_ptr(), D,
+                                                  torch.cuda.current_stream().cuda_stream), "rowgrad_normalize")
+            assert torch.equal(d["gsum"][:, :col_off], before[:, :col_off])          # block 0 is not normalised
         gS, gEl = torch.empty(N, d_in, device=DEV), torch.empty(N, d_in, device=DEV)
         gW1, gW2 = torch.zeros(d_out, d_in, device=DEV), torch.zeros(d_out, d_in, device=DEV)
         gb1, gb2 = torch.zeros(d_out, device=DEV), torch.zeros(d_out, device=DEV)
@@ -466,7 +476,7 @@ def test_dense_backward_vs_float64(N, d_in, d_out):
         _lib.check(lib.ngcf_dense_bwd(d["gE_next"].data_ptr() if use_next else None, d["slot"].data_ptr(),
                                       d["gsum"].data_ptr(), D, col_off, d["E_out"].data_ptr(), d["S"].data_ptr(),
                                       d["E"].data_ptr(), N, d_in, d_out, d["W1"].data_ptr(), d["W2"].data_ptr(), 0.2,
-                                      d["mult"].data_ptr() if use_mult else None, None, 0.0, 0, None, 0, 0, gS.data_ptr(),
+                                      d["mult"].data_ptr() if use_mult else None, None, 0.0, 0, None, 0, 0, pre, gS.data_ptr(),
                                       gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(),
                                       scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "dense_bwd")
         torch.cuda.synchronize()
@@ -603,8 +613,11 @@ def test_node_dropout_modes_agree():
         loss.backward()
         res[mode] = [uu.detach().clone(), pp.detach().clone(), loss.detach().clone()] + \
                     [p.grad.clone() for p in m.parameters() if p.grad is not None]
-    for a, b_ in zip(res["bits"], res["inkernel"]):
-        assert torch.equal(a, b_)
+    for i, (a, b_) in enumerate(zip(res["bits"], res["inkernel"])):
+        if i < 3:
+            assert torch.equal(a, b_)                             # outputs and loss: the very same sums
+        else:
+            assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) <= 2e-6   # W/b gradients are summed with float atomics
     # compaction shifts an entry's position inside its row, hence its lane group in the row sum: same terms,
     # different fp32 summation tree
     for a, b_ in zip(res["compact"], res["inkernel"]):

@@ -53,7 +53,7 @@ t("node_dropout_compact (L and L^T, 3 layers)", lambda: node_dropout_compact(pla
 t("node_dropout_bits (L and L^T)", lambda: node_dropout_bits(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True))
 t("dense_fwd (mess_p 0.1)", lambda: lib.ngcf_dense_fwd(S.data_ptr(), X.data_ptr(), N, d, d, wcat.data_ptr(), bias.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, Y.data_ptr(), st))
 t("dense_fwd (no dropout)", lambda: lib.ngcf_dense_fwd(S.data_ptr(), X.data_ptr(), N, d, d, wcat.data_ptr(), bias.data_ptr(), 0.2, None, None, 0.0, 1, None, 0, 0, Y.data_ptr(), st))
-t("dense_bwd + wgrad (mess_p 0.1)", lambda: lib.ngcf_dense_bwd(gE.data_ptr(), slot.data_ptr(), gsum.data_ptr(), 4 * d, d, E_out.data_ptr(), S.data_ptr(), X.data_ptr(), N, d, d, W1.data_ptr(), W2.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, gS.data_ptr(), gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(), gM.data_ptr(), st))
+t("dense_bwd + wgrad (mess_p 0.1)", lambda: lib.ngcf_dense_bwd(gE.data_ptr(), slot.data_ptr(), gsum.data_ptr(), 4 * d, d, E_out.data_ptr(), S.data_ptr(), X.data_ptr(), N, d, d, W1.data_ptr(), W2.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, 1, gS.data_ptr(), gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(), gM.data_ptr(), st))
 os.environ["NGCF_B200_DENSE"] = "ffma"
 t("dense_fwd FFMA (mess_p 0.1)", lambda: lib.ngcf_dense_fwd(S.data_ptr(), X.data_ptr(), N, d, d, wcat.data_ptr(), bias.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, Y.data_ptr(), st))
-t("dense_bwd FFMA (mess_p 0.1)", lambda: lib.ngcf_dense_bwd(gE.data_ptr(), slot.data_ptr(), gsum.data_ptr(), 4 * d, d, E_out.data_ptr(), S.data_ptr(), X.data_ptr(), N, d, d, W1.data_ptr(), W2.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, gS.data_ptr(), gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(), gM.data_ptr(), st))
+t("dense_bwd FFMA (mess_p 0.1)", lambda: lib.ngcf_dense_bwd(gE.data_ptr(), slot.data_ptr(), gsum.data_ptr(), 4 * d, d, E_out.data_ptr(), S.data_ptr(), X.data_ptr(), N, d, d, W1.data_ptr(), W2.data_ptr(), 0.2, None, None, 0.1, 1, None, 0, 0, 1, gS.data_ptr(), gEl.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(), gb2.data_ptr(), gM.data_ptr(), st))
