@@ -76,6 +76,7 @@ typedef struct ngcf_csr {
     const int32_t* hub_ent;         /* [2*nnz_hub] */
     const int32_t* chunk_row;       /* [n_chunks] */
     const int32_t* chunk_tiles;     /* [4*n_chunk_tiles] */
+    const int32_t* hub_rows;        /* [n_hub] row of hub h */
     int32_t n_tiles, n_ftiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
 } ngcf_csr;

@@ -19,7 +19,7 @@ class NgcfCsr(C.Structure):
     """Mirror of ``ngcf_csr`` (include/ngcf_b200.h): a host struct of device pointers."""
     _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp), ("ftiles", _vp),
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
-                ("chunk_row", _vp), ("chunk_tiles", _vp),
+                ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp),
                 ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
                 ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
 

@@ -5,6 +5,8 @@
 // Two launches per product: the hub pass reduces the chunks of the long rows into hub_partial (the same
 // kernel, run over the chunk CSR), the row pass gathers every ordinary row and sums the partials of hub rows.
 // One CTA (4 warps) per tile; the hardware block scheduler balances the tiles.
+#include <stdlib.h>
+
 #include "spmm_core.cuh"
 
 namespace {
@@ -13,9 +15,6 @@ using namespace ngcf;
 
 constexpr int SP_THREADS = 128;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SP_TILE_ROWS = 16;
-constexpr int SP_TILE_ENT = 512;
-static_assert(SP_TILE_ENT >= SPLIT, "a tile must hold the longest ordinary row");
 
 struct SpmmArgs {
     const TileInfo* tiles;
@@ -294,6 +293,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+int ngcf_spmm_stream(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
+                     const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial,
+                     const int32_t* c_ent, const int32_t* c_trp, float* Y, int64_t ldy, cudaStream_t st);
+// NGCF_B200_SPMM=tiled keeps every product on the first (tiled, register-staged) kernel: A/B timing and tests
+static bool ngcf_spmm_force_tiled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NGCF_B200_SPMM");
+        v = (e && e[0] == 't') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 extern "C" int ngcf_spmm_split_threshold(void) { return ngcf::SPLIT; }
 extern "C" int ngcf_spmm_tile_rows(void) { return SP_TILE_ROWS; }
 extern "C" int ngcf_spmm_tile_entries(void) { return SP_TILE_ENT; }
@@ -331,6 +343,10 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
                      (!addend || (aligned16(addend) && ld_add % 4 == 0)) &&
                      (!slot || (aligned16(gsum) && ld_gsum % 4 == 0)) && (g->n_hub == 0 || aligned16(hub_partial));
+    // plain and per-step compacted entry lists take the streaming kernel (spmm_stream.cu); in-kernel hash dropout,
+    // decision bytes and widths that are not a multiple of 4 stay on the tiled kernel below
+    if (vec && !keep_bits && drop_p == 0.f && !ngcf_spmm_force_tiled() && (g->n_hub == 0 || g->hub_rows))
+        return ngcf_spmm_stream(g, X, ldx, d, addend, ld_add, slot, gsum, ld_gsum, hub_partial, c_ent, c_trp, Y, ldy, st);
     if (g->n_hub > 0 && g->n_chunks > 0) {
         SpmmArgs h{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
                    reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, nullptr, nullptr, nullptr, X,

@@ -78,11 +78,12 @@ class CsrSide:
             self.hub_chunk_ptr = cptr.to(torch.int32)
             self.chunk_ptr = chunk_ptr.to(torch.int32)
             self.chunk_row = hub[owner].to(torch.int32)
+            self.hub_rows = hub.to(torch.int32).contiguous()
         else:
             self.colidx, self.perm = colidx.contiguous(), perm.contiguous()
             self.nnz_hub, self.n_chunks = 0, 0
             short_deg = deg
-            self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = None
+            self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = self.hub_rows = None
         self.nnz_short = self.nnz - self.nnz_hub
         self.rowptr = torch.zeros(self.n_rows + 1, **i32)
         self.rowptr[1:] = torch.cumsum(short_deg, 0).to(torch.int32)
@@ -120,6 +121,7 @@ class CsrSide:
             s.hub_ent = ent.data_ptr() + 8 * self.nnz_short
             s.chunk_row = _lib.ptr(self.chunk_row)
             s.chunk_tiles = _lib.ptr(self.chunk_tiles)
+            s.hub_rows = _lib.ptr(self.hub_rows)
             s.n_tiles = int(self.tiles.shape[0])
             s.n_ftiles = int(self.ftiles.shape[0])
             s.n_hub = self.n_hub
