@@ -2,9 +2,11 @@
 // Replaces torch.mm(L, E) (NGCF.py:130: coalesce -> COO->CSR -> cusparseSpMM on CUDA) and the transposed
 // product of its backward (MmBackward0).  See spmm_core.cuh for the data layout and the mapping.
 //
-// Two launches per product: the hub pass reduces the chunks of the long rows into hub_partial (the same
-// kernel, run over the chunk CSR), the row pass gathers every ordinary row and sums the partials of hub rows.
-// One CTA (4 warps) per tile; the hardware block scheduler balances the tiles.
+// ONE launch covers the hub-chunk tiles (first: they are the longest) and the ordinary-row tiles; a small second
+// kernel completes the hub rows from their chunk partial sums, in chunk order.  (First version: hub pass and row pass
+// as two launches, the row pass reading hub_of_row[row] before every row — tools/spmm_timeline.py showed that
+// dependent load plus the narrow tail batches as 4-8 exposed round trips per 16-row tile, and the two launches
+// each paid their own tail.)  One CTA (8 warps) per tile; the hardware block scheduler balances the tiles.
 #include <stdlib.h>
 
 #include "spmm_core.cuh"
@@ -16,34 +18,52 @@ using namespace ngcf;
 constexpr int SP_THREADS = 128;
 constexpr int SP_WARPS = SP_THREADS / 32;
 
-struct SpmmArgs {
+struct TileSide {                   // one tile list: the ordinary rows, or the hub chunks
     const TileInfo* tiles;
     const int32_t* rowptr;
     const int2* ent;
-    const int32_t* row_key;         // hub pass: row of each chunk (dropout key); row pass: NULL
-    const int32_t* hub_of_row;      // row pass: hub id or -1 per row (NULL when the matrix has no hubs)
-    const int32_t* hub_chunk_ptr;
-    const float* hub_partial;       // row pass: input [n_chunks, d]
+    const int32_t* row_key;         // chunk side: row of each chunk (dropout key); row side: NULL
+    const uint8_t* bits;            // optional decision bytes (ngcf_node_dropout_bits), indexed like `ent`
+    const int2* cent;               // optional: this layer's compacted entries (ngcf_node_dropout_compact), tile t at e0
+    const int32_t* ctrp;            // ... and its tile-relative row pointers [n_tiles][SP_TILE_ROWS + 1]
+    float* Y;                       // output rows (chunk side: hub_partial, one row per chunk)
+    int64_t ldy;
+};
+
+struct SpmmArgs {
+    TileSide rows, chunks;
+    int n_chunk_tiles;              // CTAs [0, n_chunk_tiles) take chunk tiles, the rest row tiles
     const float* X;
     uint32_t ldx;
     int d;
-    const float* addend;
+    const float* addend;            // row side only
     int64_t ld_add;
     const int32_t* slot;
     const float* gsum;
     int64_t ld_gsum;
-    float* Y;
-    int64_t ldy;
     float drop_p;
     uint64_t seed;
     const uint64_t* seed_dev;
     int layer;
     int transposed;
     uint32_t row_off;
-    const uint8_t* bits;
-    const int2* cent;               // optional: this layer's compacted entries (ngcf_node_dropout_compact), tile t at e0
-    const int32_t* ctrp;            // ... and its tile-relative row pointers [n_tiles][SP_TILE_ROWS + 1]
+    unsigned long long* dbg;        // optional [n_ctas][4] = {start, staged, done, smid} in globaltimer ns (tools/spmm_timeline.py)
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void stamp_done(unsigned long long* dbg) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[blockIdx.x * 4 + 2] = gtime_ns();
+        dbg[blockIdx.x * 4 + 3] = smid;
+    }
+}
 
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -55,48 +75,72 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     __shared__ __align__(16) int2 ent_s[SP_TILE_ENT];
     __shared__ int rp_s[SP_TILE_ROWS + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
+    const bool chunk_side = (int)blockIdx.x < a.n_chunk_tiles;
+    const TileSide& sd = chunk_side ? a.chunks : a.rows;
+    const int t = chunk_side ? (int)blockIdx.x : (int)blockIdx.x - a.n_chunk_tiles;
+    const int4 raw = *reinterpret_cast<const int4*>(sd.tiles + t);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
-    DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
-                a.row_off, a.bits};
     const int nr = ti.r1 - ti.r0;
-    if (a.ctrp) {
+    if (sd.ctrp) {
         // node dropout already applied for this step and layer: the tile's surviving entries sit compacted at e0
-        const int32_t* trp = a.ctrp + (size_t)blockIdx.x * (SP_TILE_ROWS + 1);
-        for (int i = tid; i <= nr; i += SP_THREADS) rp_s[i] = trp[i];
+        const int32_t* trp = sd.ctrp + (size_t)t * (SP_TILE_ROWS + 1);
+        if (tid <= nr) rp_s[tid] = trp[tid];
         const int cnt = trp[nr];
-        for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(a.cent + ti.e0 + i);
+        for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(sd.cent + ti.e0 + i);
         __syncthreads();
     } else {
-        stage_tile<SP_THREADS>(ti, a.rowptr, a.ent, a.row_key, dr, rp_s, ent_s, tid, CtaSync());
+        DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
+                    a.row_off, sd.bits};
+        stage_tile<SP_THREADS>(ti, sd.rowptr, sd.ent, sd.row_key, dr, rp_s, ent_s, tid, CtaSync());
+    }
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 1] = gtime_ns();
+
+    if (chunk_side) {
+        // a chunk = up to SPLIT entries of one hub row: the whole warp gathers it (lane groups split the entries)
+        for (int i = warp; i < nr; i += SP_WARPS) {
+            const int64_t row = ti.r0 + i;
+            if constexpr (G > 0) {
+                const float4 acc = gather_row_vec<G>(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane);
+                if (lane < G && lane * 4 < a.d) st_f4(sd.Y + row * sd.ldy + lane * 4, acc);
+            } else {
+                float acc[SC_MAXQ];
+                gather_row_sc(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane, acc);
+#pragma unroll
+                for (int q = 0; q < SC_MAXQ; ++q)
+                    if (lane + 32 * q < a.d) sd.Y[row * sd.ldy + lane + 32 * q] = acc[q];
+            }
+        }
+        if (a.dbg) stamp_done(a.dbg);
+        return;
     }
 
-    for (int i = warp; i < nr; i += SP_WARPS) {
-        const int64_t row = ti.r0 + i;
-        const int h = a.hub_of_row ? a.hub_of_row[row] : -1;
-        if constexpr (G > 0) {
-            float4 acc;
-            if (h >= 0) acc = sum_partials_vec<G>(a.hub_partial, a.hub_chunk_ptr[h], a.hub_chunk_ptr[h + 1], a.d, lane);
-            else acc = gather_row_vec<G>(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane);
-            if (lane < G && lane * 4 < a.d) {
-                const int c = lane * 4;
-                if (a.addend) {
-                    const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
-                    acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
+    // ordinary rows (hub rows are empty here: they get addend-only values that hub_finish_kernel overwrites)
+    if constexpr (G > 0) {
+        // the warp's lane groups split one row's entries (measured faster than one row per group: 43.9 vs 47.3 us for
+        // the launch at Gowalla shape — short rows leave fewer lanes idle this way)
+        for (int i = warp; i < nr; i += SP_WARPS) {
+            const int64_t row = ti.r0 + i;
+            const bool ok = lane < G && lane * 4 < a.d;
+            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);                // requested before the gathers, not after them
+            int s = -1;
+            if (ok && a.addend) ad = ld_f4(a.addend + row * a.ld_add + lane * 4);
+            if (ok && a.slot) s = a.slot[row];
+            float4 acc = gather_row_vec<G>(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane);
+            if (ok) {
+                acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
+                if (s >= 0) {
+                    const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + lane * 4);
+                    acc.x += gs.x; acc.y += gs.y; acc.z += gs.z; acc.w += gs.w;
                 }
-                if (a.slot) {
-                    const int s = a.slot[row];
-                    if (s >= 0) {
-                        const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
-                        acc.x += gs.x; acc.y += gs.y; acc.z += gs.z; acc.w += gs.w;
-                    }
-                }
-                st_f4(a.Y + row * a.ldy + c, acc);
+                st_f4(sd.Y + row * sd.ldy + lane * 4, acc);
             }
-        } else {
+        }
+    } else {
+        for (int i = warp; i < nr; i += SP_WARPS) {
+            const int64_t row = ti.r0 + i;
             float acc[SC_MAXQ];
-            if (h >= 0) sum_partials_sc(a.hub_partial, a.hub_chunk_ptr[h], a.hub_chunk_ptr[h + 1], a.d, lane, acc);
-            else gather_row_sc(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane, acc);
+            gather_row_sc(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane, acc);
             const int s = a.slot ? a.slot[row] : -1;
 #pragma unroll
             for (int q = 0; q < SC_MAXQ; ++q) {
@@ -105,8 +149,89 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
                     float r = acc[q];
                     if (a.addend) r += a.addend[row * a.ld_add + col];
                     if (s >= 0) r += a.gsum[(int64_t)s * a.ld_gsum + col];
-                    a.Y[row * a.ldy + col] = r;
+                    sd.Y[row * sd.ldy + col] = r;
                 }
+            }
+        }
+    }
+    if (a.dbg) stamp_done(a.dbg);
+}
+
+// hub rows: Y[row] = sum of the row's chunk partial sums, in chunk order (+ addend) (+ row-gradient row).
+// One warp per hub row; vector path: every group of G lanes computes the same sum, group 0 writes.
+struct HubFinishArgs {
+    const int32_t* hub_rows;
+    const int32_t* hub_chunk_ptr;
+    const float* partial;
+    int n_hub, d;
+    const float* addend;
+    int64_t ld_add;
+    const int32_t* slot;
+    const float* gsum;
+    int64_t ld_gsum;
+    float* Y;
+    int64_t ldy;
+};
+
+constexpr int HF_THREADS = 128;
+template <int G>
+__global__ void __launch_bounds__(HF_THREADS) hub_finish_kernel(HubFinishArgs a) {
+    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
+    const int64_t row = a.hub_rows[h];
+    const int s = a.slot ? a.slot[row] : -1;
+    if constexpr (G > 0) {
+        // the hub with 13 754 entries has 108 partial rows: one warp walking them four at a time was a 20 us tail.
+        // The CTA's lane groups take the chunks round robin; their sums are combined in group order (fixed tree).
+        constexpr int NGRP = HF_THREADS / G;
+        __shared__ __align__(16) float4 part[NGRP][G];
+        const int j = tid / G, l = tid % G;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l * 4 < a.d) {
+            int c = c0 + j;
+            for (; c + 3 * NGRP < c1; c += 4 * NGRP) {
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = ld_f4(a.partial + (int64_t)(c + u * NGRP) * a.d + l * 4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+            }
+            for (; c < c1; c += NGRP) {
+                const float4 x = ld_f4(a.partial + (int64_t)c * a.d + l * 4);
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            }
+        }
+        part[j][l] = acc;
+        __syncthreads();
+        if (j == 0 && l * 4 < a.d) {
+#pragma unroll
+            for (int k = 1; k < NGRP; ++k) {
+                const float4 x = part[k][l];
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            }
+            const int c = l * 4;
+            if (a.addend) {
+                const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
+                acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
+            }
+            if (s >= 0) {
+                const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
+                acc.x += gs.x; acc.y += gs.y; acc.z += gs.z; acc.w += gs.w;
+            }
+            st_f4(a.Y + row * a.ldy + c, acc);
+        }
+    } else {
+        if (tid >= 32) return;                                        // scalar path: one warp per hub row
+        float acc[SC_MAXQ];
+        sum_partials_sc(a.partial, c0, c1, a.d, lane, acc);
+#pragma unroll
+        for (int q = 0; q < SC_MAXQ; ++q) {
+            const int col = lane + 32 * q;
+            if (col < a.d) {
+                float r = acc[q];
+                if (a.addend) r += a.addend[row * a.ld_add + col];
+                if (s >= 0) r += a.gsum[(int64_t)s * a.ld_gsum + col];
+                a.Y[row * a.ldy + col] = r;
             }
         }
     }
@@ -271,40 +396,34 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
 }
 
 template <int G>
-int launch(const SpmmArgs& a, int n_tiles, cudaStream_t st, const char* what) {
-    if (n_tiles <= 0) return NGCF_OK;
-    spmm_tile_kernel<G><<<(unsigned)n_tiles, SP_THREADS, 0, st>>>(a);
-    NGCF_LAUNCH_OK(what);
+int launch(const SpmmArgs& a, int n_ctas, const HubFinishArgs& hf, cudaStream_t st) {
+    if (n_ctas > 0) {
+        spmm_tile_kernel<G><<<(unsigned)n_ctas, SP_THREADS, 0, st>>>(a);
+        NGCF_LAUNCH_OK("spmm_tile_kernel");
+    }
+    if (hf.n_hub > 0) {
+        hub_finish_kernel<G><<<(unsigned)hf.n_hub, HF_THREADS, 0, st>>>(hf);
+        NGCF_LAUNCH_OK("hub_finish_kernel");
+    }
     return NGCF_OK;
 }
 
-int launch_any(const SpmmArgs& a, int n_tiles, bool vec, cudaStream_t st, const char* what) {
-    if (!vec) return launch<0>(a, n_tiles, st, what);
+int launch_any(const SpmmArgs& a, int n_ctas, const HubFinishArgs& hf, bool vec, cudaStream_t st) {
+    if (!vec) return launch<0>(a, n_ctas, hf, st);
     const int d4 = a.d / 4;
-    if (d4 <= 1) return launch<1>(a, n_tiles, st, what);
-    if (d4 <= 2) return launch<2>(a, n_tiles, st, what);
-    if (d4 <= 4) return launch<4>(a, n_tiles, st, what);
-    if (d4 <= 8) return launch<8>(a, n_tiles, st, what);
-    if (d4 <= 16) return launch<16>(a, n_tiles, st, what);
-    return launch<32>(a, n_tiles, st, what);
+    if (d4 <= 1) return launch<1>(a, n_ctas, hf, st);
+    if (d4 <= 2) return launch<2>(a, n_ctas, hf, st);
+    if (d4 <= 4) return launch<4>(a, n_ctas, hf, st);
+    if (d4 <= 8) return launch<8>(a, n_ctas, hf, st);
+    if (d4 <= 16) return launch<16>(a, n_ctas, hf, st);
+    return launch<32>(a, n_ctas, hf, st);
 }
+
+unsigned long long* g_spmm_dbg = nullptr;    // host copy of the debug buffer pointer
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
-
-int ngcf_spmm_stream(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
-                     const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial,
-                     const int32_t* c_ent, const int32_t* c_trp, float* Y, int64_t ldy, cudaStream_t st);
-// NGCF_B200_SPMM=tiled keeps every product on the first (tiled, register-staged) kernel: A/B timing and tests
-static bool ngcf_spmm_force_tiled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("NGCF_B200_SPMM");
-        v = (e && e[0] == 't') ? 1 : 0;
-    }
-    return v == 1;
-}
 
 extern "C" int ngcf_spmm_split_threshold(void) { return ngcf::SPLIT; }
 extern "C" int ngcf_spmm_tile_rows(void) { return SP_TILE_ROWS; }
@@ -343,24 +462,26 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
                      (!addend || (aligned16(addend) && ld_add % 4 == 0)) &&
                      (!slot || (aligned16(gsum) && ld_gsum % 4 == 0)) && (g->n_hub == 0 || aligned16(hub_partial));
-    // plain and per-step compacted entry lists take the streaming kernel (spmm_stream.cu); in-kernel hash dropout,
-    // decision bytes and widths that are not a multiple of 4 stay on the tiled kernel below
-    if (vec && !keep_bits && drop_p == 0.f && !ngcf_spmm_force_tiled() && (g->n_hub == 0 || g->hub_rows))
-        return ngcf_spmm_stream(g, X, ldx, d, addend, ld_add, slot, gsum, ld_gsum, hub_partial, c_ent, c_trp, Y, ldy, st);
-    if (g->n_hub > 0 && g->n_chunks > 0) {
-        SpmmArgs h{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
-                   reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row, nullptr, nullptr, nullptr, X,
-                   (uint32_t)ldx, d, nullptr, 0, nullptr, nullptr, 0, hub_partial, d, drop_p, seed, seed_dev, layer,
-                   transposed, (uint32_t)row_offset, keep_bits ? keep_bits + g->rowptr_nnz : nullptr,
-                   c_ent ? reinterpret_cast<const int2*>(c_ent) + g->rowptr_nnz : nullptr,
-                   c_trp ? c_trp + (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : nullptr};
-        if ((rc = launch_any(h, g->n_chunk_tiles, vec, st, "spmm_tile_kernel(hub chunks)")) != NGCF_OK) return rc;
-    }
-    SpmmArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
-               g->n_hub > 0 ? g->hub_of_row : nullptr, g->hub_chunk_ptr, hub_partial, X, (uint32_t)ldx, d, addend,
-               ld_add, slot, gsum, ld_gsum, Y, ldy, drop_p, seed, seed_dev, layer, transposed, (uint32_t)row_offset,
-               keep_bits, reinterpret_cast<const int2*>(c_ent), c_trp};
-    return launch_any(a, g->n_tiles, vec, st, "spmm_tile_kernel(rows)");
+    const bool hubs = g->n_hub > 0 && g->n_chunks > 0;
+    NGCF_REQUIRE(!hubs || g->hub_rows, "spmm: hub_rows missing");
+    SpmmArgs a{};
+    a.rows = TileSide{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
+                      keep_bits, reinterpret_cast<const int2*>(c_ent), c_trp, Y, ldy};
+    a.n_chunk_tiles = hubs ? g->n_chunk_tiles : 0;
+    if (hubs)
+        a.chunks = TileSide{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
+                            reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row,
+                            keep_bits ? keep_bits + g->rowptr_nnz : nullptr,
+                            c_ent ? reinterpret_cast<const int2*>(c_ent) + g->rowptr_nnz : nullptr,
+                            c_trp ? c_trp + (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : nullptr, hub_partial, d};
+    a.X = X; a.ldx = (uint32_t)ldx; a.d = d;
+    a.addend = addend; a.ld_add = ld_add; a.slot = slot; a.gsum = gsum; a.ld_gsum = ld_gsum;
+    a.drop_p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.layer = layer; a.transposed = transposed;
+    a.row_off = (uint32_t)row_offset;
+    a.dbg = g_spmm_dbg;
+    HubFinishArgs hf{g->hub_rows, g->hub_chunk_ptr, hub_partial, hubs ? g->n_hub : 0, d, addend, ld_add, slot, gsum,
+                     ld_gsum, Y, ldy};
+    return launch_any(a, a.n_chunk_tiles + g->n_tiles, hf, vec, st);
 }
 
 extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,
@@ -434,5 +555,11 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
         else compact_kernel<4><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
         NGCF_LAUNCH_OK(pass ? "compact_kernel(hub chunks)" : "compact_kernel(rows)");
     }
+    return NGCF_OK;
+}
+
+// debugging aid (tools/spmm_timeline.py): device buffer [n_ctas][4] of uint64 that every spmm_tile_kernel CTA stamps
+extern "C" int ngcf_debug_spmm_timeline(unsigned long long* dev_buf_or_null) {
+    g_spmm_dbg = dev_buf_or_null;
     return NGCF_OK;
 }

@@ -15,7 +15,7 @@
 
 namespace ngcf {
 
-constexpr int SPLIT = 64;           // rows with more entries than this are hubs; also the hub chunk size
+constexpr int SPLIT = 128;          // rows with more entries than this are hubs; also the hub chunk size
 constexpr int SP_TILE_ROWS = 16;    // SpMM tile: at most this many rows ...
 constexpr int SP_TILE_ENT = 512;    // ... and this many entries (staged in shared memory by one CTA)
 static_assert(SP_TILE_ENT >= SPLIT, "a tile must hold the longest ordinary row");

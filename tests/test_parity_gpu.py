@@ -614,11 +614,11 @@ def test_node_dropout_modes_agree():
         res[mode] = [uu.detach().clone(), pp.detach().clone(), loss.detach().clone()] + \
                     [p.grad.clone() for p in m.parameters() if p.grad is not None]
     for i, (a, b_) in enumerate(zip(res["bits"], res["inkernel"])):
-        if i < 3:
-            assert torch.equal(a, b_)                             # outputs and loss: the very same sums
-        else:
-            assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) <= 2e-6   # W/b gradients are summed with float atomics
+        if i < 2:
+            assert torch.equal(a, b_)                             # output rows: the very same sums
+        else:                                                     # loss, W/b gradients: summed with float atomics
+            assert rel_err(a.cpu().numpy().reshape(-1), b_.cpu().numpy().reshape(-1)) <= 2e-6
     # compaction shifts an entry's position inside its row, hence its lane group in the row sum: same terms,
     # different fp32 summation tree
     for a, b_ in zip(res["compact"], res["inkernel"]):
-        assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) <= 2e-6
+        assert rel_err(a.cpu().numpy().reshape(-1), b_.cpu().numpy().reshape(-1)) <= 2e-6
