@@ -305,26 +305,45 @@ def run_ours(args):
     else:
         ms_e2e, loss_val = ms_e2e_eager, loss_eager
 
-    # ---- roofline of the dominant kernel: the propagation SpMM, timed alone, cold L2 ----------------------------
+    # ---- roofline of the dominant kernel: the propagation SpMM of layer 0 exactly as the step runs it (this step's
+    # node-dropout survivors, compacted), timed alone, cold L2 ----------------------------------------------------------
+    from seoul_tourism_recommendation_ngcf_b200.plan import node_dropout_compact
     plan = model._last.plan                       # this rank's row shard when world > 1
     N, nnz, d = plan.fwd.n_rows, plan.fwd.nnz, info["emb"]
     X = model._packed_table()
     Y = torch.empty(N, d, device=dev)
+    comp, _ = node_dropout_compact(plan.fwd, NODE_P, 1, None, info["layers"], model._shard.r0 if model._shard else 0,
+                                   as_L=True, as_Lt=False)
+    per = lib.ngcf_spmm_tile_rows() + 1
+
+    def kept_entries(side, trp):
+        t = trp.view(-1, per).cpu().numpy()
+        tiles = [side.tiles.cpu().numpy()] + ([side.chunk_tiles.cpu().numpy()] if side.chunk_tiles is not None else [])
+        nr = np.concatenate([x[:, 1] - x[:, 0] for x in tiles])
+        return int(t[np.arange(t.shape[0]), nr].sum())
+
+    nnz_kept = kept_entries(plan.fwd, comp[0][1])
     reps = 20
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for _ in range(3):
-        spmm(plan.fwd, None, X, d, out=Y, drop_p=NODE_P, seed=1, layer=0)
-    torch.cuda.synchronize()
+
+    def time_spmm(compact):
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for _ in range(3):
+            spmm(plan.fwd, None, X, d, out=Y, compact=compact)
+        torch.cuda.synchronize()
+        for j in range(reps):
+            flush.zero_()
+            kev[j][0].record()
+            spmm(plan.fwd, None, X, d, out=Y, compact=compact)
+            kev[j][1].record()
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in kev)
+
     w0 = time.time()
-    for j in range(reps):
-        flush.zero_()
-        kev[j][0].record()
-        spmm(plan.fwd, None, X, d, out=Y, drop_p=NODE_P, seed=1, layer=0)
-        kev[j][1].record()
-    torch.cuda.synchronize()
+    k_ms = time_spmm(comp[0])
+    k_ms_full = time_spmm(None)                                  # the same product without node dropout (eval / demo)
     windows.append((w0, time.time()))
-    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
-    alg_bytes = 8 * nnz + 4 * (N + 1) + 8 * N * d               # SURVEY.md section 8(d), SpMM-only per layer
+    alg_bytes = 8 * nnz_kept + 4 * (N + 1) + 8 * N * d          # SURVEY.md section 8(d), SpMM-only per layer
+    alg_bytes_full = 8 * nnz + 4 * (N + 1) + 8 * N * d
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -335,11 +354,20 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.shape)
-    roofline = {"kernel": "spmm_tile_kernel<16> x2 (hub-chunk pass + row pass) = one ngcf_spmm call, layer 0"
+    roofline = {"kernel": "spmm_tile_kernel<16> (hub-chunk tiles + row tiles in one launch) = one ngcf_spmm call: "
+                          "layer 0 of the step, node-dropout survivors (p = 0.3) compacted"
                           + (f", row shard of rank 0 of {world}" if world > 1 else ""),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                "kernel_ms": round(k_ms, 5), "peak_source": peak_src, "timing": "CUDA events, cold L2 (flushed)"}
+                "entries_gathered": nnz_kept, "kernel_ms": round(k_ms, 5), "peak_source": peak_src,
+                "timing": "CUDA events around the call, cold L2 (flushed), mean of 20",
+                "l2_gather_tb_s": round(nnz_kept * 4 * d / (k_ms * 1e-3) / 1e12, 2),
+                "note": "every entry gathers one 4*d-byte embedding row through L2 (l2_gather_tb_s): that traffic, "
+                        "not HBM, bounds the kernel; see DESIGN.md section 4",
+                "no_dropout": {"kernel_ms": round(k_ms_full, 5), "algorithmic_bytes": alg_bytes_full,
+                               "achieved": round(alg_bytes_full / (k_ms_full * 1e-3) / 1e9, 1),
+                               "frac": round(alg_bytes_full / (k_ms_full * 1e-3) / 1e9 / peak, 4),
+                               "l2_gather_tb_s": round(nnz * 4 * d / (k_ms_full * 1e-3) / 1e12, 2)}}
 
     clocks = sampler.stop(windows)
 
@@ -377,7 +405,7 @@ def run_ours(args):
         "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": int(L._nnz()), "N": int(L.shape[0]),
                    "parallelism": "single GPU" if world == 1 else
                    f"row-sharded x{world} (equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads)",
-                   "rng": "device (counter-based hash, in-kernel)", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "rng": "device (counter-based hash); node-dropout survivors compacted once per step", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                    "api": api},
         "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_val},

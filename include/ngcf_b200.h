@@ -77,6 +77,8 @@ typedef struct ngcf_csr {
     const int32_t* chunk_row;       /* [n_chunks] */
     const int32_t* chunk_tiles;     /* [4*n_chunk_tiles] */
     const int32_t* hub_rows;        /* [n_hub] row of hub h */
+    int32_t* hub_done;              /* [n_hub] completion counters of a product in flight: all zero between calls
+                                       (ngcf_spmm leaves them zero); one product per csr at a time */
     int32_t n_tiles, n_ftiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
 } ngcf_csr;
@@ -108,8 +110,8 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
 
 /* ---- SpMM: torch.mm(L, E), NGCF.py:130, and its backward L^T·gS (autograd MmBackward0) ----------
  * Y[i,:] = sum_t val[t] * X[col[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
- * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in order by the row
- * pass, so the result is deterministic (no float atomics).
+ * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in chunk order by the warp
+ * that completes the hub's last chunk, so the result is deterministic (no float atomics).
  *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
  *               (the IndexBackward scatter of NGCF.py:151-155 folded into the last backward SpMM).
  *   drop_p > 0: device-RNG node dropout (NGCF.py:93-100,124-126) evaluated in-kernel: entry (r,c) of L survives

@@ -29,7 +29,7 @@ def _stream() -> int:
 
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
-    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "comp_b_stream", "mess_bits",
                  "rows", "offsets", "W1", "W2")
 
 
@@ -53,16 +53,29 @@ class _Propagate(torch.autograd.Function):
         X0 = mod._packed_table()                                       # [N(_pad), d0] = cat(user, item), NGCF.py:120
         st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
-        st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
+        st.bits_f = st.bits_b = st.comp_f = st.comp_b = st.comp_b_stream = None
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
             # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
             # deletes the dropped entries like NGCF.sparse_dropout does, so layer k gathers (1-p)^(k+1) of the rows
             shared = st.plan.side(True, False) is side
             if mod._node_mode == "compact":
-                st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
-                if shared:
-                    st.comp_b = ct
+                if mod._overlap and torch.is_grad_enabled():
+                    # the forward needs L's survivors now; L^T's are first used by the backward, so that half of the
+                    # pass runs on a side stream next to the forward (joined in backward)
+                    main = torch.cuda.current_stream()
+                    if mod._side_stream is None:
+                        mod._side_stream = torch.cuda.Stream()
+                    mod._side_stream.wait_stream(main)
+                    with torch.cuda.stream(mod._side_stream):
+                        _, st.comp_b = node_dropout_compact(st.plan.side(True, False), st.drop_p, st.seed, st.seed_dev, K,
+                                                            r0, as_L=False, as_Lt=True)
+                    st.comp_b_stream = mod._side_stream
+                    st.comp_f, _ = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=False)
+                else:
+                    st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
+                    if shared:
+                        st.comp_b = ct
             elif mod._node_mode == "bits":
                 st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
                 if shared:
@@ -151,6 +164,9 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
+        if st.comp_b_stream is not None:                              # L^T's survivors were compacted next to the forward
+            torch.cuda.current_stream().wait_stream(st.comp_b_stream)
+            st.comp_b_stream = None
         if st.drop_p > 0 and mod._node_mode == "compact" and st.comp_b is None:
             _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         if st.drop_p > 0 and mod._node_mode == "bits" and st.bits_b is None:
@@ -248,6 +264,10 @@ class NGCF(nn.Module):
         self._all_E = None
         self._mess_bits = os.environ.get("NGCF_B200_MESS_BITS", "0") == "1"   # precompute message-dropout bits per step
         self._node_mode = "compact"   # device-RNG node dropout: "compact" (survivors only), "bits", or "inkernel"
+        # L^T's half of the compaction pass on a side stream next to the forward: measured SLOWER (650 vs 632 us per
+        # step at Gowalla shape: the forward's kernels are throughput-bound, the extra pass re-reads the entries)
+        self._overlap = os.environ.get("NGCF_B200_OVERLAP", "0") == "1"
+        self._side_stream = None
         self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libngcf_b200.so")
+LIB_PATH = os.environ.get("NGCF_B200_LIB") or os.path.join(_PKG, "libngcf_b200.so")   # env override: A/B builds
 
 _vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_size_t
 
@@ -19,7 +19,7 @@ class NgcfCsr(C.Structure):
     """Mirror of ``ngcf_csr`` (include/ngcf_b200.h): a host struct of device pointers."""
     _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp), ("ftiles", _vp),
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
-                ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp),
+                ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp),
                 ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
                 ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
 

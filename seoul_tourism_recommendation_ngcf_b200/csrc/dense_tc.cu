@@ -19,6 +19,14 @@ namespace {
 
 using namespace tc;
 
+// optional per-role timeline of CTA 0 (tools/bwd_timeline.py): SM clock at the protocol points of each tile
+__device__ long long g_bwd_dbg[4][8][8];   // [3][tile][k] = loader warp 0 inside its tile: first half computed, next loads issued, second half, fence
+__device__ int g_bwd_dbg_on = 0;
+#define BWD_STAMP(role, it, k)                                                   \
+    do {                                                                         \
+        if (dbg && lane == 0 && (it) < 8) g_bwd_dbg[role][it][k] = clock64();    \
+    } while (0)
+
 constexpr int TC_ROWS = 128;                 // UMMA M
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_LOAD_WARPS = 8;
@@ -104,8 +112,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     }
     if (warp == FW_MMA_WARP) tmem_alloc(&bars->tmem_base, 128);           // 2 accumulators x 64 fp32 columns
     // B[n][k] = wcat[k][n], split and swizzled (row n of K block kb: 32 values of k)
+    // (consecutive threads take consecutive n: the four loads below are then coalesced rows of wcat; with c fastest
+    // every lane touched its own cache line and this set-up was ~30 % of the kernel's warp time in ncu)
     for (int i = tid; i < d_out * KB * 8; i += TC_THREADS) {
-        const int c = i & 7, n = (i >> 3) % d_out, kb = (i >> 3) / d_out;
+        const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
         float4 w;
         const float* src = a.wcat + (int64_t)(kb * 32 + c * 4) * d_out + n;
         w.x = src[0]; w.y = src[d_out]; w.z = src[2 * d_out]; w.w = src[3 * d_out];
@@ -123,6 +133,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     const uint32_t tmem_base = bars->tmem_base;
 
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    const bool dbg = g_bwd_dbg_on && blockIdx.x == 0 && (warp == 0 || warp == FW_MMA_WARP || warp == FW_MMA_WARP + 1);
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();
 
     if (warp < FW_EPI_WARPS) {
         // ======================= epilogue =======================================================================
@@ -138,7 +150,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int buf = it & 1;
+            BWD_STAMP(0, it, 0);
             mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+            BWD_STAMP(0, it, 1);
             tc_fence_after_sync();
             float v[32];
             if (has_chunk) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 64 + c * 32, v);
@@ -186,6 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                     }
                 }
             }
+            BWD_STAMP(0, it, 2);
         }
     } else if (warp == FW_MMA_WARP) {
         // ======================= MMA issuer =====================================================================
@@ -225,53 +240,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         }
     } else {
         // ======================= loaders ========================================================================
+        // Software-pipelined by quarter steps (64 rows x 32 columns of S and of E = 4 + 4 float4 per thread): the loads
+        // of the next quarter are in flight while this one is split and stored (first version: load a half, wait,
+        // convert — the loaders were the critical path at ~7000 cycles per tile, two exposed round trips each).
         const int lt = tid - (FW_EPI_WARPS + 1) * 32;                     // 0 .. 127
         constexpr int LT = FW_LOAD_WARPS * 32;
-        constexpr int Q = TC_ROWS * 8 / LT;                               // 16-byte chunks per thread per 32-column half
-        for (int it = 0; it < n_my; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int64_t row0 = (int64_t)tile * TC_ROWS;
-            for (int hh = 0; hh < KBH; ++hh) {
-                const int kb1 = hh, kb2 = KBH + hh;
-                float4 s[Q], e[Q];
+        constexpr int QQ = (TC_ROWS / 2) * 8 / LT;                        // 16-byte chunks per thread per quarter step
+        struct Stage {
+            float4 s[QQ], e[QQ];
+        };
+        const int total_q = n_my * KBH * 2;
+        auto issue = [&](Stage& g, int i) {
+            const int it = i / (2 * KBH), hh = (i >> 1) % KBH, half_rows = (i & 1) * (TC_ROWS / 2);
+            const int64_t row0 = (int64_t)(blockIdx.x + it * gridDim.x) * TC_ROWS + half_rows;
 #pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
-                    const int64_t row = row0 + r;
-                    s[q] = e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < a.n_rows) {
-                        s[q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
-                        e[q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
-                    }
-                }
-                mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
-                mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
-                    const uint32_t off = sw128_offset(r, c);
-                    const float4 x1 = make_float4(s[q].x + e[q].x, s[q].y + e[q].y, s[q].z + e[q].z, s[q].w + e[q].w);
-                    const float4 x2 = make_float4(s[q].x * e[q].x, s[q].y * e[q].y, s[q].z * e[q].z, s[q].w * e[q].w);
-                    float4 hi, lo;
-                    split_tf32(x1, hi, lo);
-                    *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
-                    *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
-                    split_tf32(x2, hi, lo);
-                    *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
-                    *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bars->full[kb1]);
-                    mbar_arrive(&bars->full[kb2]);
+            for (int q = 0; q < QQ; ++q) {
+                const int idx = q * LT + lt, r = idx >> 3, c = idx & 7;
+                const int64_t row = row0 + r;
+                g.s[q] = g.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < a.n_rows) {
+                    g.s[q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
+                    g.e[q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
                 }
             }
+        };
+        auto convert = [&](const Stage& g, int i) {
+            const int hh = (i >> 1) % KBH, half_rows = (i & 1) * (TC_ROWS / 2);
+            const int kb1 = hh, kb2 = KBH + hh;
+#pragma unroll
+            for (int q = 0; q < QQ; ++q) {
+                const int idx = q * LT + lt, r = (idx >> 3) + half_rows, c = idx & 7;
+                const uint32_t off = sw128_offset(r, c);
+                const float4 sv = g.s[q], ev = g.e[q];
+                const float4 x1 = make_float4(sv.x + ev.x, sv.y + ev.y, sv.z + ev.z, sv.w + ev.w);
+                const float4 x2 = make_float4(sv.x * ev.x, sv.y * ev.y, sv.z * ev.z, sv.w * ev.w);
+                float4 hi, lo;
+                split_tf32_trunc(x1, hi, lo);
+                *reinterpret_cast<float4*>(A_hi + kb1 * TC_A_BLOCK + off) = hi;
+                *reinterpret_cast<float4*>(A_lo + kb1 * TC_A_BLOCK + off) = lo;
+                split_tf32_trunc(x2, hi, lo);
+                *reinterpret_cast<float4*>(A_hi + kb2 * TC_A_BLOCK + off) = hi;
+                *reinterpret_cast<float4*>(A_lo + kb2 * TC_A_BLOCK + off) = lo;
+            }
+        };
+        Stage g0, g1;
+        if (total_q > 0) issue(g0, 0);
+        for (int i = 0; i < total_q; i += 2) {                            // quarter i: rows 0..63 (g0), i + 1: rows 64..127 (g1)
+            const int it = i / (2 * KBH), hh = (i >> 1) % KBH;
+            const int kb1 = hh, kb2 = KBH + hh;
+            issue(g1, i + 1);
+            BWD_STAMP(2, it, hh * 3 + 0);
+            mbar_wait(&bars->empty[kb1], (it & 1) ^ 1);
+            mbar_wait(&bars->empty[kb2], (it & 1) ^ 1);
+            BWD_STAMP(2, it, hh * 3 + 1);
+            convert(g0, i);
+            if (i + 2 < total_q) issue(g0, i + 2);
+            convert(g1, i + 1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->full[kb1]);
+                mbar_arrive(&bars->full[kb2]);
+            }
+            BWD_STAMP(2, it, hh * 3 + 2);
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[1][7][7] = clock64();
     if (warp == FW_MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 128);
@@ -326,14 +363,6 @@ struct BwdTcArgs {
     int64_t row_off;
 };
 
-// optional per-role timeline of CTA 0 (tools/bwd_timeline.py): SM clock at the protocol points of each tile
-__device__ long long g_bwd_dbg[4][8][8];   // [3][tile][k] = loader warp 0 inside its tile: first half computed, next loads issued, second half, fence
-__device__ int g_bwd_dbg_on = 0;
-#define BWD_STAMP(role, it, k)                                                   \
-    do {                                                                         \
-        if (dbg && lane == 0 && (it) < 8) g_bwd_dbg[role][it][k] = clock64();    \
-    } while (0)
-
 struct BwdBars {
     uint64_t full_gm, empty_gm, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
@@ -382,8 +411,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // T x2 (128 columns each)
     if (tid < 64) bars->colsum[tid] = 0.f;
     // BT[n][o] = W1[o][n] (n < 64), W2[o][n-64]; W1/W2 are [d_out, d_in] row-major
+    // (consecutive threads take consecutive n = consecutive addresses of W1 / W2: coalesced)
     for (int i = tid; i < 128 * KBo * 8; i += TC_THREADS) {
-        const int c = i & 7, n = (i >> 3) & 127, kb = i >> 10;
+        const int n = i & 127, c = (i >> 7) & 7, kb = i >> 10;
         const float* W = (n < d_in ? a.W1 : a.W2) + (n & 63);
         const int o0 = kb * 32 + c * 4;
         float4 w = make_float4(W[(int64_t)o0 * d_in], W[(int64_t)(o0 + 1) * d_in], W[(int64_t)(o0 + 2) * d_in],
@@ -621,7 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
                 if (col_ok) {
                     float4 hi, lo;
-                    split_tf32(g, hi, lo);
+                    split_tf32_trunc(g, hi, lo);
                     const uint32_t off = (hl >> 3) * TC_A_BLOCK + sw128_offset(r, hl & 7);
                     *reinterpret_cast<float4*>(GM_hi + off) = hi;
                     *reinterpret_cast<float4*>(GM_lo + off) = lo;

@@ -2,8 +2,8 @@
 // Replaces torch.mm(L, E) (NGCF.py:130: coalesce -> COO->CSR -> cusparseSpMM on CUDA) and the transposed
 // product of its backward (MmBackward0).  See spmm_core.cuh for the data layout and the mapping.
 //
-// ONE launch covers the hub-chunk tiles (first: they are the longest) and the ordinary-row tiles; a small second
-// kernel completes the hub rows from their chunk partial sums, in chunk order.  (First version: hub pass and row pass
+// ONE launch covers the hub-chunk tiles (first: they are the longest) and the ordinary-row tiles; the warp that
+// stores the last chunk partial of a hub row completes that row from the partial sums, in chunk order.  (First version: hub pass and row pass
 // as two launches, the row pass reading hub_of_row[row] before every row — tools/spmm_timeline.py showed that
 // dependent load plus the narrow tail batches as 4-8 exposed round trips per 16-row tile, and the two launches
 // each paid their own tail.)  One CTA (8 warps) per tile; the hardware block scheduler balances the tiles.
@@ -41,6 +41,13 @@ struct SpmmArgs {
     const int32_t* slot;
     const float* gsum;
     int64_t ld_gsum;
+    // hub rows: the warp that stores the LAST chunk partial of a hub (counted in hub_done) sums the hub's partials in
+    // chunk order and writes the row; the counter is left at zero again
+    const int32_t* hub_of_row;      // [n_rows] hub id or -1 (NULL: no hubs)
+    const int32_t* hub_chunk_ptr;   // [n_hub + 1]
+    int32_t* hub_done;              // [n_hub], all zero between calls
+    float* Yrows;                   // the product's output (chunk side writes its own hub rows there)
+    int64_t ld_yrows;
     float drop_p;
     uint64_t seed;
     const uint64_t* seed_dev;
@@ -74,6 +81,7 @@ template <int G>
 __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     __shared__ __align__(16) int2 ent_s[SP_TILE_ENT];
     __shared__ int rp_s[SP_TILE_ROWS + 1];
+    __shared__ int hub_s[SP_TILE_ROWS];                               // row side: hub id of each tile row, or -1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
     const bool chunk_side = (int)blockIdx.x < a.n_chunk_tiles;
@@ -82,6 +90,8 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     const int4 raw = *reinterpret_cast<const int4*>(sd.tiles + t);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
     const int nr = ti.r1 - ti.r0;
+    if (tid < nr)      // chunk side: the chunk's row; row side: is the row a hub (then it is not written here)
+        hub_s[tid] = chunk_side ? a.hub_of_row[sd.row_key[ti.r0 + tid]] : (a.hub_of_row ? a.hub_of_row[ti.r0 + tid] : -1);
     if (sd.ctrp) {
         // node dropout already applied for this step and layer: the tile's surviving entries sit compacted at e0
         const int32_t* trp = sd.ctrp + (size_t)t * (SP_TILE_ROWS + 1);
@@ -99,27 +109,69 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     if (chunk_side) {
         // a chunk = up to SPLIT entries of one hub row: the whole warp gathers it (lane groups split the entries)
         for (int i = warp; i < nr; i += SP_WARPS) {
-            const int64_t row = ti.r0 + i;
+            const int64_t chunk = ti.r0 + i;
+            const int h = hub_s[i];
             if constexpr (G > 0) {
                 const float4 acc = gather_row_vec<G>(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane);
-                if (lane < G && lane * 4 < a.d) st_f4(sd.Y + row * sd.ldy + lane * 4, acc);
+                if (lane < G && lane * 4 < a.d) st_f4(sd.Y + chunk * sd.ldy + lane * 4, acc);
             } else {
                 float acc[SC_MAXQ];
                 gather_row_sc(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane, acc);
 #pragma unroll
                 for (int q = 0; q < SC_MAXQ; ++q)
-                    if (lane + 32 * q < a.d) sd.Y[row * sd.ldy + lane + 32 * q] = acc[q];
+                    if (lane + 32 * q < a.d) sd.Y[chunk * sd.ldy + lane + 32 * q] = acc[q];
+            }
+            // completion count of the hub; the last arriving warp finishes the row
+            __threadfence();
+            __syncwarp();
+            const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(a.hub_done + h, 1) + 1 == c1 - c0);
+            last = __shfl_sync(FULL_MASK, last, 0);
+            if (!last) continue;
+            __threadfence();
+            if (lane == 0) a.hub_done[h] = 0;                         // ready for the next product
+            const int64_t row = sd.row_key[chunk] ;
+            const int s = a.slot ? a.slot[row] : -1;
+            if constexpr (G > 0) {
+                float4 sum = sum_partials_split<G>(sd.Y, c0, c1, a.d, lane);
+                if (lane < G && lane * 4 < a.d) {
+                    const int c = lane * 4;
+                    if (a.addend) {
+                        const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
+                        sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
+                    }
+                    if (s >= 0) {
+                        const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
+                        sum.x += gs.x; sum.y += gs.y; sum.z += gs.z; sum.w += gs.w;
+                    }
+                    st_f4(a.Yrows + row * a.ld_yrows + c, sum);
+                }
+            } else {
+                float sum[SC_MAXQ];
+                sum_partials_sc(sd.Y, c0, c1, a.d, lane, sum);
+#pragma unroll
+                for (int q = 0; q < SC_MAXQ; ++q) {
+                    const int col = lane + 32 * q;
+                    if (col < a.d) {
+                        float r = sum[q];
+                        if (a.addend) r += a.addend[row * a.ld_add + col];
+                        if (s >= 0) r += a.gsum[(int64_t)s * a.ld_gsum + col];
+                        a.Yrows[row * a.ld_yrows + col] = r;
+                    }
+                }
             }
         }
         if (a.dbg) stamp_done(a.dbg);
         return;
     }
 
-    // ordinary rows (hub rows are empty here: they get addend-only values that hub_finish_kernel overwrites)
+    // ordinary rows (hub rows are written by the chunk side)
     if constexpr (G > 0) {
         // the warp's lane groups split one row's entries (measured faster than one row per group: 43.9 vs 47.3 us for
         // the launch at Gowalla shape — short rows leave fewer lanes idle this way)
         for (int i = warp; i < nr; i += SP_WARPS) {
+            if (hub_s[i] >= 0) continue;
             const int64_t row = ti.r0 + i;
             const bool ok = lane < G && lane * 4 < a.d;
             float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);                // requested before the gathers, not after them
@@ -138,6 +190,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
         }
     } else {
         for (int i = warp; i < nr; i += SP_WARPS) {
+            if (hub_s[i] >= 0) continue;
             const int64_t row = ti.r0 + i;
             float acc[SC_MAXQ];
             gather_row_sc(ent_s, rp_s[i], rp_s[i + 1], a.X, a.ldx, a.d, lane, acc);
@@ -155,86 +208,6 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
         }
     }
     if (a.dbg) stamp_done(a.dbg);
-}
-
-// hub rows: Y[row] = sum of the row's chunk partial sums, in chunk order (+ addend) (+ row-gradient row).
-// One warp per hub row; vector path: every group of G lanes computes the same sum, group 0 writes.
-struct HubFinishArgs {
-    const int32_t* hub_rows;
-    const int32_t* hub_chunk_ptr;
-    const float* partial;
-    int n_hub, d;
-    const float* addend;
-    int64_t ld_add;
-    const int32_t* slot;
-    const float* gsum;
-    int64_t ld_gsum;
-    float* Y;
-    int64_t ldy;
-};
-
-constexpr int HF_THREADS = 128;
-template <int G>
-__global__ void __launch_bounds__(HF_THREADS) hub_finish_kernel(HubFinishArgs a) {
-    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
-    const int64_t row = a.hub_rows[h];
-    const int s = a.slot ? a.slot[row] : -1;
-    if constexpr (G > 0) {
-        // the hub with 13 754 entries has 108 partial rows: one warp walking them four at a time was a 20 us tail.
-        // The CTA's lane groups take the chunks round robin; their sums are combined in group order (fixed tree).
-        constexpr int NGRP = HF_THREADS / G;
-        __shared__ __align__(16) float4 part[NGRP][G];
-        const int j = tid / G, l = tid % G;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l * 4 < a.d) {
-            int c = c0 + j;
-            for (; c + 3 * NGRP < c1; c += 4 * NGRP) {
-                float4 x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = ld_f4(a.partial + (int64_t)(c + u * NGRP) * a.d + l * 4);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
-            }
-            for (; c < c1; c += NGRP) {
-                const float4 x = ld_f4(a.partial + (int64_t)c * a.d + l * 4);
-                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-            }
-        }
-        part[j][l] = acc;
-        __syncthreads();
-        if (j == 0 && l * 4 < a.d) {
-#pragma unroll
-            for (int k = 1; k < NGRP; ++k) {
-                const float4 x = part[k][l];
-                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-            }
-            const int c = l * 4;
-            if (a.addend) {
-                const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
-                acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
-            }
-            if (s >= 0) {
-                const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
-                acc.x += gs.x; acc.y += gs.y; acc.z += gs.z; acc.w += gs.w;
-            }
-            st_f4(a.Y + row * a.ldy + c, acc);
-        }
-    } else {
-        if (tid >= 32) return;                                        // scalar path: one warp per hub row
-        float acc[SC_MAXQ];
-        sum_partials_sc(a.partial, c0, c1, a.d, lane, acc);
-#pragma unroll
-        for (int q = 0; q < SC_MAXQ; ++q) {
-            const int col = lane + 32 * q;
-            if (col < a.d) {
-                float r = acc[q];
-                if (a.addend) r += a.addend[row * a.ld_add + col];
-                if (s >= 0) r += a.gsum[(int64_t)s * a.ld_gsum + col];
-                a.Y[row * a.ldy + col] = r;
-            }
-        }
-    }
 }
 
 // Node-dropout decisions of one step for every entry of a tile list, all layers at once (bit k = survives layer k).
@@ -396,27 +369,22 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
 }
 
 template <int G>
-int launch(const SpmmArgs& a, int n_ctas, const HubFinishArgs& hf, cudaStream_t st) {
-    if (n_ctas > 0) {
-        spmm_tile_kernel<G><<<(unsigned)n_ctas, SP_THREADS, 0, st>>>(a);
-        NGCF_LAUNCH_OK("spmm_tile_kernel");
-    }
-    if (hf.n_hub > 0) {
-        hub_finish_kernel<G><<<(unsigned)hf.n_hub, HF_THREADS, 0, st>>>(hf);
-        NGCF_LAUNCH_OK("hub_finish_kernel");
-    }
+int launch(const SpmmArgs& a, int n_ctas, cudaStream_t st) {
+    if (n_ctas <= 0) return NGCF_OK;
+    spmm_tile_kernel<G><<<(unsigned)n_ctas, SP_THREADS, 0, st>>>(a);
+    NGCF_LAUNCH_OK("spmm_tile_kernel");
     return NGCF_OK;
 }
 
-int launch_any(const SpmmArgs& a, int n_ctas, const HubFinishArgs& hf, bool vec, cudaStream_t st) {
-    if (!vec) return launch<0>(a, n_ctas, hf, st);
+int launch_any(const SpmmArgs& a, int n_ctas, bool vec, cudaStream_t st) {
+    if (!vec) return launch<0>(a, n_ctas, st);
     const int d4 = a.d / 4;
-    if (d4 <= 1) return launch<1>(a, n_ctas, hf, st);
-    if (d4 <= 2) return launch<2>(a, n_ctas, hf, st);
-    if (d4 <= 4) return launch<4>(a, n_ctas, hf, st);
-    if (d4 <= 8) return launch<8>(a, n_ctas, hf, st);
-    if (d4 <= 16) return launch<16>(a, n_ctas, hf, st);
-    return launch<32>(a, n_ctas, hf, st);
+    if (d4 <= 1) return launch<1>(a, n_ctas, st);
+    if (d4 <= 2) return launch<2>(a, n_ctas, st);
+    if (d4 <= 4) return launch<4>(a, n_ctas, st);
+    if (d4 <= 8) return launch<8>(a, n_ctas, st);
+    if (d4 <= 16) return launch<16>(a, n_ctas, st);
+    return launch<32>(a, n_ctas, st);
 }
 
 unsigned long long* g_spmm_dbg = nullptr;    // host copy of the debug buffer pointer
@@ -463,7 +431,7 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
                      (!addend || (aligned16(addend) && ld_add % 4 == 0)) &&
                      (!slot || (aligned16(gsum) && ld_gsum % 4 == 0)) && (g->n_hub == 0 || aligned16(hub_partial));
     const bool hubs = g->n_hub > 0 && g->n_chunks > 0;
-    NGCF_REQUIRE(!hubs || g->hub_rows, "spmm: hub_rows missing");
+    NGCF_REQUIRE(!hubs || g->hub_done, "spmm: hub_done counters missing");
     SpmmArgs a{};
     a.rows = TileSide{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
                       keep_bits, reinterpret_cast<const int2*>(c_ent), c_trp, Y, ldy};
@@ -479,9 +447,12 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     a.drop_p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.layer = layer; a.transposed = transposed;
     a.row_off = (uint32_t)row_offset;
     a.dbg = g_spmm_dbg;
-    HubFinishArgs hf{g->hub_rows, g->hub_chunk_ptr, hub_partial, hubs ? g->n_hub : 0, d, addend, ld_add, slot, gsum,
-                     ld_gsum, Y, ldy};
-    return launch_any(a, a.n_chunk_tiles + g->n_tiles, hf, vec, st);
+    a.hub_of_row = hubs ? g->hub_of_row : nullptr;
+    a.hub_chunk_ptr = g->hub_chunk_ptr;
+    a.hub_done = g->hub_done;
+    a.Yrows = Y;
+    a.ld_yrows = ldy;
+    return launch_any(a, a.n_chunk_tiles + g->n_tiles, vec, st);
 }
 
 extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,

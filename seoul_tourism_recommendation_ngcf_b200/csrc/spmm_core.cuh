@@ -19,6 +19,9 @@ constexpr int SPLIT = 128;          // rows with more entries than this are hubs
 constexpr int SP_TILE_ROWS = 16;    // SpMM tile: at most this many rows ...
 constexpr int SP_TILE_ENT = 512;    // ... and this many entries (staged in shared memory by one CTA)
 static_assert(SP_TILE_ENT >= SPLIT, "a tile must hold the longest ordinary row");
+#ifndef NGCF_SPMM_TAIL
+#define NGCF_SPMM_TAIL 4       // predicated remainder batch per lane group (2, 4 and 8 measure the same within noise)
+#endif
 constexpr int UNROLL = 8;           // gathered rows in flight per lane group
 
 struct TileInfo {                   // int4: rows [r0, r1), entries [e0, e1) of one tile
@@ -85,7 +88,7 @@ template <int G>
 __device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b, const float* __restrict__ X,
                                                  uint32_t ldx, int d, int lane) {
     constexpr int NG = 32 / G;
-    constexpr int TAIL = 4;           // (one predicated batch of UNROLL for the whole remainder measured slower)
+    constexpr int TAIL = NGCF_SPMM_TAIL;
     const int g = lane / G, l = lane % G;
     // byte addressing: one IMAD.WIDE.U32 (col * row_bytes + base) per gathered row
     const char* xl = reinterpret_cast<const char*>(X + ((l * 4) < d ? l * 4 : 0));   // lanes past the width re-read column 0
@@ -164,6 +167,40 @@ __device__ __forceinline__ float4 sum_partials_vec(const float* __restrict__ par
     return acc;
 }
 
+// the same sum with the warp's lane groups taking the partial rows round robin, UNROLL of them in flight per lane
+// (the widest hub of a power-law graph has ~100 chunks), combined in group order: a fixed tree, deterministic.
+// Partial rows were written by other CTAs during this launch: read them past L1 (ld.global.cg).
+template <int G>
+__device__ __forceinline__ float4 sum_partials_split(const float* partial, int c0, int c1, int d, int lane) {
+    constexpr int NG = 32 / G;
+    const int g = lane / G, l = lane % G;
+    const bool active = (l * 4) < d;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        int c = c0 + g;
+        for (; c + (UNROLL - 1) * NG < c1; c += UNROLL * NG) {
+            float4 x[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                x[u] = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)(c + u * NG) * d + l * 4));
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+        }
+        for (; c < c1; c += NG) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)c * d + l * 4));
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+    }
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(FULL_MASK, acc.x, off);
+        acc.y += __shfl_xor_sync(FULL_MASK, acc.y, off);
+        acc.z += __shfl_xor_sync(FULL_MASK, acc.z, off);
+        acc.w += __shfl_xor_sync(FULL_MASK, acc.w, off);
+    }
+    return acc;
+}
+
 // ---- scalar path: any d <= 128 (the reference's own width is 65: 260-byte rows).  Lane owns columns
 // lane + 32q; the whole warp fetches one gathered row per step. -------------------------------------------------
 constexpr int SC_MAXQ = NGCF_MAX_WIDTH / 32;
@@ -205,7 +242,7 @@ __device__ __forceinline__ void sum_partials_sc(const float* __restrict__ partia
 #pragma unroll
         for (int q = 0; q < SC_MAXQ; ++q) {
             const int col = lane + 32 * q;
-            if (col < d) acc[q] += partial[(int64_t)c * d + col];
+            if (col < d) acc[q] += __ldcg(partial + (int64_t)c * d + col);
         }
     }
 }

@@ -20,23 +20,21 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spins until the phase with the given parity has completed.  A protocol bug would otherwise hang the GPU; after
-// ~2^28 polls (seconds) the kernel traps instead so the launch fails with an error.
+// Waits until the phase with the given parity has completed (try_wait suspends the warp in hardware; an explicit
+// nanosleep back-off between polls was measured and changes nothing).  A protocol bug would otherwise hang the GPU;
+// after ~2^28 polls (seconds) the kernel traps instead so the launch fails with an error.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
+    for (uint32_t spin = 0; ; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-#ifdef NGCF_MBAR_TEST_WAIT
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (done) break;
         if (spin > (1u << 28)) __trap();
     }
 }
@@ -150,6 +148,19 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
     split_tf32(x.y, hi.y, lo.y);
     split_tf32(x.z, hi.z, lo.z);
     split_tf32(x.w, hi.w, lo.w);
+}
+
+// Cheap split for the streamed A operands of the forward GEMM and of the backward's GEMM 1 (the loader warps are
+// instruction-bound): hi = x as it is — the tensor core ignores the low 13 mantissa bits of a TF32 operand, i.e.
+// truncates — and lo = x - trunc(x), exact in fp32 (its own truncation to TF32 loses < 2^-21 |x|).  Truncation errors
+// share the sign of x, which is harmless over these K <= 128 contractions (measured ~1e-6 vs float64) but is why the
+// weight-gradient GEMM (contraction over ~10^5 rows) keeps the round-to-nearest split above.
+__device__ __forceinline__ void split_tf32_trunc(const float4& x, float4& hi, float4& lo) {
+    hi = x;
+    lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+    lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+    lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+    lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
 }
 
 // byte offset of the 16-byte chunk c (0..7) of row r inside a K-major (or MN-major) 128-byte-swizzled block whose

@@ -79,11 +79,12 @@ class CsrSide:
             self.chunk_ptr = chunk_ptr.to(torch.int32)
             self.chunk_row = hub[owner].to(torch.int32)
             self.hub_rows = hub.to(torch.int32).contiguous()
+            self.hub_done = torch.zeros(self.n_hub, **i32)   # completion counters of the product in flight
         else:
             self.colidx, self.perm = colidx.contiguous(), perm.contiguous()
             self.nnz_hub, self.n_chunks = 0, 0
             short_deg = deg
-            self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = self.hub_rows = None
+            self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = self.hub_rows = self.hub_done = None
         self.nnz_short = self.nnz - self.nnz_hub
         self.rowptr = torch.zeros(self.n_rows + 1, **i32)
         self.rowptr[1:] = torch.cumsum(short_deg, 0).to(torch.int32)
@@ -122,6 +123,7 @@ class CsrSide:
             s.chunk_row = _lib.ptr(self.chunk_row)
             s.chunk_tiles = _lib.ptr(self.chunk_tiles)
             s.hub_rows = _lib.ptr(self.hub_rows)
+            s.hub_done = _lib.ptr(self.hub_done)
             s.n_tiles = int(self.tiles.shape[0])
             s.n_ftiles = int(self.ftiles.shape[0])
             s.n_hub = self.n_hub
