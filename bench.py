@@ -387,7 +387,7 @@ def run_ours(args):
     # ---- CPU baseline beside it ------------------------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = time_oracle(L, batches, info, max_steps=3, warmup=1, budget_s=40.0)
+        cpu = time_oracle(L, batches, info, max_steps=40, warmup=1, budget_s=15.0)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -467,7 +467,7 @@ def run_reference(args):
     spe = info["steps_per_epoch"]
     out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "s/epoch", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": False,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": info["workload"], "steps_per_epoch": spe, "device": "cpu"},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -239,6 +239,13 @@ int ngcf_score_topk(const float* U, int64_t n_users, const float* I, int64_t n_i
                     float* out_val /*[n_users,k]*/, int64_t* out_idx /*[n_users,k]*/,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- debugging aids (tools/bwd_timeline.py, fwd_timeline.py, spmm_timeline.py); not part of the product path --------
+ * ngcf_debug_bwd_timeline: switches the in-kernel SM-clock stamps of CTA 0 of the tcgen05 dense kernels on/off and
+ * copies them back (out_host: int64[4*8*8] or NULL).  ngcf_debug_spmm_timeline: device buffer uint64[n_ctas*4]
+ * ({start, staged, done, smid} in globaltimer ns) that every SpMM CTA stamps while it is set; NULL switches it off. */
+int ngcf_debug_bwd_timeline(int enable, long long* out_host);
+int ngcf_debug_spmm_timeline(unsigned long long* dev_buf_or_null);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,8 +43,36 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 int ngcf_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// A training step is ~30 dependent launches of 5-50 us: the launch latency and the ramp-up / drain of every kernel are a
+// sizeable share of it.  The large kernels are launched with programmatic stream serialization: each signals
+// launch_dependents at its top, so the NEXT kernel's CTAs become resident while this one drains and run their
+// prologue (barriers, TMEM allocation, tile descriptors, weight tiles); they stop at pdl_wait() — which returns once
+// the preceding kernel has completed and its writes are visible — before touching anything a predecessor produced and
+// before writing anything at all.  NGCF_B200_PDL=0 launches everything fully serialised (A/B timing).
+bool ngcf_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ngcf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ngcf_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ------------------------------------------------------------------------------
 #define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     Bars* bars = reinterpret_cast<Bars*>(stage + FW_EPI_WARPS * 32 * 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
 
     // ---- one-off setup: barriers, TMEM, weights ----------------------------------------------------------------
     if (tid == 0) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
         fence_mbar_init();
     }
     if (warp == FW_MMA_WARP) tmem_alloc(&bars->tmem_base, 128);           // 2 accumulators x 64 fp32 columns
+    pdl_wait();      // wcat / bias_eff may come from the launch right before this one (ngcf_pack_weights); S, E do
     // B[n][k] = wcat[k][n], split and swizzled (row n of K block kb: 32 values of k)
     // (consecutive threads take consecutive n: the four loads below are then coalesced rows of wcat; with c fastest
     // every lane touched its own cache line and this set-up was ~30 % of the kernel's warp time in ncu)
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     BwdBars* bars = reinterpret_cast<BwdBars*>(S_s + TC_ROWS * 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
 
     if (tid == 0) {
         mbar_init(&bars->full_gm, TC_LOAD_WARPS);
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // T x2 (128 columns each)
     if (tid < 64) bars->colsum[tid] = 0.f;
     // BT[n][o] = W1[o][n] (n < 64), W2[o][n-64]; W1/W2 are [d_out, d_in] row-major
+    // W1 / W2 are the layer's parameters: nothing inside a step writes them, so their tile is built BEFORE pdl_wait()
     // (consecutive threads take consecutive n = consecutive addresses of W1 / W2: coalesced)
     for (int i = tid; i < 128 * KBo * 8; i += TC_THREADS) {
         const int n = i & 127, c = (i >> 7) & 7, kb = i >> 10;
@@ -428,6 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();      // gE_next, gsum, E_out, S, E and every output belong to the stream order
     const uint32_t tmem_base = bars->tmem_base;
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool dbg = g_bwd_dbg_on && blockIdx.x == 0 && (warp == 0 || warp == TC_EPI_WARPS || warp == TC_EPI_WARPS + 1);
@@ -741,6 +746,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
     const int stage_bytes = (8 + 2 * KBo) * WG_BLOCK;                     // X hi (4) + X lo (4) + gM hi + gM lo
     WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -754,6 +760,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();
     const uint32_t tmem_d = bars->tmem_base;
     const int n_my = (a.n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -883,10 +890,10 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     }
     const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
     switch (mess_mode(mess_mult, mess_bits, mess_p)) {
-        case MM_NONE: dense_fwd_tc_kernel<MM_NONE><<<grid, TC_THREADS, smem, st>>>(a); break;
-        case MM_MULT: dense_fwd_tc_kernel<MM_MULT><<<grid, TC_THREADS, smem, st>>>(a); break;
-        case MM_BITS: dense_fwd_tc_kernel<MM_BITS><<<grid, TC_THREADS, smem, st>>>(a); break;
-        default: dense_fwd_tc_kernel<MM_HASH><<<grid, TC_THREADS, smem, st>>>(a); break;
+        case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_NONE>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+        case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_MULT>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+        case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_BITS>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+        default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_HASH>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
     }
     NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
     return NGCF_OK;
@@ -920,13 +927,13 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
         NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    kern<<<grid, TC_THREADS, smem, st>>>(a);
+    NGCF_CUDA(ngcf_launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, st, a));
     NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
 
     WgradArgs w{S, E, gM_scratch, n_rows, d_out, gW1, gW2, (int)ceil_div64(n_rows, WG_ROWS)};
     const size_t smem2 = 1024 + (size_t)2 * (8 + 2 * KBo) * WG_BLOCK + sizeof(WgBars);
     const int grid2 = (int)min((int64_t)w.n_chunks, (int64_t)ngcf_num_sms());
-    wgrad_tc_kernel<<<grid2, TC_THREADS, smem2, st>>>(w);
+    NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, st, w));
     NGCF_LAUNCH_OK("wgrad_tc_kernel");
     return NGCF_OK;
 }

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     __shared__ int rp_s[SP_TILE_ROWS + 1];
     __shared__ int hub_s[SP_TILE_ROWS];                               // row side: hub id of each tile row, or -1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
     if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
     const bool chunk_side = (int)blockIdx.x < a.n_chunk_tiles;
     const TileSide& sd = chunk_side ? a.chunks : a.rows;
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
     const int nr = ti.r1 - ti.r0;
     if (tid < nr)      // chunk side: the chunk's row; row side: is the row a hub (then it is not written here)
         hub_s[tid] = chunk_side ? a.hub_of_row[sd.row_key[ti.r0 + tid]] : (a.hub_of_row ? a.hub_of_row[ti.r0 + tid] : -1);
+    // everything above is the plan's static layout; entries (possibly this step's compacted survivors), X, addend and
+    // the outputs belong to the stream order
+    pdl_wait();
     if (sd.ctrp) {
         // node dropout already applied for this step and layer: the tile's surviving entries sit compacted at e0
         const int32_t* trp = sd.ctrp + (size_t)t * (SP_TILE_ROWS + 1);
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
 template <int G>
 int launch(const SpmmArgs& a, int n_ctas, cudaStream_t st) {
     if (n_ctas <= 0) return NGCF_OK;
-    spmm_tile_kernel<G><<<(unsigned)n_ctas, SP_THREADS, 0, st>>>(a);
+    NGCF_CUDA(ngcf_launch_pdl(spmm_tile_kernel<G>, dim3((unsigned)n_ctas), dim3(SP_THREADS), 0, st, a));
     NGCF_LAUNCH_OK("spmm_tile_kernel");
     return NGCF_OK;
 }
