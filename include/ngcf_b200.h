@@ -79,6 +79,9 @@ typedef struct ngcf_csr {
     const int32_t* hub_rows;        /* [n_hub] row of hub h */
     int32_t* hub_done;              /* [n_hub] completion counters of a product in flight: all zero between calls
                                        (ngcf_spmm leaves them zero); one product per csr at a time */
+    const uint32_t* key_l;          /* optional [nnz] static node-dropout keys (ngcf_entry_keys), CSR read as L ... */
+    const uint32_t* key_t;          /* ... and read as L^T; NULL: the per-step pass derives them from the coordinates */
+    int64_t key_row_offset;         /* the row_offset the keys were computed for */
     int32_t n_tiles, n_ftiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
 } ngcf_csr;
@@ -152,6 +155,11 @@ int ngcf_node_dropout_compact(const ngcf_csr* csr_host, float drop_p, uint64_t s
                               int n_layers, int64_t row_offset,
                               int32_t* const* ent_as_L_host, int32_t* const* trp_as_L_host,
                               int32_t* const* ent_as_Lt_host, int32_t* const* trp_as_Lt_host, void* stream);
+
+/* Static per-entry node-dropout keys (plan time, once per csr): key_l[t] / key_t[t] for entry t in execution order
+ * (ent then hub_ent), the CSR read as L / as L^T.  With them in the descriptor ngcf_node_dropout_compact needs no row
+ * search and one hash per direction and entry. */
+int ngcf_entry_keys(const ngcf_csr* csr_host, int64_t row_offset, uint32_t* key_l, uint32_t* key_t, void* stream);
 
 /* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
  * pack:  wcat[k, o] = W1[o,k] (k < d_in), W2[o,k-d_in] (k >= d_in);  bias_eff = 2*b1 + b2
@@ -245,6 +253,7 @@ int ngcf_score_topk(const float* U, int64_t n_users, const float* I, int64_t n_i
  * ({start, staged, done, smid} in globaltimer ns) that every SpMM CTA stamps while it is set; NULL switches it off. */
 int ngcf_debug_bwd_timeline(int enable, long long* out_host);
 int ngcf_debug_spmm_timeline(unsigned long long* dev_buf_or_null);
+int ngcf_debug_compact_timeline(unsigned long long* dev_buf_or_null);   /* same, row launch of the compaction pass */
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ class NgcfCsr(C.Structure):
     """Mirror of ``ngcf_csr`` (include/ngcf_b200.h): a host struct of device pointers."""
     _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp), ("ftiles", _vp),
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
-                ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp),
+                ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp), ("key_l", _vp), ("key_t", _vp), ("key_row_offset", _i64),
                 ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
                 ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "ngcf_spmm_split_threshold": [],
     "ngcf_spmm": [_csr_p, _vp, _i64, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _u64, _vp, C.c_int, C.c_int, _i64,
                   _vp, _vp, _vp, _vp, _i64, _vp],
+    "ngcf_entry_keys": [_csr_p, _i64, _vp, _vp, _vp],
     "ngcf_node_dropout_compact": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                   C.POINTER(_vp), _vp],
     "ngcf_node_dropout_bits": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp, _vp],
@@ -61,6 +62,7 @@ SIGNATURES = {
                                C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, _vp],
     "ngcf_debug_bwd_timeline": [C.c_int, _vp],
     "ngcf_debug_spmm_timeline": [_vp],
+    "ngcf_debug_compact_timeline": [_vp],
     "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.POINTER(_sz)],
     "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],
 }

@@ -120,16 +120,22 @@ __device__ __forceinline__ uint64_t ngcf_seed(uint64_t seed, const uint64_t* see
     return seed + (seed_dev ? *seed_dev : 0ull);
 }
 
-// Node dropout (NGCF.py:93-100,124-126) in device-RNG mode: bit k of the result = entry (row, col) of L survives
-// layer k, i.e. its draws for layers 0..k are all >= p (cumulative over layers, values unscaled).  Keyed on the
-// entry's coordinates in L, so the forward CSR and the CSR of L^T agree without a permutation.
-__device__ __forceinline__ uint32_t node_keep_bits(float p, uint64_t seed, int n_layers, uint32_t row, uint32_t col) {
-    const uint32_t thr = ngcf_threshold16(p);
+// Node dropout (NGCF.py:93-100,124-126) in device-RNG mode.  An entry (row, col) of L has a STATIC 32-bit key (it
+// depends on the coordinates only, so the plan can store it per entry: the per-step pass then needs neither the
+// entry's row nor a hash of two coordinates); the step's draws are two mixes of key ^ seed: four 16-bit uniforms per
+// group of four layers.  Bit k of the result = the entry survives layer k, i.e. its draws for layers 0..k are all
+// >= p (cumulative over layers, values unscaled).  Keyed on the coordinates IN L, so the forward CSR and the CSR of
+// L^T agree without a permutation.
+__device__ __forceinline__ uint32_t ngcf_node_key(uint32_t row, uint32_t col) {
+    return ngcf_mix(ngcf_mix(row + 0x9E3779B9u) ^ (col * 0x85EBCA77u + 0xC2B2AE3Du));
+}
+__device__ __forceinline__ uint32_t node_keep_bits_key(uint32_t thr, uint64_t seed, int n_layers, uint32_t key) {
     uint32_t bits = 0;
     bool keep = true;
     for (int g = 0; g * 4 < n_layers && keep; ++g) {
-        const uint2 r = ngcf_hash64(seed, row, col, (uint32_t)g, NGCF_STREAM_NODE);
-        const uint32_t u[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
+        const uint32_t h = ngcf_mix(key ^ (uint32_t)seed ^ ((uint32_t)g * 0x632BE5ABu) ^ NGCF_STREAM_NODE);
+        const uint32_t y = ngcf_mix(h ^ (uint32_t)(seed >> 32));
+        const uint32_t u[4] = {h & 0xffffu, h >> 16, y & 0xffffu, y >> 16};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             keep = keep && (u[j] >= thr);
@@ -137,6 +143,9 @@ __device__ __forceinline__ uint32_t node_keep_bits(float p, uint64_t seed, int n
         }
     }
     return bits;
+}
+__device__ __forceinline__ uint32_t node_keep_bits(float p, uint64_t seed, int n_layers, uint32_t row, uint32_t col) {
+    return node_keep_bits_key(ngcf_threshold16(p), seed, n_layers, ngcf_node_key(row, col));
 }
 __device__ __forceinline__ bool node_keep(float p, uint64_t seed, int layer, uint32_t row, uint32_t col) {
     return (node_keep_bits(p, seed, layer + 1, row, col) >> layer) & 1u;

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     const uint32_t tmem_base = bars->tmem_base;
 
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
-    const bool dbg = g_bwd_dbg_on && blockIdx.x == 0 && (warp == 0 || warp == FW_MMA_WARP || warp == FW_MMA_WARP + 1);
+    const bool dbg = g_bwd_dbg_on == 1 && blockIdx.x == 0 && (warp == 0 || warp == FW_MMA_WARP || warp == FW_MMA_WARP + 1);
     if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();
 
     if (warp < FW_EPI_WARPS) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     pdl_wait();      // gE_next, gsum, E_out, S, E and every output belong to the stream order
     const uint32_t tmem_base = bars->tmem_base;
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool dbg = g_bwd_dbg_on && blockIdx.x == 0 && (warp == 0 || warp == TC_EPI_WARPS || warp == TC_EPI_WARPS + 1);
+    const bool dbg = g_bwd_dbg_on == 1 && blockIdx.x == 0 && (warp == 0 || warp == TC_EPI_WARPS || warp == TC_EPI_WARPS + 1);
     if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();   // start of the steady state
 
     if (warp < TC_EPI_WARPS) {
@@ -763,10 +763,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
     pdl_wait();
     const uint32_t tmem_d = bars->tmem_base;
     const int n_my = (a.n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool dbg = g_bwd_dbg_on == 2 && blockIdx.x == 0 && (warp == 0 || warp == TC_EPI_WARPS || warp == TC_EPI_WARPS + 1);
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();
 
     if (warp < TC_EPI_WARPS) {
         // ======================= final flush =====================================================================
         mbar_wait(&bars->d_full, 0);
+        BWD_STAMP(0, 0, 0);
         tc_fence_after_sync();
         const int m = warp * 32 + lane;                                   // TMEM lane = column j of [W1 | W2]
         float* gw = (m < d_in ? a.gW1 : a.gW2) + (m & 63);
@@ -776,6 +779,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(gw + (int64_t)(c * 32 + j) * d_in, v[j]);
         }
+        BWD_STAMP(0, 0, 1);
     } else if (warp == TC_EPI_WARPS) {
         // ======================= MMA issuer =====================================================================
         const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 1, 1);
@@ -808,36 +812,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
         __syncwarp();
     } else {
         // ======================= loaders =========================================================================
+        // software-pipelined by half stages (32 rows: 2 + 2 + 2 float4 per thread): the loads of the next half are in
+        // flight while this one is split and stored (first version: load a 64-row stage, wait, convert — one exposed
+        // round trip per stage, ~7.5 stages per CTA)
         const int lt = tid - (TC_EPI_WARPS + 1) * 32;                     // 0 .. 255
         constexpr int LT = TC_LOAD_WARPS * 32;
         const int gq = d_out / 4;                                         // float4 per gM row
-        for (int it = 0; it < n_my; ++it) {
-            const int chunk = blockIdx.x + it * gridDim.x;
-            const int sgi = it & 1;
-            const int64_t row0 = (int64_t)chunk * WG_ROWS;
+        struct Half {
+            float4 s[2], e[2], g[2];
+        };
+        const int total = 2 * n_my;
+        auto issue = [&](Half& h, int i) {
+            const int64_t row0 = (int64_t)(blockIdx.x + (i >> 1) * gridDim.x) * WG_ROWS;
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {                              // 64 rows x 16 float4 = 4 per thread per stage
+                const int idx = ((i & 1) * 2 + q2) * LT + lt, r = idx >> 4, c = idx & 15;
+                const int64_t row = row0 + r;
+                h.s[q2] = h.e[q2] = h.g[q2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < a.n_rows) {
+                    h.s[q2] = ld_f4(a.S + row * d_in + c * 4);
+                    h.e[q2] = ld_f4(a.E + row * d_in + c * 4);
+                    if (c < gq) h.g[q2] = ld_f4(a.gM + row * d_out + c * 4);
+                }
+            }
+        };
+        auto convert = [&](const Half& h, int i) {
+            const int sgi = (i >> 1) & 1;
             uint8_t* x_hi = smem + sgi * stage_bytes;
             uint8_t* x_lo = x_hi + 4 * WG_BLOCK;
             uint8_t* g_hi = x_lo + 4 * WG_BLOCK;
             uint8_t* g_lo = g_hi + KBo * WG_BLOCK;
-            float4 s4[4], e4[4], g4[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                                 // 64 rows x 16 float4 = 4 per thread
-                const int idx = q * LT + lt, r = idx >> 4, c = idx & 15;
-                const int64_t row = row0 + r;
-                s4[q] = e4[q] = g4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < a.n_rows) {
-                    s4[q] = ld_f4(a.S + row * d_in + c * 4);
-                    e4[q] = ld_f4(a.E + row * d_in + c * 4);
-                    if (c < gq) g4[q] = ld_f4(a.gM + row * d_out + c * 4);
-                }
-            }
-            mbar_wait(&bars->empty[sgi], ((it >> 1) & 1) ^ 1);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int idx = q * LT + lt, r = idx >> 4, c = idx & 15;
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const int idx = ((i & 1) * 2 + q2) * LT + lt, r = idx >> 4, c = idx & 15;
                 const uint32_t off = (c >> 3) * WG_BLOCK + sw128b32_offset(r, c & 7);
-                const float4 x1 = make_float4(s4[q].x + e4[q].x, s4[q].y + e4[q].y, s4[q].z + e4[q].z, s4[q].w + e4[q].w);
-                const float4 x2 = make_float4(s4[q].x * e4[q].x, s4[q].y * e4[q].y, s4[q].z * e4[q].z, s4[q].w * e4[q].w);
+                const float4 sv = h.s[q2], ev = h.e[q2];
+                const float4 x1 = make_float4(sv.x + ev.x, sv.y + ev.y, sv.z + ev.z, sv.w + ev.w);
+                const float4 x2 = make_float4(sv.x * ev.x, sv.y * ev.y, sv.z * ev.z, sv.w * ev.w);
                 float4 hi, lo;
                 split_tf32(x1, hi, lo);
                 *reinterpret_cast<float4*>(x_hi + off) = hi;
@@ -846,19 +857,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
                 *reinterpret_cast<float4*>(x_hi + 2 * WG_BLOCK + off) = hi;
                 *reinterpret_cast<float4*>(x_lo + 2 * WG_BLOCK + off) = lo;
                 if (c < gq) {
-                    split_tf32(g4[q], hi, lo);
+                    split_tf32(h.g[q2], hi, lo);
                     *reinterpret_cast<float4*>(g_hi + off) = hi;
                     *reinterpret_cast<float4*>(g_lo + off) = lo;
                 }
             }
+        };
+        Half h0, h1;
+        if (total > 0) issue(h0, 0);
+        for (int i = 0; i < total; i += 2) {                              // half i: rows 0..31 of its stage, i + 1: rows 32..63
+            const int it = i >> 1, sgi = it & 1;
+            issue(h1, i + 1);
+            mbar_wait(&bars->empty[sgi], ((it >> 1) & 1) ^ 1);
+            convert(h0, i);
+            if (i + 2 < total) issue(h0, i + 2);
+            convert(h1, i + 1);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->full[sgi]);
+            BWD_STAMP(2, it, 0);
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[1][7][7] = clock64();
     if (warp == TC_EPI_WARPS) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_d, 64);

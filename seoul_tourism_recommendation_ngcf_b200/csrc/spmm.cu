@@ -258,6 +258,39 @@ __global__ void __launch_bounds__(BITS_THREADS) dropout_bits_kernel(BitsArgs a, 
     }
 }
 
+// Static node-dropout keys of every entry of a tile list (plan time, once): key_l = ngcf_node_key(row, col) for the
+// CSR read as L, key_t = ngcf_node_key(col, row) for the same CSR read as L^T.
+struct KeyArgs {
+    const TileInfo* tiles;
+    const int32_t* rowptr;
+    const int2* ent;
+    const int32_t* row_key;
+    uint32_t row_off;
+    uint32_t* key_l;
+    uint32_t* key_t;
+};
+__global__ void __launch_bounds__(BITS_THREADS) entry_keys_kernel(KeyArgs a, int n_tiles) {
+    __shared__ int rp_s[BITS_TILES * SP_TILE_ROWS + 1];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * BITS_TILES, t1 = min(t0 + BITS_TILES, n_tiles) - 1;
+    const int4 first = *reinterpret_cast<const int4*>(a.tiles + t0);
+    const int4 last = *reinterpret_cast<const int4*>(a.tiles + t1);
+    const int r0 = first.x, nr = last.y - first.x, e0 = first.z, cnt = last.w - first.z;
+    for (int i = tid; i <= nr; i += BITS_THREADS) rp_s[i] = a.rowptr[r0 + i] - e0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += BITS_THREADS) {
+        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + e0 + i).x;
+        int lo = 0, hi = nr - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t r = (uint32_t)(a.row_key ? a.row_key[r0 + lo] : r0 + lo) + a.row_off;
+        a.key_l[e0 + i] = ngcf_node_key(r, c);
+        a.key_t[e0 + i] = ngcf_node_key(c, r);
+    }
+}
+
 // ---- per-step node-dropout compaction -----------------------------------------------------------------------------
 // The reference's sparse_dropout (NGCF.py:93-100) DELETES the dropped entries, cumulatively over the layers, so its
 // layer-k product walks only (1-p)^(k+1) of the Laplacian.  One pass per step does the same for every layer and both
@@ -275,101 +308,112 @@ struct CompactArgs {
     const uint64_t* seed_dev;
     int n_layers;
     uint32_t row_off;
+    const uint32_t* key_l;                   // optional static per-entry keys (ngcf_entry_keys), indexed like `ent`:
+    const uint32_t* key_t;                   //   ngcf_node_key(row, col) and ngcf_node_key(col, row)
+    unsigned long long* dbg;                 // optional [n_ctas][4] = {start, loaded, decided, done} ns (tools/spmm_timeline.py)
     int2* out_ent[2][NGCF_MAX_LAYERS];       // [0] keyed (row, col) = this CSR read as L, [1] keyed (col, row) = as L^T
     int32_t* out_trp[2][NGCF_MAX_LAYERS];    // NULL: direction/layer not wanted
 };
 
 constexpr int CP_THREADS = 128;
-constexpr int CP_PER = SP_TILE_ENT / CP_THREADS;     // consecutive entries per thread
+constexpr int CP_PER = SP_TILE_ENT / CP_THREADS;     // entries per thread: entry q * 128 + tid, i.e. segment q * 4 + warp
+constexpr int CP_SEGS = SP_TILE_ENT / 32;            // 32-entry segments of a tile (= one warp ballot each)
 static_assert(CP_PER * CP_THREADS == SP_TILE_ENT, "tile entries must split evenly over the compaction CTA");
 
-// combo c = dir * n_layers + layer keeps a 16-bit counter in word c >> 2 at bit 16 * (c & 3) (counts <= 512)
-template <int NW>
+// combo c = dir * n_layers + layer.  Order-preserving compaction by warp ballots: entry p of the tile sits in segment
+// p >> 5 at lane p & 31, its position among a combo's survivors is the segment's base + the survivors below its lane.
+// Consecutive lanes write consecutive survivors: the stores are coalesced without a shared-memory copy.
+// (First version: four consecutive entries per thread and packed 16-bit counters in 64-bit words — the bit loops and
+// variable 64-bit shifts of that bookkeeping cost twice the hashes; tools/spmm_timeline.py: 13.6 us per CTA.)
+template <int MAXC>
 __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
     __shared__ int rp_s[SP_TILE_ROWS + 1];
-    __shared__ uint64_t pre_s[NW][SP_TILE_ENT + 1];  // kept entries before entry i, per combo
-    __shared__ uint64_t wtot_s[NW][CP_THREADS / 32];
+    __shared__ uint32_t mask_s[MAXC][CP_SEGS];        // survivors of each segment, per combo
+    __shared__ int base_s[MAXC][CP_SEGS + 1];         // survivors before each segment; [CP_SEGS] = total
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
     const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
     const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
-    const int K = a.n_layers;
+    const int K = a.n_layers, n_combo = 2 * K;
     for (int i = tid; i <= nr; i += CP_THREADS) rp_s[i] = a.rowptr[ti.r0 + i] - ti.e0;
-    const int base = tid * CP_PER;
+    const bool want_l = a.out_ent[0][0] != nullptr, want_t = a.out_ent[1][0] != nullptr;
     int2 e[CP_PER];
+    uint32_t kl[CP_PER], kt[CP_PER];
 #pragma unroll
     for (int q = 0; q < CP_PER; ++q) {
+        const int p = q * CP_THREADS + tid;
         e[q] = make_int2(0, 0);
-        if (base + q < cnt) e[q] = ld_stream_i2(a.ent + ti.e0 + base + q);
+        kl[q] = kt[q] = 0;
+        if (p < cnt) {
+            e[q] = ld_stream_i2(a.ent + ti.e0 + p);
+            if (a.key_l) {
+                if (want_l) kl[q] = a.key_l[ti.e0 + p];
+                if (want_t) kt[q] = a.key_t[ti.e0 + p];
+            }
+        }
     }
     __syncthreads();
     const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
-    const bool want_l = a.out_ent[0][0] != nullptr, want_t = a.out_ent[1][0] != nullptr;
-    uint32_t keep[CP_PER];                            // bits [0, K): as L, bits [K, 2K): as L^T  (= combo index)
-    uint64_t mine[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) mine[w] = 0;
+    const uint32_t thr = ngcf_threshold16(a.p);
+    uint32_t keep[CP_PER];                            // bit c = the entry survives combo c
 #pragma unroll
     for (int q = 0; q < CP_PER; ++q) {
+        const int p = q * CP_THREADS + tid;
         keep[q] = 0;
-        const int i = base + q;
-        if (i < cnt) {
-            int lo = 0, hi = nr - 1;                  // last row with rp_s[row] <= i
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
+        if (p < cnt) {
+            if (!a.key_l) {                           // no static keys in the plan: derive them from the coordinates
+                int lo = 0, hi = nr - 1;              // last row with rp_s[row] <= p
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rp_s[mid] <= p) lo = mid; else hi = mid - 1;
+                }
+                const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
+                kl[q] = ngcf_node_key(r, (uint32_t)e[q].x);
+                kt[q] = ngcf_node_key((uint32_t)e[q].x, r);
             }
-            const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
-            const uint32_t c = (uint32_t)e[q].x;
-            if (want_l) keep[q] = node_keep_bits(a.p, seed, K, r, c);
-            if (want_t) keep[q] |= node_keep_bits(a.p, seed, K, c, r) << K;
+            if (want_l) keep[q] = node_keep_bits_key(thr, seed, K, kl[q]);
+            if (want_t) keep[q] |= node_keep_bits_key(thr, seed, K, kt[q]) << K;
         }
-#pragma unroll
-        for (int w = 0; w < NW; ++w)
-            for (uint32_t m = (keep[q] >> (4 * w)) & 0xfu; m; m &= m - 1) mine[w] += 1ull << (16 * (__ffs(m) - 1));
     }
-    uint64_t run[NW];                                 // exclusive prefix of this thread's first entry
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 1] = gtime_ns();
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        uint64_t inc = mine[w];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint64_t v = __shfl_up_sync(FULL_MASK, inc, off);
-            if (lane >= off) inc += v;
+    for (int q = 0; q < CP_PER; ++q)
+        for (int c = 0; c < n_combo; ++c) {
+            const uint32_t m = __ballot_sync(FULL_MASK, (keep[q] >> c) & 1u);
+            if (lane == 0) mask_s[c][q * (CP_THREADS / 32) + warp] = m;
         }
-        if (lane == 31) wtot_s[w][warp] = inc;
-        run[w] = inc - mine[w];
+    __syncthreads();
+    if (tid < n_combo) {                              // 16 segment totals per combo: a serial scan is enough
+        int run = 0;
+        for (int sgm = 0; sgm < CP_SEGS; ++sgm) {
+            base_s[tid][sgm] = run;
+            run += __popc(mask_s[tid][sgm]);
+        }
+        base_s[tid][CP_SEGS] = run;
     }
     __syncthreads();
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-        for (int j = 0; j < warp; ++j) run[w] += wtot_s[w][j];
+    const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
     for (int q = 0; q < CP_PER; ++q) {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) pre_s[w][base + q] = run[w];
-#pragma unroll
-        for (int w = 0; w < NW; ++w)
-            for (uint32_t m = (keep[q] >> (4 * w)) & 0xfu; m; m &= m - 1) {
-                const int c4 = __ffs(m) - 1, c = 4 * w + c4;
-                const int dir = c >= K, layer = dir ? c - K : c;
-                const int pos = (int)((run[w] >> (16 * c4)) & 0xffffu);
-                a.out_ent[dir][layer][ti.e0 + pos] = e[q];
-                run[w] += 1ull << (16 * c4);
-            }
+        const int sgm = q * (CP_THREADS / 32) + warp;
+        for (uint32_t m = keep[q]; m; m &= m - 1) {
+            const int c = __ffs(m) - 1;
+            const int dir = c >= K, layer = dir ? c - K : c;
+            a.out_ent[dir][layer][ti.e0 + base_s[c][sgm] + __popc(mask_s[c][sgm] & below)] = e[q];
+        }
     }
-    if (tid == CP_THREADS - 1) {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) pre_s[w][SP_TILE_ENT] = run[w];
-    }
-    __syncthreads();
-    const int n_combo = 2 * K;
     for (int j = tid; j < (nr + 1) * n_combo; j += CP_THREADS) {
         const int c = j / (nr + 1), i = j - c * (nr + 1);
         const int dir = c >= K, layer = dir ? c - K : c;
         int32_t* trp = a.out_trp[dir][layer];
-        if (trp) trp[(size_t)blockIdx.x * (SP_TILE_ROWS + 1) + i] = (int)((pre_s[c >> 2][rp_s[i]] >> (16 * (c & 3))) & 0xffffu);
+        if (!trp) continue;
+        const int p = rp_s[i], sgm = p >> 5;          // p <= cnt <= 512: segment 16 = the total
+        int v = base_s[c][sgm];
+        if (sgm < CP_SEGS) v += __popc(mask_s[c][sgm] & ((1u << (p & 31)) - 1u));
+        trp[(size_t)blockIdx.x * (SP_TILE_ROWS + 1) + i] = v;
     }
+    if (a.dbg) stamp_done(a.dbg);
 }
 
 template <int G>
@@ -392,6 +436,7 @@ int launch_any(const SpmmArgs& a, int n_ctas, bool vec, cudaStream_t st) {
 }
 
 unsigned long long* g_spmm_dbg = nullptr;    // host copy of the debug buffer pointer
+unsigned long long* g_spmm_dbg_compact = nullptr;   // ... for the row launch of the compaction pass
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -514,6 +559,11 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
         a.row_key = pass ? g->chunk_row : nullptr;
         a.p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.n_layers = n_layers; a.row_off = (uint32_t)row_offset;
         const size_t e_off = pass ? (size_t)g->rowptr_nnz : 0, t_off = pass ? (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : 0;
+        a.dbg = pass == 0 ? g_spmm_dbg_compact : nullptr;
+        if (g->key_l && g->key_t && g->key_row_offset == row_offset) {
+            a.key_l = g->key_l + e_off;
+            a.key_t = g->key_t + e_off;
+        }
         for (int k = 0; k < n_layers; ++k) {
             if (ent_as_L_host) {
                 a.out_ent[0][k] = reinterpret_cast<int2*>(ent_as_L_host[k]) + e_off;
@@ -524,10 +574,8 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
                 a.out_trp[1][k] = trp_as_Lt_host[k] + t_off;
             }
         }
-        const int nw = (2 * n_layers + 3) / 4;
-        if (nw <= 1) compact_kernel<1><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
-        else if (nw == 2) compact_kernel<2><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
-        else compact_kernel<4><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        if (2 * n_layers <= 8) compact_kernel<8><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        else compact_kernel<16><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
         NGCF_LAUNCH_OK(pass ? "compact_kernel(hub chunks)" : "compact_kernel(rows)");
     }
     return NGCF_OK;
@@ -536,5 +584,30 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
 // debugging aid (tools/spmm_timeline.py): device buffer [n_ctas][4] of uint64 that every spmm_tile_kernel CTA stamps
 extern "C" int ngcf_debug_spmm_timeline(unsigned long long* dev_buf_or_null) {
     g_spmm_dbg = dev_buf_or_null;
+    return NGCF_OK;
+}
+extern "C" int ngcf_debug_compact_timeline(unsigned long long* dev_buf_or_null) {
+    g_spmm_dbg_compact = dev_buf_or_null;
+    return NGCF_OK;
+}
+
+extern "C" int ngcf_entry_keys(const ngcf_csr* g, int64_t row_offset, uint32_t* key_l, uint32_t* key_t, void* stream) {
+    int rc = ngcf_check_csr(g, "entry_keys");
+    if (rc != NGCF_OK) return rc;
+    NGCF_REQUIRE(key_l && key_t, "entry_keys: null output");
+    NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "entry_keys: row_offset");
+    cudaStream_t st = as_stream(stream);
+    if (g->n_tiles > 0) {
+        KeyArgs a{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
+                  (uint32_t)row_offset, key_l, key_t};
+        entry_keys_kernel<<<(unsigned)ceil_div64(g->n_tiles, BITS_TILES), BITS_THREADS, 0, st>>>(a, g->n_tiles);
+        NGCF_LAUNCH_OK("entry_keys_kernel(rows)");
+    }
+    if (g->n_hub > 0 && g->n_chunk_tiles > 0) {
+        KeyArgs a{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr, reinterpret_cast<const int2*>(g->hub_ent),
+                  g->chunk_row, (uint32_t)row_offset, key_l + g->rowptr_nnz, key_t + g->rowptr_nnz};
+        entry_keys_kernel<<<(unsigned)ceil_div64(g->n_chunk_tiles, BITS_TILES), BITS_THREADS, 0, st>>>(a, g->n_chunk_tiles);
+        NGCF_LAUNCH_OK("entry_keys_kernel(hub chunks)");
+    }
     return NGCF_OK;
 }

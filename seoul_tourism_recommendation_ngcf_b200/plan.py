@@ -99,6 +99,8 @@ class CsrSide:
         else:
             self.chunk_tiles = None
         self.ent = None          # base entry pairs, set by LaplacianPlan
+        self.key_l = self.key_t = None   # static node-dropout keys (ensure_keys)
+        self.key_row_offset = 0
         self._partial = {}
         self._struct_cache = {}
 
@@ -124,6 +126,9 @@ class CsrSide:
             s.chunk_tiles = _lib.ptr(self.chunk_tiles)
             s.hub_rows = _lib.ptr(self.hub_rows)
             s.hub_done = _lib.ptr(self.hub_done)
+            s.key_l = _lib.ptr(self.key_l)
+            s.key_t = _lib.ptr(self.key_t)
+            s.key_row_offset = self.key_row_offset
             s.n_tiles = int(self.tiles.shape[0])
             s.n_ftiles = int(self.ftiles.shape[0])
             s.n_hub = self.n_hub
@@ -132,6 +137,18 @@ class CsrSide:
             s.rowptr_nnz = self.nnz_short
             self._struct_cache[key] = s
         return s
+
+    def ensure_keys(self, row_offset: int = 0):
+        """Static node-dropout keys of every entry (once per side): the per-step compaction then needs no row search."""
+        if self.key_l is None or self.key_row_offset != row_offset:
+            lib = _lib.load()
+            dev = self.rowptr.device
+            kl = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            kt = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            _lib.check(lib.ngcf_entry_keys(C.byref(self.descriptor(None)), int(row_offset), kl.data_ptr(), kt.data_ptr(),
+                                           _stream()), "entry_keys")
+            self.key_l, self.key_t, self.key_row_offset = kl, kt, int(row_offset)
+            self._struct_cache.clear()
 
     def hub_partial(self, d: int):
         if not self.n_hub:
@@ -236,6 +253,7 @@ def node_dropout_compact(side: CsrSide, drop_p: float, seed: int, seed_dev, n_la
     L^T.  Returns (per-layer list of (ent, trp) or None, same for L^T); pass one pair to ``spmm(compact=...)``."""
     lib = _lib.load()
     dev = side.rowptr.device
+    side.ensure_keys(row_offset)
     n_t = int(side.tiles.shape[0]) + (int(side.chunk_tiles.shape[0]) if side.chunk_tiles is not None else 0)
     per = lib.ngcf_spmm_tile_rows() + 1
 

@@ -45,3 +45,13 @@ for role, rn in ((2, "loader"), (1, "mma"), (0, "epilogue")):
             print(f"{rn:9s} tile {it}: " + "  ".join(f"{n}={v}" for n, v in row))
 for it in range(4):
     print(f"loader tile {it}: half 0 computed / next half issued / half 1 computed / fenced:", [int(v - t0) for v in t[3, it]])
+
+# weight-gradient kernel (enable = 2 stamps wgrad_tc_kernel instead)
+raw.ngcf_debug_bwd_timeline(2, None)
+flush.zero_(); run(); torch.cuda.synchronize()
+out = np.zeros(4 * 8 * 8, dtype=np.int64)
+raw.ngcf_debug_bwd_timeline(0, out.ctypes.data)
+t = out.reshape(4, 8, 8); t0 = t[0, 7, 7]
+print("wgrad_tc_kernel CTA 0, cycles after set-up: total =", int(t[1, 7, 7] - t0),
+      " loader stage ends:", [int(t[2, it, 0] - t0) for it in range(8) if t[2, it, 0] > 0],
+      " flush:", int(t[0, 0, 0] - t0), "->", int(t[0, 0, 1] - t0))

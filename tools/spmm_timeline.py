@@ -46,3 +46,20 @@ start, done = t_all[:, 0] - t0, t_all[:, 2] - t0
 print(f"avg resident CTAs per SM over the span: {np.sum(done - start) / (done.max() * 148):.2f}")
 for q in (0.25, 0.5, 0.75, 0.9, 1.0):
     print(f"  {int(q * 100):3d}% of CTAs started by {np.quantile(start, q) / 1e3:6.1f} us, done by {np.quantile(done, q) / 1e3:6.1f} us")
+
+# ---- the compaction pass (row launch) ----
+raw.ngcf_debug_compact_timeline.argtypes = [C.c_void_p]
+buf2 = torch.zeros(n_t * 4, dtype=torch.int64, device=dev)
+for _ in range(2):
+    node_dropout_compact(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True)
+flush.zero_(); torch.cuda.synchronize()
+raw.ngcf_debug_compact_timeline(buf2.data_ptr())
+node_dropout_compact(plan.fwd, 0.3, 1, None, 3, as_L=True, as_Lt=True)
+torch.cuda.synchronize()
+raw.ngcf_debug_compact_timeline(None)
+t = buf2.cpu().numpy().reshape(-1, 4).astype(np.int64)
+t0 = t[:, 0].min()
+start, loaded, done = t[:, 0] - t0, t[:, 1] - t0, t[:, 2] - t0
+print(f"compaction, row launch: {n_t} CTAs, span {done.max() / 1e3:.1f} us; load+decide mean {np.mean(loaded - start):.0f} ns, "
+      f"scan+write mean {np.mean(done - loaded):.0f} ns, life mean {np.mean(done - start):.0f} ns; "
+      f"resident CTAs per SM {np.sum(done - start) / (done.max() * 148):.1f}")
