@@ -83,6 +83,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// streaming 128-bit load of data this kernel only reads once: no L1 line is allocated.  In the tensor-core kernels
+// ~216 KB of the SM's 256 KB are shared memory, the L1 that remains is a few tens of KB, and every outstanding
+// allocating load pins a line of it: 8 loader warps x 8 loads x 4 lines could not even be in flight together.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
 // streaming (read-once) loads: keep CSR arrays out of L1 so gathered embedding rows stay resident
 __device__ __forceinline__ int ld_stream_i32(const int* p) {
     int v;

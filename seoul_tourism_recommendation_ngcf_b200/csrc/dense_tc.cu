@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                 const int64_t row = row0 + r;
                 g.s[q] = g.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row < a.n_rows) {
-                    g.s[q] = ld_f4(a.S + row * d_in + hh * 32 + c * 4);
-                    g.e[q] = ld_f4(a.E + row * d_in + hh * 32 + c * 4);
+                    g.s[q] = ld_stream_f4(a.S + row * d_in + hh * 32 + c * 4);
+                    g.e[q] = ld_stream_f4(a.E + row * d_in + hh * 32 + c * 4);
                 }
             }
         };
@@ -581,8 +581,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 h.e[j] = h.gn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 h.sl[j] = -1;
                 if (ok) {
-                    h.e[j] = ld_f4(a.E_out + row * d_out + c0);
-                    if (a.gE_next) h.gn[j] = ld_f4(a.gE_next + row * d_out + c0);
+                    h.e[j] = ld_stream_f4(a.E_out + row * d_out + c0);
+                    if (a.gE_next) h.gn[j] = ld_stream_f4(a.gE_next + row * d_out + c0);
                     if (a.slot) h.sl[j] = a.slot[row];
                 }
             }
@@ -830,9 +830,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
                 const int64_t row = row0 + r;
                 h.s[q2] = h.e[q2] = h.g[q2] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row < a.n_rows) {
-                    h.s[q2] = ld_f4(a.S + row * d_in + c * 4);
-                    h.e[q2] = ld_f4(a.E + row * d_in + c * 4);
-                    if (c < gq) h.g[q2] = ld_f4(a.gM + row * d_out + c * 4);
+                    h.s[q2] = ld_stream_f4(a.S + row * d_in + c * 4);
+                    h.e[q2] = ld_stream_f4(a.E + row * d_in + c * 4);
+                    if (c < gq) h.g[q2] = ld_stream_f4(a.gM + row * d_out + c * 4);
                 }
             }
         };

@@ -39,7 +39,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+#ifdef NGCF_NO_PROXY_FENCE
+__device__ __forceinline__ void fence_proxy_async_smem() {}
+#else
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // ---- cp.async (LDGSTS): 16 bytes global -> shared without a register stage; src_bytes < 16 zero-fills the rest ------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
