@@ -305,6 +305,23 @@ def run_ours(args):
     else:
         ms_e2e, loss_val = ms_e2e_eager, loss_eager
 
+    # ---- the reference's whole training iteration (experiment.py:45-58): the step above + Adam (main.py:74) -----------
+    # reported beside the metric, not in it (BASELINE.json's metric is fwd + bwd + BPR)
+    with_adam = None
+    if gstep is not None and world == 1:
+        try:
+            gstep_opt = pkg.GraphedStep(model, crit, BATCH, node_flag=True, optimizer=pkg.Adam(model.parameters(), lr=5e-5))
+            for j in range(max(args.warmup, 3)):
+                gstep_opt(dbatches[j % len(dbatches)])
+            fence()
+            ms_opt = timed_resident(gstep_opt)
+            with_adam = {"ms_per_step": round(ms_opt, 5), "adam_ms": round(ms_opt - ms_per_step, 5),
+                         "api": "GraphedStep(optimizer=ngcf_b200.Adam(lr=5e-5)): fwd + BPR + bwd + ngcf_adam_step (one launch "
+                                "over all parameters) in one replayed graph",
+                         "adam_algorithmic_bytes": 28 * sum(p.numel() for p in model.parameters() if p.grad is not None)}
+        except Exception as e:
+            log(f"[bench] step + Adam graph failed ({type(e).__name__}: {e})")
+
     # ---- roofline of the dominant kernel: the propagation SpMM of layer 0 exactly as the step runs it (this step's
     # node-dropout survivors, compacted), timed alone, cold L2 ----------------------------------------------------------
     from seoul_tourism_recommendation_ngcf_b200.plan import node_dropout_compact
@@ -414,7 +431,7 @@ def run_ours(args):
                   "api": "drop-in NGCF.forward + BPR + loss.backward() issued eagerly from Python"},
         "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
         "gpu_launches_note": "library kernels per step (captured once, replayed per step under GraphedStep)",
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "training_iteration_with_adam": with_adam,
     }
     if breakdown:
         out["breakdown"] = breakdown

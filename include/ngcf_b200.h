@@ -30,6 +30,7 @@ extern "C" {
 #define NGCF_B200_ABI_VERSION 3
 #define NGCF_MAX_LAYERS 8
 #define NGCF_MAX_WIDTH 128          /* widest embedding / layer size the kernels accept */
+#define NGCF_ADAM_MAX_TENSORS 32     /* parameter tensors one ngcf_adam_step call updates */
 
 typedef enum {
     NGCF_OK = 0,
@@ -246,6 +247,18 @@ int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int k, size_t* b
 int ngcf_score_topk(const float* U, int64_t n_users, const float* I, int64_t n_items, int D, int k,
                     float* out_val /*[n_users,k]*/, int64_t* out_idx /*[n_users,k]*/,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimizer step: torch.optim.Adam(model.parameters(), lr) of main.py:74, stepped at experiment.py:58 -----------
+ * One launch over up to NGCF_ADAM_MAX_TENSORS parameter tensors (host arrays of device pointers, sizes in elements):
+ *   g' = g + weight_decay p;  m = beta1 m + (1-beta1) g';  v = beta2 v + (1-beta2) g'^2;
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)          (torch's non-amsgrad Adam)
+ * t = step + *step_dev (step_dev: optional device counter, for CUDA-graph replay; t counts from 1).  zero_grads != 0
+ * also clears the gradients (optimizer.zero_grad(), experiment.py:55) in the same pass.  Hyper-parameters are doubles:
+ * 1 - beta and the bias corrections are formed in double like torch's Python floats, the element math is fp32. */
+int ngcf_adam_step(float* const* params_host, float* const* grads_host, float* const* exp_avg_host,
+                   float* const* exp_avg_sq_host, const int64_t* sizes_host, int n_tensors, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int64_t step, const int64_t* step_dev,
+                   int zero_grads, void* stream);
 
 /* ---- debugging aids (tools/bwd_timeline.py, fwd_timeline.py, spmm_timeline.py); not part of the product path --------
  * ngcf_debug_bwd_timeline: switches the in-kernel SM-clock stamps of CTA 0 of the tcgen05 dense kernels on/off and

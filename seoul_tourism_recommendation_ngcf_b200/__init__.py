@@ -2,6 +2,7 @@
 from .NGCF import NGCF
 from .bprloss import BPR
 from .graph import GraphedStep
+from .optim import Adam
 from .scoring import score_topk
 
-__all__ = ["NGCF", "BPR", "GraphedStep", "score_topk"]
+__all__ = ["NGCF", "BPR", "GraphedStep", "Adam", "score_topk"]

@@ -60,6 +60,8 @@ SIGNATURES = {
                        _u64, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ngcf_rowgrad_normalize": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, C.POINTER(_vp),
                                C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, _vp],
+    "ngcf_adam_step": [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.c_int,
+                       C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _vp, C.c_int, _vp],
     "ngcf_debug_bwd_timeline": [C.c_int, _vp],
     "ngcf_debug_spmm_timeline": [_vp],
     "ngcf_debug_compact_timeline": [_vp],

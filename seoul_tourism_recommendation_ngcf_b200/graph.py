@@ -22,25 +22,30 @@ class GraphedStep:
     ``year`` must be a host tensor (it selects ``lap_list[year.min() % 18]`` on the host, NGCF.py:117); one graph is
     kept per selected Laplacian.  ``node_flag`` / train-vs-eval mode are frozen at capture time."""
 
-    def __init__(self, model, criterion, batch_size: int, node_flag: bool = True, warmup: int = 1):
+    def __init__(self, model, criterion, batch_size: int, node_flag: bool = True, warmup: int = 1, optimizer=None):
         dev = model.user_embedding.weight.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedStep needs the model on a CUDA device")
         self.model, self.criterion, self.node_flag, self.warmup = model, criterion, bool(node_flag), int(warmup)
         self.B = int(batch_size)
+        # optional ngcf_b200.Adam: its step (and the zeroing of the gradients for the next batch, experiment.py:55,58)
+        # joins the graph, so a replay is the reference's whole training iteration
+        self.optimizer = optimizer
         self.static_idx = torch.zeros(len(FIELDS), self.B, dtype=torch.int64, device=dev)
         self.stage = torch.zeros(len(FIELDS), self.B, dtype=torch.int64).pin_memory()
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.graphs = {}
         self.launches_per_step = None
 
-    def _run(self, year):
+    def _run(self, year, with_optimizer: bool = True):
         m = self.model
         f = {k: self.static_idx[i] for i, k in enumerate(FIELDS)}
         u, p, n = m(year=year, u_id=f["u_id"], age=f["age"], sex=f["sex"], month=f["month"], day=f["day"], dow=f["dow"],
                     pos_item=f["pos_item"], neg_item=f["neg_item"], node_flag=self.node_flag)
         loss = self.criterion(u, p, n)
         loss.backward()
+        if self.optimizer is not None and with_optimizer:
+            self.optimizer.step()         # (a replay overwrites every gradient buffer, so nothing needs zeroing)
         self.seed_dev.add_(0x9E3779B97F4A7C15 & (2 ** 62 - 1))        # next step: a different RNG key
         return loss
 
@@ -51,9 +56,15 @@ class GraphedStep:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):                                    # warm-up outside the graph (plans, buffers)
+            # the forward rewrites the batch users' rows in place (feature mix, NGCF.py:114-115: not idempotent unless
+            # emb_ratio == 1), so the warm-up runs on a snapshot of the user table that is put back afterwards
+            users_before = m.user_embedding.weight.detach().clone()
             for _ in range(self.warmup):
                 m.zero_grad(set_to_none=True)
-                self._run(year)
+                self._run(year, with_optimizer=False)                 # no parameter changes before the capture
+            if self.optimizer is not None:                            # optimizer state must exist before the capture
+                self.optimizer.prepare([p for p in m.parameters() if p.grad is not None])
+            m.user_embedding.weight.data.copy_(users_before)
         torch.cuda.current_stream().wait_stream(s)
         m.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()

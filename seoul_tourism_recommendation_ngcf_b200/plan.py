@@ -247,13 +247,17 @@ def node_dropout_bits(side: CsrSide, drop_p: float, seed: int, seed_dev, n_layer
 
 
 def node_dropout_compact(side: CsrSide, drop_p: float, seed: int, seed_dev, n_layers: int, row_offset: int = 0,
-                         as_L: bool = True, as_Lt: bool = False):
+                         as_L: bool = True, as_Lt: bool = False, static_keys: bool = True):
     """One step's node dropout applied like the reference does it (entries deleted, cumulatively per layer,
     NGCF.py:93-100): per layer the surviving entries of every SpMM tile, compacted, for ``side`` read as L and/or as
     L^T.  Returns (per-layer list of (ent, trp) or None, same for L^T); pass one pair to ``spmm(compact=...)``."""
     lib = _lib.load()
     dev = side.rowptr.device
-    side.ensure_keys(row_offset)
+    if static_keys:
+        side.ensure_keys(row_offset)
+    elif side.key_l is not None:                     # (tests) the pass then derives the keys from the coordinates
+        side.key_l = side.key_t = None
+        side._struct_cache.clear()
     n_t = int(side.tiles.shape[0]) + (int(side.chunk_tiles.shape[0]) if side.chunk_tiles is not None else 0)
     per = lib.ngcf_spmm_tile_rows() + 1
 

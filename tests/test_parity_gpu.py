@@ -277,6 +277,11 @@ def test_device_rng_dropout_statistics_and_consistency():
     _, ct2 = node_dropout_compact(ps.bwd, 0.3, 1234, None, 3, as_L=False, as_Lt=True)
     assert torch.equal(spmm(ps.bwd, None, eye, 128, transposed=True, compact=ct2[2]), m2.T)
     from seoul_tourism_recommendation_ngcf_b200 import _lib
+    # static per-entry keys (the plan's default) and keys derived from the coordinates inside the pass: same survivors
+    cl_nk, ct_nk = node_dropout_compact(ps.fwd, 0.3, 1234, None, 3, as_L=True, as_Lt=True, static_keys=False)
+    for k in range(3):
+        for x, y in ((cl[k], cl_nk[k]), (ct[k], ct_nk[k])):
+            assert torch.equal(spmm(ps.fwd, None, eye, 128, compact=x), spmm(ps.fwd, None, eye, 128, compact=y))
     per = _lib.load().ngcf_spmm_tile_rows() + 1
     tiles = ps.fwd.tiles.cpu().numpy()
     for k, frac in ((0, 0.7), (2, 0.343)):                       # survivors per tile = what the bits say, in order
@@ -622,3 +627,60 @@ def test_node_dropout_modes_agree():
     # different fp32 summation tree
     for a, b_ in zip(res["compact"], res["inkernel"]):
         assert rel_err(a.cpu().numpy().reshape(-1), b_.cpu().numpy().reshape(-1)) <= 2e-6
+
+
+def test_adam_matches_torch_adam():
+    """ngcf_adam_step against torch.optim.Adam on the CPU (the reference's optimizer, main.py:74): five steps over
+    tensors of awkward sizes, one without gradient (the feature tables never get one, NGCF.py:115)."""
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(70, 64), (129, 64), (64, 64), (64,), (5, 13), (1,), (4097, 3)]
+    ref = [torch.nn.Parameter(torch.randn(*sh, generator=gen)) for sh in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref]
+    for wd in (0.0, 0.01):
+        o_ref = torch.optim.Adam(ref, lr=3e-3, weight_decay=wd)
+        o_our = pkg.Adam(ours, lr=3e-3, weight_decay=wd)
+        for step in range(5):
+            for i, (a, b) in enumerate(zip(ref, ours)):
+                if i == 4:
+                    a.grad = b.grad = None
+                    continue
+                g = torch.randn(a.shape, generator=gen) * (10.0 ** (step - 2))
+                a.grad, b.grad = g.clone(), g.clone().to(DEV)
+            o_ref.step()
+            o_our.step(zero_grads=(step == 4))
+            for i, (a, b) in enumerate(zip(ref, ours)):
+                assert rel_err(b.detach().cpu().numpy().reshape(-1), a.detach().numpy().reshape(-1)) <= 2e-6, (wd, step, i)
+        assert all(float(b.grad.abs().max()) == 0.0 for i, b in enumerate(ours) if i != 4)      # zero_grads
+        sd = o_our.state_dict()
+        assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
+        assert 4 not in sd["state"] or not sd["state"][4]
+        assert rel_err(sd["state"][1]["exp_avg_sq"].cpu().numpy(), o_ref.state_dict()["state"][1]["exp_avg_sq"].numpy()) <= 2e-6
+
+
+def test_graphed_training_iteration_with_adam_tracks_torch_adam():
+    """GraphedStep(optimizer=Adam): forward + BPR + backward + Adam as one replayed graph, against the same three
+    steps taken eagerly with torch.optim.Adam (dropout off so both see the same gradients)."""
+    n_user, n_item, B = 600, 400, 256
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, 20000, seed=2)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    nd = synth.num_dict_for(n_user, n_item)
+    batches = [{k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=10 + j).items()} for j in range(3)]
+    models = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        m = pkg.NGCF(64, [64, 64], 0.0, [0.0, 0.0], 0.5, [L, L], nd, B, torch.device(DEV)).to(DEV)
+        m.train()
+        models.append(m)
+    crit = pkg.BPR(0.025, B)
+    ref_opt = torch.optim.Adam(models[0].parameters(), lr=1e-2)
+    for b in batches:
+        ref_opt.zero_grad()
+        loss = crit(*_call(models[0], b, False))
+        loss.backward()
+        ref_opt.step()
+    gstep = pkg.GraphedStep(models[1], crit, B, node_flag=False, optimizer=pkg.Adam(models[1].parameters(), lr=1e-2))
+    for b in batches:
+        loss_g = gstep({k: (v if k == "year" else v.to(DEV)) for k, v in b.items()})
+    assert abs(float(loss_g) - float(loss)) <= 1e-4 * abs(float(loss))
+    for (k, a), (_, c) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert rel_err(c.detach().cpu().numpy(), a.detach().cpu().numpy()) <= 1e-4, k
