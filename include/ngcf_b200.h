@@ -61,16 +61,14 @@ int ngcf_coo_to_csr(const int64_t* coo_row, const int64_t* coo_col, int64_t nnz,
  * with more than ngcf_spmm_split_threshold() entries ("hubs") are empty in rowptr/ent and live in hub_ent, cut
  * into chunks of at most that many entries; chunk c covers hub_ent[chunk_ptr[c] .. chunk_ptr[c+1]) and belongs
  * to row chunk_row[c]; hub row with id h = hub_of_row[row] owns chunks hub_chunk_ptr[h] .. hub_chunk_ptr[h+1].
- * Tiles are int32 quadruples {r0, r1, e0, e1}: rows [r0, r1) with entries [e0, e1) of ent (tiles, ftiles) or
- * chunks [r0, r1) with entries [e0, e1) of hub_ent (chunk_tiles).  `tiles`/`chunk_tiles` hold at most
- * ngcf_spmm_tile_rows() rows and ngcf_spmm_tile_entries() entries (standalone SpMM); `ftiles` at most
- * ngcf_fused_tile_rows() rows and ngcf_fused_tile_entries() entries (fused forward layer). */
+ * Tiles are int32 quadruples {r0, r1, e0, e1}: rows [r0, r1) with entries [e0, e1) of ent (tiles) or
+ * chunks [r0, r1) with entries [e0, e1) of hub_ent (chunk_tiles); at most ngcf_spmm_tile_rows() rows and
+ * ngcf_spmm_tile_entries() entries each. */
 typedef struct ngcf_csr {
     int64_t n_rows;
     const int32_t* rowptr;          /* [n_rows+1], hub rows empty */
     const int32_t* ent;             /* [2*nnz_short] */
     const int32_t* tiles;           /* [4*n_tiles] */
-    const int32_t* ftiles;          /* [4*n_ftiles] */
     const int32_t* hub_of_row;      /* [n_rows] hub id or -1; may be NULL when n_hub == 0 */
     const int32_t* hub_chunk_ptr;   /* [n_hub+1] */
     const int32_t* chunk_ptr;       /* [n_chunks+1] */
@@ -83,15 +81,13 @@ typedef struct ngcf_csr {
     const uint32_t* key_l;          /* optional [nnz] static node-dropout keys (ngcf_entry_keys), CSR read as L ... */
     const uint32_t* key_t;          /* ... and read as L^T; NULL: the per-step pass derives them from the coordinates */
     int64_t key_row_offset;         /* the row_offset the keys were computed for */
-    int32_t n_tiles, n_ftiles, n_hub, n_chunks, n_chunk_tiles;
+    int32_t n_tiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
 } ngcf_csr;
 
 int ngcf_spmm_split_threshold(void);
 int ngcf_spmm_tile_rows(void);
 int ngcf_spmm_tile_entries(void);
-int ngcf_fused_tile_rows(void);
-int ngcf_fused_tile_entries(void);
 
 /* ent_out[t] = (colidx[t], coo_val[perm[t]] * keep_mask[perm[t]]): entry pairs in execution order (ordinary rows
  * first, then hub chunks; colidx/perm in that order), optionally with an explicit node-dropout mask folded in.

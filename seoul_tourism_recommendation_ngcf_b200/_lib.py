@@ -17,10 +17,10 @@ _vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, 
 
 class NgcfCsr(C.Structure):
     """Mirror of ``ngcf_csr`` (include/ngcf_b200.h): a host struct of device pointers."""
-    _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp), ("ftiles", _vp),
+    _fields_ = [("n_rows", _i64), ("rowptr", _vp), ("ent", _vp), ("tiles", _vp),
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
                 ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp), ("key_l", _vp), ("key_t", _vp), ("key_row_offset", _i64),
-                ("n_tiles", _i32), ("n_ftiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
+                ("n_tiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
                 ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
 
 
@@ -36,8 +36,6 @@ SIGNATURES = {
     "ngcf_edge_entries": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "ngcf_spmm_tile_rows": [],
     "ngcf_spmm_tile_entries": [],
-    "ngcf_fused_tile_rows": [],
-    "ngcf_fused_tile_entries": [],
     "ngcf_feature_mix": [_vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(_vp), _vp, _i64, _f32,
                          _vp, _vp],
     "ngcf_spmm_split_threshold": [],

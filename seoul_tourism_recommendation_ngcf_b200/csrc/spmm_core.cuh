@@ -1,5 +1,4 @@
-// Device-side core of the tiled CSR SpMM, shared by the standalone SpMM (spmm.cu: backward L^T·gS, inference
-// helpers) and the fused forward layer (fused_fwd.cu).
+// Device-side core of the tiled CSR SpMM (spmm.cu: L·E of the forward, L^T·gS of the backward).
 //
 // Layout (built once per Laplacian by plan.py, see ngcf_csr in ngcf_b200.h):
 //   * entries are interleaved (col, value-bits) pairs, so one 8-byte shared-memory read yields both;

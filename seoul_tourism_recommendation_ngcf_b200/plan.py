@@ -91,8 +91,6 @@ class CsrSide:
         rp_host = self.rowptr.cpu().numpy()
         self.tiles = torch.from_numpy(greedy_tiles(rp_host, lib.ngcf_spmm_tile_rows(),
                                                    lib.ngcf_spmm_tile_entries())).to(dev)
-        self.ftiles = torch.from_numpy(greedy_tiles(rp_host, lib.ngcf_fused_tile_rows(),
-                                                    lib.ngcf_fused_tile_entries())).to(dev)
         if self.n_chunks:
             self.chunk_tiles = torch.from_numpy(greedy_tiles(self.chunk_ptr.cpu().numpy(), lib.ngcf_spmm_tile_rows(),
                                                              lib.ngcf_spmm_tile_entries())).to(dev)
@@ -117,7 +115,6 @@ class CsrSide:
             s.rowptr = self.rowptr.data_ptr()
             s.ent = ent.data_ptr()
             s.tiles = self.tiles.data_ptr()
-            s.ftiles = self.ftiles.data_ptr()
             s.hub_of_row = _lib.ptr(self.hub_of_row)
             s.hub_chunk_ptr = _lib.ptr(self.hub_chunk_ptr)
             s.chunk_ptr = _lib.ptr(self.chunk_ptr)
@@ -130,7 +127,6 @@ class CsrSide:
             s.key_t = _lib.ptr(self.key_t)
             s.key_row_offset = self.key_row_offset
             s.n_tiles = int(self.tiles.shape[0])
-            s.n_ftiles = int(self.ftiles.shape[0])
             s.n_hub = self.n_hub
             s.n_chunks = self.n_chunks
             s.n_chunk_tiles = int(self.chunk_tiles.shape[0]) if self.chunk_tiles is not None else 0

@@ -182,7 +182,7 @@ def test_spmm_forward_and_transpose_vs_torch(d):
     assert np.array_equal(np.repeat(crow, np.diff(cp)), coo_rows[perm[side.nnz_short:]])
     hub_of = side.hub_of_row.cpu().numpy()
     assert set(np.nonzero(hub_of >= 0)[0]) == set(crow) and np.all(np.diff(rp)[hub_of >= 0] == 0)
-    for tiles, ptr in ((side.tiles, rp), (side.ftiles, rp), (side.chunk_tiles, cp)):
+    for tiles, ptr in ((side.tiles, rp), (side.chunk_tiles, cp)):
         t = tiles.cpu().numpy()
         assert t[0, 0] == 0 and t[-1, 1] == ptr.size - 1 and np.array_equal(t[1:, 0], t[:-1, 1])
         assert np.array_equal(t[:, 2], ptr[t[:, 0]]) and np.array_equal(t[:, 3], ptr[t[:, 1]])
