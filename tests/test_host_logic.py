@@ -122,3 +122,29 @@ def test_greedy_tiles_cover_rows_within_caps():
     t = greedy_tiles(np.array([0, 5, 1005, 1010]), 16, 512)
     assert t.tolist() == [[0, 1, 0, 5], [1, 2, 5, 1005], [2, 3, 1005, 1010]]
     assert greedy_tiles(np.array([0]), 16, 512).shape == (0, 4)
+
+
+def test_matrix_dropin_builds_the_reference_lap_list(tmp_path):
+    """Drop-in ``Matrix`` (matrix.py:12-83) over the sparse builder: same lap_list as the reference built from the same
+    frame (golden fixture, generated by the reference's dense Matrix.create_matrix), and the pickle round trip."""
+    import pickle
+    import pandas as pd
+    from seoul_tourism_recommendation_ngcf_b200.matrix import Matrix
+    from tests._golden import Golden
+    g = Golden("seoul_small")
+    f = g.group("frame")
+    df = pd.DataFrame({k: f[k] for k in ("year", "userid", "itemid", "visitor")})
+    df["unused"] = 0
+    m = Matrix(df, ["year", "userid", "itemid", "visitor"], "visitor", {"user": g.cfg["n_user"], "item": g.cfg["n_item"]},
+               str(tmp_path), True, torch.device("cpu"))
+    laps = m.create_matrix()
+    ref = g.lap_list()
+    assert len(laps) == len(ref)
+    for a, b in zip(laps, ref):
+        assert tuple(a.shape) == tuple(b.shape) and not a.is_coalesced()
+        assert torch.equal(a._indices(), b._indices()) and torch.equal(a._values(), b._values())
+    files = [p for p in os.listdir(tmp_path) if p.startswith("lap_list_implicit_") and p.endswith(".pkl")]
+    assert len(files) == 1
+    with open(os.path.join(tmp_path, files[0]), "rb") as fh:
+        back = pickle.load(fh)
+    assert torch.equal(back[1]._values(), ref[1]._values())
