@@ -15,7 +15,10 @@ namespace {
 
 using namespace ngcf;
 
-constexpr int SP_THREADS = 128;
+#ifndef NGCF_SPMM_THREADS
+#define NGCF_SPMM_THREADS 64
+#endif
+constexpr int SP_THREADS = NGCF_SPMM_THREADS;
 constexpr int SP_WARPS = SP_THREADS / 32;
 
 struct TileSide {                   // one tile list: the ordinary rows, or the hub chunks
@@ -77,8 +80,11 @@ struct CtaSync {
 };
 
 // G > 0: vector path with G lanes per gathered row; G == 0: scalar path
+#ifndef NGCF_SPMM_CTAS
+#define NGCF_SPMM_CTAS 20
+#endif
 template <int G>
-__global__ void __launch_bounds__(SP_THREADS, 8) spmm_tile_kernel(SpmmArgs a) {
+__global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_tile_kernel(SpmmArgs a) {
     __shared__ __align__(16) int2 ent_s[SP_TILE_ENT];
     __shared__ int rp_s[SP_TILE_ROWS + 1];
     __shared__ int hub_s[SP_TILE_ROWS];                               // row side: hub id of each tile row, or -1

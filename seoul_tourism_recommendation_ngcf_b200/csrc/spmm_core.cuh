@@ -15,13 +15,20 @@
 namespace ngcf {
 
 constexpr int SPLIT = 128;          // rows with more entries than this are hubs; also the hub chunk size
-constexpr int SP_TILE_ROWS = 16;    // SpMM tile: at most this many rows ...
-constexpr int SP_TILE_ENT = 512;    // ... and this many entries (staged in shared memory by one CTA)
+#ifndef NGCF_SPMM_TILE_ROWS
+#define NGCF_SPMM_TILE_ROWS 16
+#define NGCF_SPMM_TILE_ENT 512
+#endif
+constexpr int SP_TILE_ROWS = NGCF_SPMM_TILE_ROWS;    // SpMM tile: at most this many rows ...
+constexpr int SP_TILE_ENT = NGCF_SPMM_TILE_ENT;   // ... and this many entries (staged in shared memory by one CTA)
 static_assert(SP_TILE_ENT >= SPLIT, "a tile must hold the longest ordinary row");
 #ifndef NGCF_SPMM_TAIL
 #define NGCF_SPMM_TAIL 4       // predicated remainder batch per lane group (2, 4 and 8 measure the same within noise)
 #endif
-constexpr int UNROLL = 8;           // gathered rows in flight per lane group
+#ifndef NGCF_SPMM_UNROLL
+#define NGCF_SPMM_UNROLL 4
+#endif
+constexpr int UNROLL = NGCF_SPMM_UNROLL;           // gathered rows in flight per lane group
 
 struct TileInfo {                   // int4: rows [r0, r1), entries [e0, e1) of one tile
     int r0, r1, e0, e1;
