@@ -24,7 +24,7 @@ LEAKY_SLOPE = 0.2   # NGCF.py:140
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _lib.current_stream()
 
 
 class _Ctx:

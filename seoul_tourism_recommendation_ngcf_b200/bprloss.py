@@ -21,7 +21,7 @@ class _BprFn(torch.autograd.Function):
             gu = gp = gn = None
         _lib.check(lib.ngcf_bpr_fwd_bwd(u.data_ptr(), p.data_ptr(), n.data_ptr(), B, D, float(weight_decay),
                                         float(batch_size), wu, wp, wn, loss.data_ptr(), _lib.ptr(gu), _lib.ptr(gp),
-                                        _lib.ptr(gn), torch.cuda.current_stream().cuda_stream), "bpr_fwd_bwd")
+                                        _lib.ptr(gn), _lib.current_stream()), "bpr_fwd_bwd")
         ctx.grads = (gu, gp, gn)
         return loss
 

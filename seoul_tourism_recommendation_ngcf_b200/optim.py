@@ -69,7 +69,7 @@ class Adam(torch.optim.Optimizer):
                                               float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
                                               float(group["eps"]), float(group["weight_decay"]), 0,
                                               self._step_dev.data_ptr(), int(zero_grads),
-                                              torch.cuda.current_stream().cuda_stream), "adam_step")
+                                              _lib.current_stream()), "adam_step")
             if not capturing:
                 for p in ps:
                     self.state[p]["step"] += 1

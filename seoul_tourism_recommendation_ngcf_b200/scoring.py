@@ -28,5 +28,5 @@ def score_topk(u_embeds: torch.Tensor, item_embeds: torch.Tensor, k: int):
     val = torch.empty(U, k, dtype=torch.float32, device=u.device)
     idx = torch.empty(U, k, dtype=torch.int64, device=u.device)
     _lib.check(lib.ngcf_score_topk(u.data_ptr(), U, it.data_ptr(), n_items, D, k, val.data_ptr(), idx.data_ptr(),
-                                   ws.data_ptr(), need.value, torch.cuda.current_stream().cuda_stream), "score_topk")
+                                   ws.data_ptr(), need.value, _lib.current_stream()), "score_topk")
     return val, idx
