@@ -51,7 +51,15 @@ struct FwdTcArgs {
     float* E_out;
     int n_tiles;
     int64_t row_off;          // global index of local row 0 (RNG keys only)
+    // block decomposition of layers wider than 64 (d_in / d_out above are the BLOCK's widths): this launch contracts
+    // columns [in_off, in_off + d_in) of S / E (row stride ld_in) against rows w_row1.. (W1 part) and w_row2.. (W2 part),
+    // columns [out_off, out_off + d_out) of wcat (row stride d_out_full) into columns [out_off, ..) of E_out (row
+    // stride d_out_full).  mode: FW_SINGLE = bias + activation; FW_PARTIAL = store the raw partial sums;
+    // FW_FINAL = add the partial sums found in E_out, then bias + activation.
+    int64_t ld_in;
+    int in_off, w_row1, w_row2, out_off, d_out_full, mode;
 };
+enum { FW_SINGLE = 0, FW_PARTIAL = 1, FW_FINAL = 2 };
 
 struct Bars {
     uint64_t full[TC_MAX_KB];
@@ -119,15 +127,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     for (int i = tid; i < d_out * KB * 8; i += TC_THREADS) {
         const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
         float4 w;
-        const float* src = a.wcat + (int64_t)(kb * 32 + c * 4) * d_out + n;
-        w.x = src[0]; w.y = src[d_out]; w.z = src[2 * d_out]; w.w = src[3 * d_out];
+        const int k = kb * 32 + c * 4;                                    // 4 consecutive k stay inside the W1 or the W2 part
+        const int wrow = k < d_in ? a.w_row1 + k : a.w_row2 + (k - d_in);
+        const float* src = a.wcat + (int64_t)wrow * a.d_out_full + a.out_off + n;
+        w.x = src[0]; w.y = src[a.d_out_full]; w.z = src[2 * a.d_out_full]; w.w = src[3 * a.d_out_full];
         float4 hi, lo;
         split_tf32(w, hi, lo);
         const uint32_t off = kb * b_block + sw128_offset(n, c);
         *reinterpret_cast<float4*>(B_hi + off) = hi;
         *reinterpret_cast<float4*>(B_lo + off) = lo;
     }
-    for (int i = tid; i < 64; i += TC_THREADS) bias_s[i] = i < d_out ? a.bias_eff[i] : 0.f;
+    for (int i = tid; i < 64; i += TC_THREADS) bias_s[i] = i < d_out ? a.bias_eff[a.out_off + i] : 0.f;
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -163,43 +173,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
             if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);           // accumulator drained: next tile may reuse it
             if (!has_chunk) continue;
             const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
-            const int64_t my_row = row_base + lane;
-            uint32_t keep = 0xffffffffu;                                  // this row's 32 dropout decisions of the chunk
-            if (MM == MM_BITS && my_row < a.n_rows) keep = a.mess_bits[my_row * ((d_out + 31) >> 5) + c];
+            // raw accumulators through the per-warp transposition buffer; everything else happens in the coalesced
+            // layout (thread = 4 consecutive columns of rows i * 4 + rr): partial sums of an earlier K block, bias,
+            // LeakyReLU, dropout (one RNG call = exactly the thread's four columns), store
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float o[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float m = v[j + t] + bias_s[c * 32 + j + t];
-                    o[t] = m > 0.f ? m : a.slope * m;                                   // LeakyReLU, NGCF.py:140
-                }
-                if (MM == MM_BITS) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) o[t] = (keep >> (j + t)) & 1u ? o[t] * inv_keep : 0.f;
-                } else if (MM == MM_HASH) {
-                    const float4 mm = mess_multiplier4_pre(thr, inv_keep, seed, a.layer, (uint64_t)((my_row + a.row_off) * d_out + c * 32 + j) >> 2);
-                    o[0] *= mm.x; o[1] *= mm.y; o[2] *= mm.z; o[3] *= mm.w;
-                }
-                st_f4(st + stage_off(lane, j >> 2), make_float4(o[0], o[1], o[2], o[3]));
-            }
+            for (int j = 0; j < 32; j += 4)
+                st_f4(st + stage_off(lane, j >> 2), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             __syncwarp();
             float4 r4[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + stage_off(i * 4 + rr, c4));
             __syncwarp();
-            const int col = c * 32 + c4 * 4;
+            const int col = c * 32 + c4 * 4;                              // within the block's d_out columns
             if (col < d_out) {
+                const int gcol = a.out_off + col;                         // within the layer's d_out_full columns
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
+                const int words = (a.d_out_full + 31) >> 5;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int64_t row = row_base + i * 4 + rr;
-                    if (row < a.n_rows) {
-                        if (MM == MM_MULT) {
-                            const float4 mm = ld_f4(a.mess_mult + row * d_out + col);
-                            r4[i].x *= mm.x; r4[i].y *= mm.y; r4[i].z *= mm.z; r4[i].w *= mm.w;
-                        }
-                        st_f4(a.E_out + row * d_out + col, r4[i]);
+                    if (row >= a.n_rows) continue;
+                    float* dst = a.E_out + row * a.d_out_full + gcol;
+                    float4 x = r4[i];
+                    if (a.mode == FW_PARTIAL) {
+                        st_f4(dst, x);
+                        continue;
                     }
+                    if (a.mode == FW_FINAL) {
+                        const float4 prev = ld_f4(dst);
+                        x.x += prev.x; x.y += prev.y; x.z += prev.z; x.w += prev.w;
+                    }
+                    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                    x.x = x.x > 0.f ? x.x : a.slope * x.x;                // LeakyReLU, NGCF.py:140
+                    x.y = x.y > 0.f ? x.y : a.slope * x.y;
+                    x.z = x.z > 0.f ? x.z : a.slope * x.z;
+                    x.w = x.w > 0.f ? x.w : a.slope * x.w;
+                    if (MM == MM_BITS) {
+                        const uint32_t w = a.mess_bits[row * words + (gcol >> 5)] >> (gcol & 31);
+                        x.x = w & 1u ? x.x * inv_keep : 0.f; x.y = w & 2u ? x.y * inv_keep : 0.f;
+                        x.z = w & 4u ? x.z * inv_keep : 0.f; x.w = w & 8u ? x.w * inv_keep : 0.f;
+                    } else if (MM == MM_HASH) {
+                        const float4 mm = mess_multiplier4_pre(thr, inv_keep, seed, a.layer,
+                                                               (uint64_t)((row + a.row_off) * a.d_out_full + gcol) >> 2);
+                        x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+                    } else if (MM == MM_MULT) {
+                        const float4 mm = ld_f4(a.mess_mult + row * a.d_out_full + gcol);
+                        x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+                    }
+                    st_f4(dst, x);
                 }
             }
             BWD_STAMP(0, it, 2);
@@ -261,8 +282,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
                 const int64_t row = row0 + r;
                 g.s[q] = g.e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row < a.n_rows) {
-                    g.s[q] = ld_stream_f4(a.S + row * d_in + hh * 32 + c * 4);
-                    g.e[q] = ld_stream_f4(a.E + row * d_in + hh * 32 + c * 4);
+                    g.s[q] = ld_stream_f4(a.S + row * a.ld_in + a.in_off + hh * 32 + c * 4);
+                    g.e[q] = ld_stream_f4(a.E + row * a.ld_in + a.in_off + hh * 32 + c * 4);
                 }
             }
         };
@@ -890,19 +911,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
 
 }  // namespace
 
+// widths up to 64 are one block; 128 is decomposed into 64-wide blocks of the same kernel (K halves accumulate through
+// the partial sums parked in E_out, N halves are independent)
 bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out) {
-    return (d_in == 32 || d_in == 64) && d_out >= 16 && d_out <= 64 && d_out % 16 == 0;
+    const bool in_ok = d_in == 32 || d_in == 64 || d_in == 128;
+    const bool out_ok = (d_out >= 16 && d_out <= 64 && d_out % 16 == 0) || d_out == 128;
+    return in_ok && out_ok;
 }
 
 int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, int d_out, const float* wcat,
                       const float* bias_eff, float slope, const float* mess_mult, const uint32_t* mess_bits, float mess_p,
                       uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out,
                       cudaStream_t st) {
-    FwdTcArgs a{S, E, n_rows, d_in, d_out, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, E_out,
-                (int)ceil_div64(n_rows, TC_ROWS), row_offset};
-    const int KB = 2 * d_in / 32;
-    const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * d_out * 128) + 64 * sizeof(float) +
-                        FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
     static bool attr_set = false;
     if (!attr_set) {
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -911,14 +931,30 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
-    switch (mess_mode(mess_mult, mess_bits, mess_p)) {
-        case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_NONE>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-        case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_MULT>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-        case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_BITS>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-        default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_HASH>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-    }
-    NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
+    const int bk = d_in > 64 ? 64 : d_in, bn = d_out > 64 ? 64 : d_out;   // block widths
+    const int KH = d_in / bk, NH = d_out / bn;
+    const int n_tiles = (int)ceil_div64(n_rows, TC_ROWS);
+    const int grid = (int)min((int64_t)n_tiles, (int64_t)ngcf_num_sms());
+    const int KB = 2 * bk / 32;
+    const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * bn * 128) + 64 * sizeof(float) +
+                        FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
+    for (int nh = 0; nh < NH; ++nh)
+        for (int kh = 0; kh < KH; ++kh) {
+            FwdTcArgs a{S, E, n_rows, bk, bn, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer,
+                        E_out, n_tiles, row_offset};
+            a.ld_in = d_in; a.in_off = kh * bk;
+            a.w_row1 = kh * bk; a.w_row2 = d_in + kh * bk;
+            a.out_off = nh * bn; a.d_out_full = d_out;
+            a.mode = KH == 1 ? FW_SINGLE : (kh == 0 ? FW_PARTIAL : FW_FINAL);
+            const int mm = a.mode == FW_PARTIAL ? MM_NONE : mess_mode(mess_mult, mess_bits, mess_p);
+            switch (mm) {
+                case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_NONE>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+                case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_MULT>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+                case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_BITS>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+                default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_HASH>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+            }
+            NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
+        }
     return NGCF_OK;
 }
 

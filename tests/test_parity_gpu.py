@@ -421,7 +421,7 @@ def _dense_fwd(S, E, W1, b1, W2, b2, mess_mult=None):
 
 
 @pytest.mark.parametrize("N,d_in,d_out", [(1000, 64, 64), (128, 64, 64), (70839, 64, 64), (333, 32, 48), (777, 64, 16),
-                                          (500, 65, 64), (300, 128, 128), (257, 20, 36)])
+                                          (500, 65, 64), (300, 128, 128), (5000, 128, 64), (1300, 64, 128), (257, 20, 36)])
 def test_dense_forward_vs_float64(N, d_in, d_out):
     """Per-layer epilogue (NGCF.py:131-142) against a float64 restatement.  Widths 32/64 take the tcgen05 3xTF32
     kernel, everything else the FFMA kernel; both must be at fp32 accuracy (1e-5 here, far inside the 1e-4 bar:
