@@ -438,7 +438,7 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                       uint64_t seed,
                       const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out, cudaStream_t st);
 
-bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out);
+bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out, int gh_normalized);
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
@@ -507,7 +507,7 @@ extern "C" int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const f
     NGCF_REQUIRE(mess_p >= 0.f && mess_p < 1.f, "dense_bwd: mess_p %f not in [0,1)", mess_p);
     NGCF_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31), "dense_bwd: n_rows %lld", (long long)n_rows);
     if (n_rows == 0) return NGCF_OK;
-    if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out) && aligned16(S) &&
+    if (ngcf_use_tensor_cores() && gM_scratch && ngcf_dense_bwd_tc_eligible(d_in, d_out, gh_normalized) && aligned16(S) &&
         aligned16(E) && aligned16(gS) && aligned16(gEl) && aligned16(gM_scratch))
         return ngcf_dense_bwd_tc(gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2,
                                  slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer, row_offset, gh_normalized, gS,

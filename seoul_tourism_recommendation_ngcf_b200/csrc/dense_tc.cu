@@ -384,6 +384,12 @@ struct BwdTcArgs {
     float* gb2;
     int n_tiles;
     int64_t row_off;
+    // block decomposition of layers wider than 64 (d_in = 64 and d_out above are the BLOCK's widths): this launch takes
+    // columns [out_off, out_off + d_out) of E_out / gE_next / gM / the dropout source (row stride d_out_full) and
+    // rows out_off.. of W1 / W2, and produces columns [in_off, in_off + 64) of gS / gEl from the same columns of E / S
+    // (row stride d_in_full) and of W1 / W2.  accumulate: add to the gS / gEl already there (an earlier d_out block);
+    // first_in: this launch also writes gM and the bias gradients (once per d_out block).
+    int d_out_full, out_off, d_in_full, in_off, accumulate, first_in;
 };
 
 struct BwdBars {
@@ -439,10 +445,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     // (consecutive threads take consecutive n = consecutive addresses of W1 / W2: coalesced)
     for (int i = tid; i < 128 * KBo * 8; i += TC_THREADS) {
         const int n = i & 127, c = (i >> 7) & 7, kb = i >> 10;
-        const float* W = (n < d_in ? a.W1 : a.W2) + (n & 63);
-        const int o0 = kb * 32 + c * 4;
-        float4 w = make_float4(W[(int64_t)o0 * d_in], W[(int64_t)(o0 + 1) * d_in], W[(int64_t)(o0 + 2) * d_in],
-                               W[(int64_t)(o0 + 3) * d_in]);
+        const float* W = (n < d_in ? a.W1 : a.W2) + a.in_off + (n & 63);
+        const int o0 = a.out_off + kb * 32 + c * 4;
+        const int64_t ldw = a.d_in_full;
+        float4 w = make_float4(W[(int64_t)o0 * ldw], W[(int64_t)(o0 + 1) * ldw], W[(int64_t)(o0 + 2) * ldw],
+                               W[(int64_t)(o0 + 3) * ldw]);
         float4 hi, lo;
         split_tf32(w, hi, lo);
         const uint32_t off = kb * TC_A_BLOCK + sw128_offset(n, c);
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 const int rl = warp * 32 + 2 * i + hsel;
                 const int64_t row = row0 + rl;
                 const bool ok = row < a.n_rows;
-                const int64_t src = (ok ? row : 0) * d_in + c * 4;
+                const int64_t src = (ok ? row : 0) * a.d_in_full + a.in_off + c * 4;
                 const uint32_t off = es_off(rl, c);
                 cp_async16(e_s32 + off, a.E + src, ok ? 16u : 0u);
                 cp_async16(s_s32 + off, a.S + src, ok ? 16u : 0u);
@@ -529,11 +536,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 const int rl = warp * 32 + 2 * i + hsel;
                 const int64_t row = row0 + rl;
                 const uint32_t off = es_off(rl, c);
-                const float4 x = *reinterpret_cast<const float4*>(E_s + off);
-                const float4 y = *reinterpret_cast<const float4*>(S_s + off);
+                float4 x = *reinterpret_cast<const float4*>(E_s + off);
+                float4 y = *reinterpret_cast<const float4*>(S_s + off);
                 if (row < a.n_rows) {
-                    st_f4(a.gS + row * d_in + c * 4, x);
-                    st_f4(a.gEl + row * d_in + c * 4, y);
+                    float* ps = a.gS + row * a.d_in_full + a.in_off + c * 4;
+                    float* pe = a.gEl + row * a.d_in_full + a.in_off + c * 4;
+                    if (a.accumulate) {                                   // an earlier d_out block left its share there
+                        const float4 x0 = ld_f4(ps), y0 = ld_f4(pe);
+                        x.x += x0.x; x.y += x0.y; x.z += x0.z; x.w += x0.w;
+                        y.x += y0.x; y.y += y0.y; y.z += y0.z; y.w += y0.w;
+                    }
+                    st_f4(ps, x);
+                    st_f4(pe, y);
                 }
             }
             __syncwarp();
@@ -602,8 +616,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 h.e[j] = h.gn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 h.sl[j] = -1;
                 if (ok) {
-                    h.e[j] = ld_stream_f4(a.E_out + row * d_out + c0);
-                    if (a.gE_next) h.gn[j] = ld_stream_f4(a.gE_next + row * d_out + c0);
+                    h.e[j] = ld_stream_f4(a.E_out + row * a.d_out_full + a.out_off + c0);
+                    if (a.gE_next) h.gn[j] = ld_stream_f4(a.gE_next + row * a.d_out_full + a.out_off + c0);
                     if (a.slot) h.sl[j] = a.slot[row];
                 }
             }
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 for (int j = 0; j < HP; ++j) {
                     const int s = h.sl[j];
                     if (s >= 0) {                                         // col_off need not be a multiple of 4 (width 65 first)
-                        const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + c0;
+                        const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + a.out_off + c0;
                         h.gn[j].x += gp[0]; h.gn[j].y += gp[1]; h.gn[j].z += gp[2]; h.gn[j].w += gp[3];
                     }
                 }
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                     if (__any_sync(FULL_MASK, s >= 0)) {
                         float4 gh = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (s >= 0) {                                         // col_off need not be a multiple of 4 (width 65 first)
-                            const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + c0;
+                            const float* gp = a.gsum + (int64_t)s * a.ld_gsum + a.col_off + a.out_off + c0;
                             gh = make_float4(gp[0], gp[1], gp[2], gp[3]);
                         }
                         const float4 e = h.e[j];
@@ -659,21 +673,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
                 float4 g = h.gn[j];
                 float4 mult = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (MM == MM_MULT) {
-                    if (in) mult = ld_f4(a.mess_mult + row * d_out + c0);
+                    if (in) mult = ld_f4(a.mess_mult + row * a.d_out_full + a.out_off + c0);
                 } else if (MM == MM_BITS) {
                     uint32_t w = 0;
-                    if (in) w = a.mess_bits[row * ((d_out + 31) >> 5) + (c0 >> 5)] >> (c0 & 31);
+                    if (in) w = a.mess_bits[row * ((a.d_out_full + 31) >> 5) + ((a.out_off + c0) >> 5)] >> ((a.out_off + c0) & 31);
                     mult = make_float4(w & 1u ? inv_keep : 0.f, w & 2u ? inv_keep : 0.f, w & 4u ? inv_keep : 0.f,
                                        w & 8u ? inv_keep : 0.f);
                 } else if (MM == MM_HASH) {
-                    mult = mess_multiplier4_pre(thr, inv_keep, seed, a.layer, (uint64_t)((row + a.row_off) * d_out + c0) >> 2);
+                    mult = mess_multiplier4_pre(thr, inv_keep, seed, a.layer,
+                                                (uint64_t)((row + a.row_off) * a.d_out_full + a.out_off + c0) >> 2);
                 }
                 g.x *= mult.x * (e.x > 0.f ? 1.f : a.slope);              // dropout + LeakyReLU backward
                 g.y *= mult.y * (e.y > 0.f ? 1.f : a.slope);
                 g.z *= mult.z * (e.z > 0.f ? 1.f : a.slope);
                 g.w *= mult.w * (e.w > 0.f ? 1.f : a.slope);
                 if (!in) g = make_float4(0.f, 0.f, 0.f, 0.f);             // rows past the end / unused columns
-                if (in) st_f4(a.gM + row * d_out + c0, g);
+                if (in && a.first_in) st_f4(a.gM + row * a.d_out_full + a.out_off + c0, g);
                 colsum.x += g.x; colsum.y += g.y; colsum.z += g.z; colsum.w += g.w;
                 if (col_ok) {
                     float4 hi, lo;
@@ -719,10 +734,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_LOAD_WARPS * 32) : "memory");   // loader warps only
         const int lt = tid - (TC_EPI_WARPS + 1) * 32;
-        if (lt < d_out) {
+        if (lt < d_out && a.first_in) {
             const float cs = bars->colsum[lt];
-            atomicAdd(a.gb2 + lt, cs);
-            atomicAdd(a.gb1 + lt, 2.0f * cs);                             // w1_list[i] is applied twice (NGCF.py:131,133)
+            atomicAdd(a.gb2 + a.out_off + lt, cs);
+            atomicAdd(a.gb1 + a.out_off + lt, 2.0f * cs);                 // w1_list[i] is applied twice (NGCF.py:131,133)
         }
     }
 
@@ -750,6 +765,9 @@ struct WgradArgs {
     float* gW1;
     float* gW2;
     int n_chunks;
+    // block decomposition: columns [in_off, in_off + 64) of S / E (row stride d_in_full) against columns
+    // [out_off, out_off + d_out) of gM (row stride d_out_full) -> rows out_off.., columns in_off.. of gW1 / gW2
+    int d_in_full, in_off, d_out_full, out_off;
 };
 
 struct WgBars {
@@ -793,12 +811,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
         BWD_STAMP(0, 0, 0);
         tc_fence_after_sync();
         const int m = warp * 32 + lane;                                   // TMEM lane = column j of [W1 | W2]
-        float* gw = (m < d_in ? a.gW1 : a.gW2) + (m & 63);
+        float* gw = (m < d_in ? a.gW1 : a.gW2) + (int64_t)a.out_off * a.d_in_full + a.in_off + (m & 63);
         for (int c = 0; c < KBo; ++c) {
             float v[32];
             tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + c * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(gw + (int64_t)(c * 32 + j) * d_in, v[j]);
+            for (int j = 0; j < 32; ++j) atomicAdd(gw + (int64_t)(c * 32 + j) * a.d_in_full, v[j]);
         }
         BWD_STAMP(0, 0, 1);
     } else if (warp == TC_EPI_WARPS) {
@@ -851,9 +869,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
                 const int64_t row = row0 + r;
                 h.s[q2] = h.e[q2] = h.g[q2] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row < a.n_rows) {
-                    h.s[q2] = ld_stream_f4(a.S + row * d_in + c * 4);
-                    h.e[q2] = ld_stream_f4(a.E + row * d_in + c * 4);
-                    if (c < gq) h.g[q2] = ld_stream_f4(a.gM + row * d_out + c * 4);
+                    h.s[q2] = ld_stream_f4(a.S + row * a.d_in_full + a.in_off + c * 4);
+                    h.e[q2] = ld_stream_f4(a.E + row * a.d_in_full + a.in_off + c * 4);
+                    if (c < gq) h.g[q2] = ld_stream_f4(a.gM + row * a.d_out_full + a.out_off + c * 4);
                 }
             }
         };
@@ -958,20 +976,27 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     return NGCF_OK;
 }
 
-bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out) { return d_in == 64 && (d_out == 32 || d_out == 64); }
+// d_in = 64 with d_out in {32, 64} is one block; 128-wide sides are decomposed into 64-wide blocks of the same kernels:
+// T = gM·[W1|W2] is linear in gM, so the d_out halves accumulate into gS / gEl in place; the weight-gradient blocks are
+// independent.  A blocked d_out needs the output-row gradients already normalize-backwarded (gh_normalized): the
+// in-kernel version needs the norm of the whole E_out row.
+bool ngcf_dense_bwd_tc_eligible(int d_in, int d_out, int gh_normalized) {
+    if (d_in == 64 && (d_out == 32 || d_out == 64)) return true;
+    return (d_in == 64 || d_in == 128) && (d_out == 64 || d_out == 128) && (d_out <= 64 || gh_normalized);
+}
 
 int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                       const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                       const float* W1, const float* W2, float slope, const float* mess_mult, const uint32_t* mess_bits,
-                      float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, int gh_normalized,
-                      float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2, float* gM_scratch,
-                      cudaStream_t st) {
-    BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, d_in, d_out, W1, W2, slope, mess_mult,
-                mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, (int)ceil_div64(n_rows, TC_ROWS),
-                row_offset};
-    const int KBo = d_out / 32;
+                      float mess_p, uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset,
+                      int gh_normalized, float* gS, float* gEl, float* gW1, float* gb1, float* gW2, float* gb2,
+                      float* gM_scratch, cudaStream_t st) {
+    const int bn = d_out > 64 ? 64 : d_out;                               // block width on the d_out side
+    const int IH = d_in / 64, OH = d_out / bn;
+    const int KBo = bn / 32;
+    const int n_tiles = (int)ceil_div64(n_rows, TC_ROWS);
     const size_t smem = 1024 + (size_t)4 * KBo * TC_A_BLOCK + 2 * TC_ROWS * 256 + sizeof(BwdBars);
-    const int grid = (int)min((int64_t)a.n_tiles, (int64_t)ngcf_num_sms());
+    const int grid = (int)min((int64_t)n_tiles, (int64_t)ngcf_num_sms());
     void (*kern)(BwdTcArgs) = nullptr;
     const bool pre = gh_normalized != 0;
     switch (mess_mode(mess_mult, mess_bits, mess_p)) {
@@ -986,14 +1011,24 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
         NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    NGCF_CUDA(ngcf_launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, st, a));
-    NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
-
-    WgradArgs w{S, E, gM_scratch, n_rows, d_out, gW1, gW2, (int)ceil_div64(n_rows, WG_ROWS)};
+    for (int ih = 0; ih < IH; ++ih)
+        for (int oh = 0; oh < OH; ++oh) {
+            BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, 64, bn, W1, W2, slope, mess_mult,
+                        mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, n_tiles, row_offset};
+            a.d_out_full = d_out; a.out_off = oh * bn; a.d_in_full = d_in; a.in_off = ih * 64;
+            a.accumulate = oh > 0; a.first_in = ih == 0;
+            NGCF_CUDA(ngcf_launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, st, a));
+            NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
+        }
+    const int n_chunks = (int)ceil_div64(n_rows, WG_ROWS);
     const size_t smem2 = 1024 + (size_t)2 * (8 + 2 * KBo) * WG_BLOCK + sizeof(WgBars);
-    const int grid2 = (int)min((int64_t)w.n_chunks, (int64_t)ngcf_num_sms());
-    NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, st, w));
-    NGCF_LAUNCH_OK("wgrad_tc_kernel");
+    const int grid2 = (int)min((int64_t)n_chunks, (int64_t)ngcf_num_sms());
+    for (int ih = 0; ih < IH; ++ih)
+        for (int oh = 0; oh < OH; ++oh) {
+            WgradArgs w{S, E, gM_scratch, n_rows, bn, gW1, gW2, n_chunks, d_in, ih * 64, d_out, oh * bn};
+            NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, st, w));
+            NGCF_LAUNCH_OK("wgrad_tc_kernel");
+        }
     return NGCF_OK;
 }
 

@@ -443,7 +443,7 @@ def test_dense_forward_vs_float64(N, d_in, d_out):
 
 
 @pytest.mark.parametrize("N,d_in,d_out", [(1000, 64, 64), (128, 64, 64), (70839, 64, 64), (4321, 64, 32), (500, 65, 64),
-                                          (300, 128, 128), (257, 20, 36)])
+                                          (300, 128, 128), (5000, 128, 64), (1300, 64, 128), (257, 20, 36)])
 def test_dense_backward_vs_float64(N, d_in, d_out):
     """Row-local backward of one layer against a float64 restatement; d_in = 64 takes the
     tcgen05 kernel (both GEMMs 3xTF32, weight gradients accumulated in TMEM), other widths the FFMA kernel."""
