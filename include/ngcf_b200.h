@@ -227,8 +227,9 @@ int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_h
  *   gS[i]  = gM·W1 + (gM·W2) * E[i]      gEl[i] = gM·W1 + (gM·W2) * S[i]
  *   gW1 += gM^T (S+E)   gb1 += 2 colsum(gM)   gW2 += gM^T (S*E)   gb2 += colsum(gM)   (atomic accumulate
  *   into caller-zeroed buffers).  W1/W2 are the nn.Linear weights, [d_out, d_in] row-major.
- *   gM_scratch: optional [n_rows, d_out] scratch; when given (and d_in = 64, d_out in {32, 64}) the tcgen05 path
- *   runs: both GEMMs as 3xTF32 tensor-core products, the weight gradients accumulated in TMEM. */
+ *   gM_scratch: optional [n_rows, d_out] scratch; when given the tcgen05 path runs for d_in = 64 with d_out in
+ *   {32, 64}, and for widths 64 / 128 on either side as 64-wide blocks (a 128-wide d_out needs gh_normalized): both
+ *   GEMMs as 3xTF32 tensor-core products, the weight gradients accumulated in TMEM. */
 int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,
