@@ -684,3 +684,31 @@ def test_graphed_training_iteration_with_adam_tracks_torch_adam():
     assert abs(float(loss_g) - float(loss)) <= 1e-4 * abs(float(loss))
     for (k, a), (_, c) in zip(models[0].named_parameters(), models[1].named_parameters()):
         assert rel_err(c.detach().cpu().numpy(), a.detach().cpu().numpy()) <= 1e-4, k
+
+
+def test_edge_cases_empty_graph_single_row_batch_and_repeated_users():
+    """Degenerate inputs the reference handles without special code: a Laplacian without any entry (L·E = 0), a
+    one-row batch, a batch that repeats one user (the last duplicate's feature mix wins, rows gathered twice)."""
+    n_user, n_item = 37, 23
+    N = n_user + n_item
+    nd = synth.num_dict_for(n_user, n_item)
+    empty = torch.sparse_coo_tensor(torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0), (N, N))
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, 300, seed=1)
+    L = laplacian.laplacian_coo(u, i, r, n_user, n_item)
+    for lap, B, rep in ((empty, 4, False), (L, 1, False), (L, 6, True)):
+        torch.manual_seed(0)
+        m = pkg.NGCF(64, [64, 64], 0.0, [0.0, 0.0], 1.0, [lap, lap], nd, B, torch.device("cpu"))
+        params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m = m.to(DEV).eval()
+        b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=2).items()}
+        if rep:
+            b["u_id"][:] = b["u_id"][0]
+        want_loss, want_grads, mid = O.train_step(params, lap, b, emb_ratio=1.0, weight_decay=0.025, batch_size_ctor=B)
+        uu, pp, nn_ = _call(m, b, False)
+        loss = pkg.BPR(0.025, B)(uu, pp, nn_)
+        loss.backward()
+        assert rel_err(uu.detach().cpu().numpy(), mid["u"].numpy()) <= TOL
+        assert abs(float(loss) - float(want_loss)) <= TOL * abs(float(want_loss))
+        for k, g in want_grads.items():
+            if g is not None:
+                assert rel_err(dict(m.named_parameters())[k].grad.cpu().numpy(), g.numpy()) <= TOL, (k, B, rep)
