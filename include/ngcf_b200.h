@@ -240,7 +240,7 @@ int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum,
 /* ---- scoring: demo.py:234-235, experiment.py:93,104,109 ----------------------------------------------
  * scores = U·I^T without materialising them; per user row the k largest (descending; ties by lower item
  * id).  k <= 128.  workspace: ngcf_score_topk_workspace bytes. */
-int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int k, size_t* bytes_host);
+int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int D, int k, size_t* bytes_host);
 int ngcf_score_topk(const float* U, int64_t n_users, const float* I, int64_t n_items, int D, int k,
                     float* out_val /*[n_users,k]*/, int64_t* out_idx /*[n_users,k]*/,
                     void* workspace, size_t workspace_bytes, void* stream);

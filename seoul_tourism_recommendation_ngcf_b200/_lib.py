@@ -63,7 +63,7 @@ SIGNATURES = {
     "ngcf_debug_bwd_timeline": [C.c_int, _vp],
     "ngcf_debug_spmm_timeline": [_vp],
     "ngcf_debug_compact_timeline": [_vp],
-    "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.POINTER(_sz)],
+    "ngcf_score_topk_workspace": [_i64, _i64, C.c_int, C.c_int, C.POINTER(_sz)],
     "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],
 }
 

@@ -90,13 +90,13 @@ score_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int
     const int user = blockIdx.x, lane = threadIdx.x;
     const float* v = pv + (int64_t)user * n_split * k;
     const int* ix = pi + (int64_t)user * n_split * k;
-    for (int j = lane; j < k; j += 32) { lv[j] = v[j]; li[j] = ix[j]; }
+    for (int j = lane; j < k; j += 32) { lv[j] = -FLT_MAX; li[j] = 0x7fffffff; }
     __syncwarp();
-    for (int sp = 1; sp < n_split; ++sp)
+    for (int sp = 0; sp < n_split; ++sp)                               // partial lists need not be sorted
         for (int j = 0; j < k; ++j) {
             const float s = v[sp * k + j];
             const int id = ix[sp * k + j];
-            if (id == 0x7fffffff) break;
+            if (id == 0x7fffffff) continue;
             warp_insert(lv, li, k, s, id, lane);
         }
     for (int j = lane; j < k; j += 32) {
@@ -117,11 +117,20 @@ int pick_split(int64_t n_users, int64_t n_items) {
 
 }  // namespace
 
-extern "C" int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int k, size_t* bytes_host) {
+bool ngcf_score_topk_tc_eligible(int64_t n_users, int64_t n_items, int D, int k);
+int ngcf_score_topk_tc_splits(int64_t n_users, int64_t n_items);
+size_t ngcf_score_topk_tc_pack_bytes(int64_t n_users, int64_t n_items, int D);
+int ngcf_score_topk_tc(const float* U, int64_t n_users, const float* I, int64_t n_items, int D, int k, int n_split,
+                       float* pv, int* pi, uint8_t* pack, cudaStream_t st);
+bool ngcf_use_tensor_cores();
+
+extern "C" int ngcf_score_topk_workspace(int64_t n_users, int64_t n_items, int D, int k, size_t* bytes_host) {
     NGCF_REQUIRE(bytes_host, "score_topk_workspace: null pointer");
     NGCF_REQUIRE(n_users >= 0 && n_items >= 0 && k > 0 && k <= TK_MAXK, "score_topk_workspace: bad sizes");
-    const int ns = pick_split(n_users > 0 ? n_users : 1, n_items);
-    *bytes_host = (size_t)(n_users > 0 ? n_users : 1) * ns * k * 8 + 256;
+    const int64_t nu = n_users > 0 ? n_users : 1;
+    const int ns = max(pick_split(nu, n_items), ngcf_score_topk_tc_splits(nu, n_items));   // either kernel fits
+    *bytes_host = (size_t)nu * ns * k * 8 + 256;
+    if (D > 0 && ngcf_score_topk_tc_eligible(nu, n_items, D, k)) *bytes_host += ngcf_score_topk_tc_pack_bytes(nu, n_items, D);
     return NGCF_OK;
 }
 
@@ -134,16 +143,28 @@ extern "C" int ngcf_score_topk(const float* U, int64_t n_users, const float* I, 
     NGCF_REQUIRE(D > 0 && n_users >= 0 && n_users < 65536 * 32768LL, "score_topk: bad sizes");
     if (n_users == 0) return NGCF_OK;
     size_t need = 0;
-    int rc = ngcf_score_topk_workspace(n_users, n_items, k, &need);
+    int rc = ngcf_score_topk_workspace(n_users, n_items, D, k, &need);
     if (rc != NGCF_OK) return rc;
     if (!workspace || workspace_bytes < need) {
         ngcf_set_error("score_topk: workspace %zu bytes < required %zu", workspace_bytes, need);
         return NGCF_ERR_WORKSPACE;
     }
+    cudaStream_t st = as_stream(stream);
+    if (ngcf_use_tensor_cores() && ngcf_score_topk_tc_eligible(n_users, n_items, D, k) &&
+        (reinterpret_cast<uintptr_t>(U) & 15) == 0 && (reinterpret_cast<uintptr_t>(I) & 15) == 0) {
+        // GEMM-shaped path on the tensor cores (topk_tc.cu); partial lists per item range, merged below
+        const int ns = ngcf_score_topk_tc_splits(n_users, n_items);
+        float* pv = reinterpret_cast<float*>(workspace);
+        int* pi = reinterpret_cast<int*>(pv + (size_t)n_users * ns * k);
+        uint8_t* pack = reinterpret_cast<uint8_t*>(pi + (size_t)n_users * ns * k);
+        if ((rc = ngcf_score_topk_tc(U, n_users, I, n_items, D, k, ns, pv, pi, pack, st)) != NGCF_OK) return rc;
+        score_merge_kernel<<<(unsigned)n_users, 32, sizeof(float) * 2 * k, st>>>(pv, pi, ns, k, out_val, out_idx);
+        NGCF_LAUNCH_OK("score_merge_kernel");
+        return NGCF_OK;
+    }
     const int ns = pick_split(n_users, n_items);
     float* pv = reinterpret_cast<float*>(workspace);
     int* pi = reinterpret_cast<int*>(pv + (size_t)n_users * ns * k);
-    cudaStream_t st = as_stream(stream);
     const size_t smem1 = sizeof(float) * (((D + 3) & ~3) + 2 * TK_WARPS * k);
     NGCF_REQUIRE(smem1 <= 48 * 1024, "score_topk: D %d too wide for the v1 kernel", D);
     NGCF_REQUIRE(n_users <= 0x7fffffffLL, "score_topk: too many users");

@@ -23,7 +23,7 @@ def score_topk(u_embeds: torch.Tensor, item_embeds: torch.Tensor, k: int):
     if k > n_items:
         raise RuntimeError("selected index k out of range")          # what torch.topk raises
     need = C.c_size_t(0)
-    _lib.check(lib.ngcf_score_topk_workspace(U, n_items, k, C.byref(need)), "score_topk_workspace")
+    _lib.check(lib.ngcf_score_topk_workspace(U, n_items, D, k, C.byref(need)), "score_topk_workspace")
     ws = torch.empty(need.value, dtype=torch.uint8, device=u.device)
     val = torch.empty(U, k, dtype=torch.float32, device=u.device)
     idx = torch.empty(U, k, dtype=torch.int64, device=u.device)

@@ -35,7 +35,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.ngcf_spmm_split_threshold() > 0
     # argument validation happens before any CUDA call
     need = ctypes.c_size_t(0)
-    assert lib.ngcf_score_topk_workspace(4, 10, 0, ctypes.byref(need)) != 0
+    assert lib.ngcf_score_topk_workspace(4, 10, 64, 0, ctypes.byref(need)) != 0
     assert b"score_topk_workspace" in lib.ngcf_last_error()
 
 
