@@ -5,12 +5,13 @@
 // a persistent CTA owns a 128-user tile and a range of 128-item tiles.  A pre-pass (score_pack_kernel) splits U and I
 // once into TF32 hi / lo planes stored as ready-made operand blocks — per (128-row tile, 32-column K block) one
 // 32-KB image of the 128-byte-swizzled K-major UMMA layout — so the GEMM's producer is ONE thread issuing two 32-KB
-// cp.async.bulk (TMA) copies per K step into a 3-stage ring (first version: 8 loader warps re-split both operands for
+// cp.async.bulk (TMA) copies per K step into a 2-stage ring (first version: 8 loader warps re-split both operands for
 // every tile pair and bounded the kernel at ~26 us per tile against 3.4 us of tensor work); one thread issues the 3xTF32
 // tcgen05.mma chain into a double-buffered 128 x 128 fp32 accumulator in TMEM, and the epilogue threads (TMEM lane = user) filter the 128 scores of their user
 // against that user's current k-th best and put the few survivors into that user's list in shared memory.  The score
 // matrix never exists; partial lists per (user, item range) are merged by score_merge_kernel (topk.cu).
 #include <float.h>
+#include <stdlib.h>
 
 #include "tc.cuh"
 
@@ -21,7 +22,8 @@ using namespace tc;
 constexpr int ST_ROWS = 128;                   // users per tile (UMMA M) and items per tile (UMMA N)
 constexpr int ST_EPI_WARPS = 4;
 constexpr int ST_THREADS = (ST_EPI_WARPS + 2) * 32;                       // + MMA warp + producer warp
-constexpr int ST_STAGES = 3;
+constexpr int ST_STAGES = 2;
+constexpr int ST_EXTRA = 64;                    // appended-but-not-yet-merged entries a user's list can hold
 constexpr int ST_BLOCK = ST_ROWS * 128;        // bytes of one 32-column K block of A or B (hi or lo)
 constexpr int ST_STAGE_BYTES = 4 * ST_BLOCK;   // A hi, A lo, B hi, B lo
 constexpr int ST_MAXK = 32;
@@ -34,6 +36,7 @@ struct ScoreTcArgs {
     int tiles_per_split;       // item tiles per split
     float* pv;                 // [n_users][n_split][k]
     int* pi;
+    int dbg_skip_epilogue;     // timing experiments only (NGCF_B200_TOPK_SKIP_EPI=1): accumulators are read and dropped
 };
 
 struct ScoreBars {
@@ -46,9 +49,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) score_topk_tc_kernel(ScoreTcArg
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* ring = smem;                                                 // [ST_STAGES][A hi | A lo | B hi | B lo]
-    float* lv = reinterpret_cast<float*>(ring + ST_STAGES * ST_STAGE_BYTES);   // [k][128]: user lists, k-major
-    int* li = reinterpret_cast<int*>(lv + a.k * ST_ROWS);
-    ScoreBars* bars = reinterpret_cast<ScoreBars*>(li + a.k * ST_ROWS);
+    float* lv = reinterpret_cast<float*>(ring + ST_STAGES * ST_STAGE_BYTES);   // [k + ST_EXTRA][128]: user lists, slot-major
+    const int cap = a.k + ST_EXTRA;
+    int* li = reinterpret_cast<int*>(lv + cap * ST_ROWS);
+    ScoreBars* bars = reinterpret_cast<ScoreBars*>(li + cap * ST_ROWS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ut = blockIdx.x, sp = blockIdx.y;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) score_topk_tc_kernel(ScoreTcArg
         fence_mbar_init();
     }
     if (warp == ST_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // 2 accumulators x 128 fp32 columns
-    for (int i = tid; i < a.k * ST_ROWS; i += ST_THREADS) { lv[i] = -FLT_MAX; li[i] = 0x7fffffff; }
+    for (int i = tid; i < a.k * ST_ROWS; i += ST_THREADS) { lv[i] = -FLT_MAX; li[i] = 0x7fffffff; }   // the k kept slots
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -78,14 +82,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) score_topk_tc_kernel(ScoreTcArg
 
     if (warp < ST_EPI_WARPS) {
         // ======================= epilogue: per-user top-k ==========================================================
-        // The list is UNSORTED with a tracked minimum: a survivor overwrites the slot of the current minimum and the
-        // k entries are rescanned for the new one (uniform trip count).  A sorted insertion loop made every event cost
-        // the longest shift among the warp's 32 independent users: 150 k cycles per 128-item tile while the lists warm up.
+        // Slots [0, k) hold the user's k best so far (unsorted), slots [k, k + ST_EXTRA) collect survivors of the filter
+        // "score > k-th best as of the last merge" with two stores each.  When any user of the warp runs short of room
+        // all 32 merge together (per extra entry: scan the k kept slots for the weakest, replace it if beaten), so the
+        // cost of a merge is paid once per warp, not once per user.  (First version: every survivor was merged at once —
+        // 32 independent users per warp made nearly every score column an event: 11 of the kernel's 14 ms.)
         const int row = warp * 32 + lane;                                 // TMEM lane = user row of the tile
-        const bool live = u0 + row < a.n_users;
+        const bool live = u0 + row < a.n_users && !a.dbg_skip_epilogue;
         const int k = a.k;
-        float thr = -FLT_MAX;                                             // value of the user's weakest kept entry
-        int amin = 0;                                                     // ... and its slot
+        float thr = -FLT_MAX;                                             // k-th best as of the last merge
+        int cnt = k;                                                      // next free slot
+        auto merge = [&]() {
+            const int extras = __reduce_max_sync(FULL_MASK, cnt) - k;
+            for (int x = 0; x < extras; ++x) {
+                const bool has = k + x < cnt;
+                const float s = has ? lv[(k + x) * ST_ROWS + row] : -FLT_MAX;
+                const int id = has ? li[(k + x) * ST_ROWS + row] : 0x7fffffff;
+                float mv = lv[row];
+                int mi = li[row], mp = 0;
+#pragma unroll 4
+                for (int p = 1; p < k; ++p) {                             // weakest kept entry: lowest score, then highest id
+                    const float pv_ = lv[p * ST_ROWS + row];
+                    const int pi_ = li[p * ST_ROWS + row];
+                    if (pv_ < mv || (pv_ == mv && pi_ > mi)) { mv = pv_; mi = pi_; mp = p; }
+                }
+                if (has && s > mv) {                                      // (an equal score keeps the earlier item)
+                    lv[mp * ST_ROWS + row] = s;
+                    li[mp * ST_ROWS + row] = id;
+                }
+            }
+            float mv = lv[row];
+            for (int p = 1; p < k; ++p) mv = fminf(mv, lv[p * ST_ROWS + row]);
+            thr = mv;
+            cnt = k;
+        };
         for (int it = 0; it < n_t; ++it) {
             const int buf = it & 1;
             const int64_t i0 = (int64_t)(t0 + it) * ST_ROWS;
@@ -100,30 +130,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) score_topk_tc_kernel(ScoreTcArg
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
                 }
+                if (__any_sync(FULL_MASK, cnt > k + ST_EXTRA - 32)) merge();   // room for a whole chunk of survivors
                 if (!live) continue;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float s = v[j];
                     const int64_t item = i0 + c * 32 + j;
-                    // items arrive in increasing order: an equal score never displaces an earlier one (ties go to the
-                    // lower item id, like the merge); NaN fails the comparison and is never ranked
+                    // NaN fails the comparison and is never ranked
                     if (s > thr && item < a.n_items) {
-                        lv[amin * ST_ROWS + row] = s;
-                        li[amin * ST_ROWS + row] = (int)item;
-                        float mv = lv[row];
-                        int mi = li[row], mp = 0;
-#pragma unroll 4
-                        for (int p = 1; p < k; ++p) {                     // weakest entry: lowest score, then highest id
-                            const float pv_ = lv[p * ST_ROWS + row];
-                            const int pi_ = li[p * ST_ROWS + row];
-                            if (pv_ < mv || (pv_ == mv && pi_ > mi)) { mv = pv_; mi = pi_; mp = p; }
-                        }
-                        thr = mv;
-                        amin = mp;
+                        lv[cnt * ST_ROWS + row] = s;
+                        li[cnt * ST_ROWS + row] = (int)item;
+                        ++cnt;
                     }
                 }
             }
         }
+        merge();
         if (live) {
             float* ov = a.pv + ((u0 + row) * a.n_split + sp) * k;
             int* oi = a.pi + ((u0 + row) * a.n_split + sp) * k;
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(256) score_pack_kernel(const float* __restrict
 }  // namespace
 
 bool ngcf_score_topk_tc_eligible(int64_t n_users, int64_t n_items, int D, int k) {
-    return n_users >= 32 && n_items >= 128 && D % 4 == 0 && D >= 32 && k <= ST_MAXK;
+    return n_users >= 1 && n_items >= 1024 && D % 4 == 0 && D >= 32 && k <= ST_MAXK;
 }
 
 // item splits so that user tiles x splits covers the SMs a few times over
@@ -248,8 +270,10 @@ int ngcf_score_topk_tc(const float* U, int64_t n_users, const float* I, int64_t 
         score_pack_kernel<<<(unsigned)ceil_div64(ci, 256), 256, 0, st>>>(I, n_items, D, KB, Ip, ci);
         NGCF_LAUNCH_OK("score_pack_kernel(I)");
     }
-    ScoreTcArgs a{Up, Ip, n_users, n_items, D, k, n_split, (int)((itiles + n_split - 1) / n_split), pv, pi};
-    const size_t smem = 1024 + (size_t)ST_STAGES * ST_STAGE_BYTES + (size_t)k * ST_ROWS * 8 + sizeof(ScoreBars);
+    static int skip = -1;
+    if (skip < 0) { const char* e = getenv("NGCF_B200_TOPK_SKIP_EPI"); skip = (e && e[0] == '1') ? 1 : 0; }
+    ScoreTcArgs a{Up, Ip, n_users, n_items, D, k, n_split, (int)((itiles + n_split - 1) / n_split), pv, pi, skip};
+    const size_t smem = 1024 + (size_t)ST_STAGES * ST_STAGE_BYTES + (size_t)(k + ST_EXTRA) * ST_ROWS * 8 + sizeof(ScoreBars);
     static bool attr_set = false;
     if (!attr_set) {
         NGCF_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

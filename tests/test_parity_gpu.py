@@ -214,7 +214,7 @@ def test_feature_mix_last_duplicate_wins():
 
 
 @pytest.mark.parametrize("U,I,D,k", [(3, 100, 257, 100), (37, 5000, 256, 20), (1, 129, 65, 128), (200, 300, 640, 7),
-                                     (1000, 20011, 256, 20), (129, 257, 96, 32), (300, 4000, 256, 33)])
+                                     (1000, 20011, 256, 20), (129, 1300, 96, 32), (300, 4000, 256, 33), (5, 3000, 64, 20)])
 def test_score_topk_vs_torch(U, I, D, k):
     gen = torch.Generator().manual_seed(U * 7 + k)
     u = torch.randn(U, D, generator=gen)
