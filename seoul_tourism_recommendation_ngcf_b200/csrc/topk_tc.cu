@@ -245,7 +245,7 @@ int ngcf_score_topk_tc_splits(int64_t n_users, int64_t n_items) {
     const int64_t ut = (n_users + ST_ROWS - 1) / ST_ROWS, itiles = (n_items + ST_ROWS - 1) / ST_ROWS;
     int64_t s = (int64_t)ngcf_num_sms() / ut;                            // one wave of CTAs; long item ranges amortise
     if (s > itiles) s = itiles;                                           // the warm-up of the per-user lists
-    if (s > 64) s = 64;
+    if (s > 32) s = 32;                                                   // the per-user merge of the partial lists is serial
     if (s < 1) s = 1;
     return (int)s;
 }
