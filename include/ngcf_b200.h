@@ -257,6 +257,35 @@ int ngcf_adam_step(float* const* params_host, float* const* grads_host, float* c
                    double beta2, double eps, double weight_decay, int64_t step, const int64_t* step_dev,
                    int zero_grads, void* stream);
 
+/* ---- evaluation metrics: the per-batch block of Experiment.eval, experiment.py:92-116, for all test groups at once
+ * (SURVEY.md section 8(f) #4).  Rows g*group .. g*group+group-1 (group_ptr == NULL) or group_ptr[g] .. group_ptr[g+1]-1
+ * (ragged batches, e.g. a DataLoader without drop_last; then `group` = the smallest group size, which the k's are
+ * checked against, and every size must lie in [2, 128]) of u / items are what NGCF.forward returned for test
+ * batch g (u_embeds, pos_i_embeds: row 0 the positive, rows 1.. the sampled negatives); item_ids / rating are the
+ * batch's pos_item / rating columns (rating read at row 0 of each group).  Per group:
+ *   scores[b] = u[0].items[b]                                   (pred_ratings[0], :93)
+ *   bpr  = BPR(weight_decay, batch_size_ctor)(u, items[:1], cat(items[1:], items[1:2]))      (:95-101, bprloss.py:15-22)
+ *   hit  = item_ids[0] among the ids of the k_hr best scores    (:104-106; the reference uses 3)
+ *   ndcg = 1/log2(pos+2) if its position pos < k_ndcg else 0     (:109-111, :120-126)
+ *   rmse = |scores[0] - rating[0]|                               (:114-116)
+ * bpr/hit/ndcg/rmse: [n_groups] outputs; scores: optional [n_groups*group]; totals: optional float[4] =
+ * {sum(bpr)/G, mean(hit), mean(ndcg), sum(rmse)/G}, the tuple eval() returns (:119).  2 <= group <= 128. */
+int ngcf_eval_groups(const float* u, const float* items, const int64_t* item_ids, const float* rating,
+                     const int64_t* group_ptr, int64_t n_groups, int group, int D, int k_hr, int k_ndcg, float weight_decay,
+                     float batch_size_ctor, float* bpr, float* hit, float* ndcg, float* rmse, float* scores,
+                     float* totals, void* stream);
+
+/* ---- triple sampler: TourDataset._negative_sampling, utils.py:213-275 --------------------
+ * For positive row r of user row_user[r]: out[r, 0..ng_ratio) = ng_ratio DISTINCT candidates the user has no positive
+ * feedback for, an ordered uniform sample without replacement (np.random.choice(neg_items, ng_ratio, replace=False),
+ * utils.py:258).  candidates: the sorted unique item ids (np.setxor1d's universe, utils.py:224,240);
+ * pos_ptr [n_user+1] / pos_idx: per user the ascending unique candidate INDICES of the positives.  Counter-based RNG
+ * keyed on (seed, r, draw): reproducible, order-independent, not numpy's MT19937 stream.  *n_short counts rows
+ * with fewer than ng_ratio free candidates (numpy raises there; their outputs are -1); caller zeroes it. */
+int ngcf_sample_negatives(const int32_t* pos_ptr, const int32_t* pos_idx, const int64_t* row_user, int64_t n_rows,
+                          const int64_t* candidates, int n_candidates, int ng_ratio, uint64_t seed, int64_t* out,
+                          int32_t* n_short, void* stream);
+
 /* ---- debugging aids (tools/bwd_timeline.py, fwd_timeline.py, spmm_timeline.py); not part of the product path --------
  * ngcf_debug_bwd_timeline: switches the in-kernel SM-clock stamps of CTA 0 of the tcgen05 dense kernels on/off and
  * copies them back (out_host: int64[4*8*8] or NULL).  ngcf_debug_spmm_timeline: device buffer uint64[n_ctas*4]

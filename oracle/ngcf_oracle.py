@@ -251,6 +251,91 @@ def train_step(params: dict, L, batch: dict, *, emb_ratio, weight_decay, batch_s
 
 
 # --------------------------------------------------------------------------------------------
+# evaluation loop and metrics  (experiment.py:66-130)
+# --------------------------------------------------------------------------------------------
+def forward_eval(params: dict, lap_list, batch: dict, *, emb_ratio):
+    """One eval-style forward (experiment.py:82-91): node_flag=False, eval mode, neg_item=torch.empty(0).
+    ``params['user_embedding.weight']`` is mutated in place by the feature mix, as in the reference."""
+    K = sum(1 for k in params if k.startswith("w1_list.") and k.endswith(".weight"))
+    n_user = params["user_embedding.weight"].shape[0]
+    with torch.no_grad():
+        tables = {"age": params["age_emb.weight"], "sex": params["sex_emb.weight"], "month": params["month_emb.weight"],
+                  "day": params["day_emb.weight"], "dow": params["dow_emb.weight"]}
+        feature_mix_(params["user_embedding.weight"], tables, {k: batch[k] for k in FEATURE_ORDER}, batch["u_id"],
+                     emb_ratio)
+        L = lap_list[select_year(batch["year"])]
+        E0 = torch.cat((params["user_embedding.weight"], params["item_embedding.weight"]), dim=0)
+        out = propagate(L, E0, [params[f"w1_list.{k}.weight"] for k in range(K)],
+                        [params[f"w1_list.{k}.bias"] for k in range(K)],
+                        [params[f"w2_list.{k}.weight"] for k in range(K)],
+                        [params[f"w2_list.{k}.bias"] for k in range(K)])
+        u, p, _ = gather_outputs(out["all_E"], n_user, batch["u_id"], batch["pos_item"], torch.empty(0))
+    return u, p
+
+
+def eval_group_metrics(u, pos_emb, pos_item, rating, weight_decay: float, test_batch: int, ks: int):
+    """The metric block of one test batch, experiment.py:92-116.  Returns (bpr, hit, ndcg, rmse, scores)."""
+    gt = int(pos_item[0])                                                      # :92
+    pred = torch.mm(u, pos_emb.T)                                              # :93
+    neg = pos_emb[1:]                                                          # :96
+    neg = torch.cat((neg, neg[:1]))                                            # :97
+    bpr = bpr_loss(u, pos_emb[:1], neg, weight_decay, test_batch)              # :98-100
+    _, rank = torch.topk(pred[0], 3)                                           # :104
+    rec = torch.take(pos_item, rank).tolist()                                  # :105
+    hit = 1 if gt in rec else 0                                                # :106, :127-130
+    _, rank = torch.topk(pred[0], ks)                                          # :109
+    rec = torch.take(pos_item, rank).tolist()                                  # :110
+    ndcg = float(np.reciprocal(np.log2(rec.index(gt) + 2))) if gt in rec else 0.0   # :111, :120-126
+    rmse = torch.sqrt(F.mse_loss(pred[0, 0], rating[0].to(pred.dtype)))        # :114-116, :133-141
+    return bpr, hit, ndcg, rmse, pred[0]
+
+
+def eval_epoch(params: dict, lap_list, test_batches, *, emb_ratio, weight_decay, test_batch, ks):
+    """Experiment.eval, experiment.py:66-119: one full-graph forward PER test batch (each one overwrites its
+    users' table rows), metrics accumulated the reference's way.  Returns (BPR, HR, NDCG, RMSE) and per-batch lists."""
+    params = {k: v.detach().clone() for k, v in params.items()}
+    BPR, RMSE, HR, NDCG, per = 0, 0, [], [], []
+    for b in test_batches:
+        u, p = forward_eval(params, lap_list, b, emb_ratio=emb_ratio)
+        bpr, hit, ndcg, rmse, sc = eval_group_metrics(u, p, b["pos_item"], b["rating"], weight_decay, test_batch, ks)
+        BPR += bpr; RMSE += rmse; HR.append(hit); NDCG.append(ndcg)
+        per.append(dict(bpr=float(bpr), hit=hit, ndcg=ndcg, rmse=float(rmse), scores=sc.numpy().copy()))
+    n = len(test_batches)
+    return (float(BPR / n), float(np.mean(HR)), float(np.mean(NDCG)), float(RMSE / n)), per, params
+
+
+# --------------------------------------------------------------------------------------------
+# triple sampler  (utils.py:213-275)
+# --------------------------------------------------------------------------------------------
+def negative_sampling(cols: dict, total_items, train: bool, rng=np.random):
+    """TourDataset._negative_sampling restated over plain arrays (``cols``: the frame's columns year, userid, age,
+    sex, month, day, dayofweek, rating, itemid as 1-D arrays in frame order).  Same loop order and the same
+    ``rng.choice(neg, ng_ratio, replace=False)`` call per positive row, so with the same numpy seed it returns what
+    the reference returns.  -> (users int64 [R, 7|8], items int64 [R, 2] | [R*25])."""
+    all_dest = np.unique(np.asarray(total_items))                              # utils.py:224 (set semantics)
+    ng_ratio = 1 if train else 24                                              # utils.py:227-230
+    users_list, items_list = [], []
+    uid = np.asarray(cols["userid"])
+    _, first = np.unique(uid, return_index=True)
+    for user in uid[np.sort(first)]:                                           # df['userid'].unique(): first-seen order
+        rows = np.flatnonzero(uid == user)
+        rows = rows[np.asarray(cols["rating"])[rows] > 0]                      # utils.py:238
+        neg_items = np.setxor1d(all_dest, np.asarray(cols["itemid"])[rows])    # utils.py:240
+        for r in rows:
+            ctx = [cols[k][r] for k in ("year", "userid", "age", "sex", "month", "day", "dayofweek")]
+            negs = rng.choice(neg_items.copy(), ng_ratio, replace=False)       # utils.py:258
+            if train:
+                items_list.append([cols["itemid"][r]] + negs.tolist())         # utils.py:253,261,268
+                users_list.append(ctx)
+            else:
+                items_list.append(cols["itemid"][r])                           # utils.py:249-250
+                users_list.append(ctx + [cols["rating"][r]])
+                items_list += negs.tolist()                                    # utils.py:263-265
+                users_list += [ctx + [cols["rating"][r]]] * ng_ratio
+    return torch.LongTensor(np.asarray(users_list)), torch.LongTensor(np.asarray(items_list))
+
+
+# --------------------------------------------------------------------------------------------
 # explicit float64 restatement, forward and hand-derived backward (SURVEY.md section 3.4)
 # --------------------------------------------------------------------------------------------
 def _csr64(L):

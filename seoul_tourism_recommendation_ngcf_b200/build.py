@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libngcf_b200.so")
-SOURCES = ["csr_misc.cu", "spmm.cu", "dense.cu", "dense_tc.cu", "bpr.cu", "topk.cu", "topk_tc.cu", "adam.cu"]
+SOURCES = ["csr_misc.cu", "spmm.cu", "dense.cu", "dense_tc.cu", "bpr.cu", "topk.cu", "topk_tc.cu", "adam.cu", "evalsample.cu"]
 
 
 def nvcc_path() -> str:

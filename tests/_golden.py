@@ -56,3 +56,28 @@ def rel_err(a, b):
         return 0.0
     den = np.abs(b).max()
     return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+EVAL_COLS = ("year", "userid", "age", "sex", "month", "day", "dayofweek")
+
+
+def eval_frame_cols(g, which):
+    """Columns of the eval_sampler golden's frames ('total' | 'test') named as oracle.negative_sampling expects."""
+    f = g.group(which)
+    cols = {c: f[c] for c in EVAL_COLS + ("itemid",)}
+    cols["rating"] = f["visitor"]
+    return cols
+
+
+def eval_test_batches(g, users=None, items=None):
+    """The reference's test DataLoader over TourDataset(train=False) (main.py:49-52: batch_size=test_batch,
+    shuffle=False, drop_last=True) as a list of dict batches."""
+    users = torch.from_numpy(g.raw["sampler/test_users"]) if users is None else users
+    items = torch.from_numpy(g.raw["sampler/test_items"]) if items is None else items
+    tb = g.cfg["test_batch"]
+    out = []
+    for s in range(0, (len(users) // tb) * tb, tb):
+        u = users[s:s + tb]
+        out.append(dict(year=u[:, 0], u_id=u[:, 1], age=u[:, 2], sex=u[:, 3], month=u[:, 4], day=u[:, 5], dow=u[:, 6],
+                        rating=u[:, 7], pos_item=items[s:s + tb]))
+    return out

@@ -22,6 +22,7 @@ REF = "/root/reference/model"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 sys.dont_write_bytecode = True
+ONLY = sys.argv[1:]          # --only-eval: regenerate just eval_sampler.npz
 sys.argv = [sys.argv[0]]
 sys.path.insert(0, REF)
 np.mat = np.asmatrix
@@ -200,10 +201,61 @@ def case_checkpoint_demo(name="ckpt_demo"):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB nnz={[int(L._nnz()) for L in lap_list]}")
 
 
+def case_eval_and_sampler(name="eval_sampler"):
+    """the reference's own TourDataset._negative_sampling (utils.py:213-275) and
+    Experiment.eval (experiment.py:66-119) on a small frame.  A user's id determines its features, as in the
+    reference's data (utils.py:70-74); ratings are integer counts so the reference's LongTensor packing is lossless."""
+    from torch.utils.data import DataLoader
+    from experiment import Experiment  # noqa: E402  (reference)
+    from utils import TourDataset  # noqa: E402  (reference)
+    n_user, n_item, emb, layers, ks, tb = 40, 60, 65, [65, 65], 10, 25
+    df = make_frame(n_user, n_item, 0.2, seed=21)
+    rng = np.random.default_rng(22)
+    df["visitor"] = np.ceil(df["visitor"] * 3).astype(np.int64)            # counts 0..9, ~25 % zeros
+    feat = {k: rng.integers(0, FEATURE_CARD[k], n_user) for k in ("age", "sex", "month", "day", "dayofweek")}
+    for k, v in feat.items():
+        df[k] = v[df["userid"].to_numpy()]
+    df = df.sample(frac=1.0, random_state=3).reset_index(drop=True)          # users first seen in shuffled order
+    test_df = df.iloc[::7].reset_index(drop=True)
+    lap_list = ref_lap_list(df[["year", "userid", "itemid", "visitor"]].astype({"visitor": np.float32}), n_user, n_item)
+    d = {f"total/{c}": df[c].to_numpy() for c in df.columns}
+    d.update({f"test/{c}": test_df[c].to_numpy() for c in test_df.columns})
+    np.random.seed(5)
+    ds_train = TourDataset(df=test_df, total_df=df, train=True, rating_col="visitor")
+    d["sampler/train_users"], d["sampler/train_items"] = ds_train.users.numpy(), ds_train.items.numpy()
+    np.random.seed(6)
+    ds_test = TourDataset(df=test_df, total_df=df, train=False, rating_col="visitor")
+    d["sampler/test_users"], d["sampler/test_items"] = ds_test.users.numpy(), ds_test.items.numpy()
+    nd = num_dict(n_user, n_item)
+    m = build_model(emb, layers, lap_list, nd, 64, 0.3, [0.1, 0.1], 1.0, seed=9)
+    d.update(pack_lap("lap", lap_list))
+    for k, v in m.state_dict().items():
+        d["p/" + k] = v.detach().numpy().copy()
+    loader = DataLoader(dataset=ds_test, batch_size=tb, shuffle=False, drop_last=True)      # main.py:49-52
+    exp = Experiment(model=m, optimizer=None, criterion=None, test_criterion=BPR(weight_decay=0.025, batch_size=tb),
+                     train_dataloader=None, test_dataloader=loader, epochs=1, ks=ks, device=torch.device("cpu"))
+    bpr, hr, ndcg, rmse = exp.eval()
+    d["out/metrics"] = np.array([float(bpr), float(hr), float(ndcg), float(rmse)], dtype=np.float64)
+    d["out/user_after"] = m.user_embedding.weight.detach().numpy().copy()
+    # a second pass over the now fully feature-mixed table (emb_ratio = 1 makes the mix idempotent): this is the state
+    # in which one propagation for ALL groups equals the reference's per-batch loop
+    bpr, hr, ndcg, rmse = exp.eval()
+    d["out/metrics_pass2"] = np.array([float(bpr), float(hr), float(ndcg), float(rmse)], dtype=np.float64)
+    d["cfg"] = np.array(repr(dict(n_user=n_user, n_item=n_item, emb=emb, layers=layers, ks=ks, test_batch=tb, wd=0.025,
+                                  emb_ratio=1.0, B=64, node_p=0.3, mess_p=[0.1, 0.1], seed_train=5, seed_test=6)))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB  groups={len(loader)} metrics={d['out/metrics']} "
+          f"pass2={d['out/metrics_pass2']}")
+
+
 if __name__ == "__main__":
     # one thread: torch's CPU index_put_ with duplicate user ids (NGCF.py:114) is only deterministic
     # (last write wins) single-threaded; everything else on this path is thread-count independent
     torch.set_num_threads(1)
+    if "--only-eval" in ONLY:
+        case_eval_and_sampler()
+        sys.exit(0)
     # 1. the reference's own shape family: emb 65, two layers [65,65] (saved_data_layer2), eval mode
     case_matrix_and_step("seoul_small", 48, 10, 0.6, 65, [65, 65], 16, graph_seed=1, model_seed=0, batch_seed=1,
                          year=19)
@@ -225,3 +277,5 @@ if __name__ == "__main__":
                          batch_seed=6, neg_empty=True)
     # 7. real checkpoint, demo-mode scoring + full ranking
     case_checkpoint_demo()
+    # 8. the callers either side of the path: reference sampler + Experiment.eval
+    case_eval_and_sampler()

@@ -1,0 +1,213 @@
+"""GPU parity of SURVEY.md section 8(f) #3/#4 through the C ABI: the fused evaluation-metric launch and the drop-in
+Experiment.eval against the reference's own Experiment.eval output (tests/golden/eval_sampler.npz) and the CPU
+oracle; the device triple sampler against the reference's row layout and its draw distribution.
+
+Tolerance: 1e-4 relative on BPR / RMSE / scores; HR and NDCG exact unless two scores of a group lie within
+1e-6 of each other (a rank tie the reference resolves arbitrarily)."""
+import numpy as np
+import pytest
+import torch
+
+import seoul_tourism_recommendation_ngcf_b200 as pkg
+from oracle import ngcf_oracle as O
+from seoul_tourism_recommendation_ngcf_b200 import sampler, synth
+from tests._golden import Golden, eval_frame_cols, eval_test_batches
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def g():
+    return Golden("eval_sampler")
+
+
+def _oracle_groups(u, p, ids, rating, sizes, wd, tb, ks):
+    out, o = [], 0
+    for n in sizes:
+        s = slice(o, o + n)
+        bpr, hit, ndcg, rmse, sc = O.eval_group_metrics(u[s], p[s], ids[s], rating[s], wd, tb, ks)
+        srt = np.sort(sc.numpy())
+        out.append((float(bpr), hit, ndcg, float(rmse), float(np.min(np.diff(srt))) if n > 1 else 1.0))
+        o += n
+    return out
+
+
+@pytest.mark.parametrize("G,group,D,ks,ragged", [(300, 25, 257, 10, False), (7, 3, 64, 2, False),
+                                                 (64, 128, 640, 20, False), (50, 25, 195, 10, True)])
+def test_eval_groups_vs_oracle(G, group, D, ks, ragged):
+    rng = np.random.default_rng(G + D)
+    sizes = [int(x) for x in (rng.integers(ks, group + 1, G) if ragged else np.full(G, group))]
+    rows = sum(sizes)
+    u = torch.from_numpy(rng.standard_normal((rows, D)).astype(np.float32) * 0.3)
+    p = torch.from_numpy(rng.standard_normal((rows, D)).astype(np.float32) * 0.3)
+    ids = torch.from_numpy(rng.integers(0, 5000, rows))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    for j in range(0, G, 5):                       # some groups repeat the ground-truth id further down
+        if sizes[j] > 2:
+            ids[off[j] + 2] = ids[off[j]]
+    rating = torch.from_numpy(rng.integers(0, 9, rows))
+    want = _oracle_groups(u, p, ids, rating, sizes, 0.025, 25, ks)
+    kw = dict(group_ptr=torch.from_numpy(off)) if ragged else dict(group=group)
+    tot, per = pkg.eval_groups(u.to(DEV), p.to(DEV), ids.to(DEV), rating.to(DEV), ks=ks, weight_decay=0.025,
+                               batch_size=25, return_per_group=True, **kw)
+    per, tot = per.cpu().numpy(), tot.cpu().numpy()
+    w = np.array([x[:4] for x in want], dtype=np.float64)
+    assert np.allclose(per[0], w[:, 0], rtol=TOL) and np.allclose(per[3], w[:, 3], rtol=TOL, atol=1e-5)
+    clear = np.array([x[4] > 1e-5 for x in want])
+    assert clear.mean() > 0.9
+    assert np.array_equal(per[1][clear], w[clear, 1]) and np.allclose(per[2][clear], w[clear, 2], rtol=1e-6)
+    assert np.allclose(tot[[0, 3]], w[:, [0, 3]].mean(0), rtol=TOL)
+    if clear.all():
+        assert np.allclose(tot[[1, 2]], w[:, [1, 2]].mean(0), rtol=1e-5)
+
+
+def test_eval_groups_argument_errors():
+    z = torch.zeros(50, 8, device=DEV)
+    i = torch.zeros(50, dtype=torch.int64, device=DEV)
+    with pytest.raises(RuntimeError, match="out of range"):
+        pkg.eval_groups(z, z, i, z[:, 0], group=25, ks=26, weight_decay=0.0, batch_size=25)
+    with pytest.raises(RuntimeError, match="whole groups"):
+        pkg.eval_groups(z, z, i, z[:, 0], group=24, ks=3, weight_decay=0.0, batch_size=25)
+
+
+class _TestSet(torch.utils.data.Dataset):
+    """TourDataset(train=False).__getitem__ over the reference's sampled rows (utils.py:206-209)."""
+
+    def __init__(self, users, items):
+        self.users, self.items = users, items
+
+    def __len__(self):
+        return len(self.users)
+
+    def __getitem__(self, k):
+        u = self.users[k]
+        return u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], self.items[k]
+
+
+def _experiment(g, mode):
+    cfg = g.cfg
+    m = pkg.NGCF(cfg["emb"], cfg["layers"], cfg["node_p"], cfg["mess_p"], cfg["emb_ratio"], g.lap_list(),
+                 synth.num_dict_for(cfg["n_user"], cfg["n_item"]), cfg["B"], torch.device(DEV))
+    m.load_state_dict(g.params())
+    m = m.to(DEV)
+    ds = _TestSet(torch.from_numpy(g.raw["sampler/test_users"]), torch.from_numpy(g.raw["sampler/test_items"]))
+    loader = torch.utils.data.DataLoader(ds, batch_size=cfg["test_batch"], shuffle=False, drop_last=True)
+    return m, pkg.Experiment(m, None, None, pkg.BPR(cfg["wd"], cfg["test_batch"]), None, loader, 1, cfg["ks"],
+                             torch.device(DEV), eval_mode=mode, verbose=False)
+
+
+def _close_metrics(got, want, n_groups):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert abs(got[0] - want[0]) <= TOL * abs(want[0]) and abs(got[3] - want[3]) <= TOL * abs(want[3]), (got, want)
+    # HR / NDCG: exact up to one group flipping on a rank tie
+    assert abs(got[1] - want[1]) <= 1.0 / n_groups + 1e-6 and abs(got[2] - want[2]) <= 1.0 / n_groups + 1e-6, (got, want)
+
+
+def test_experiment_eval_matches_reference_experiment(g):
+    """Drop-in Experiment.eval (per-batch forwards, one fused metric launch) vs the numbers the reference's own
+    Experiment.eval returned on the same model, graph and test rows — first and second pass (the first pass leaves
+    the feature-mixed user table behind, experiment.py:82 -> NGCF.py:114-115)."""
+    n_groups = len(g.raw["sampler/test_users"]) // g.cfg["test_batch"]
+    m, exp = _experiment(g, "reference")
+    _close_metrics(exp.eval(), g.out("metrics"), n_groups)
+    assert not m.training
+    assert np.abs(m.user_embedding.weight.detach().cpu().numpy() - g.out("user_after")).max() <= 1e-6
+    _close_metrics(exp.eval(), g.out("metrics_pass2"), n_groups)
+
+
+def test_batched_eval_equals_reference_on_a_mixed_table(g):
+    """eval_mode='batched': ONE propagation for all 104 test batches.  On the table the first pass left behind the
+    feature mix is idempotent (emb_ratio = 1), so it must reproduce the reference's second-pass numbers."""
+    n_groups = len(g.raw["sampler/test_users"]) // g.cfg["test_batch"]
+    m, exp = _experiment(g, "batched")
+    with torch.no_grad():
+        m.user_embedding.weight.copy_(torch.from_numpy(g.out("user_after")))
+    _close_metrics(exp.eval(), g.out("metrics_pass2"), n_groups)
+
+
+def _check_draws(ix, neg, ng):
+    cand, ptr, idx = ix["candidates"], ix["pos_ptr"], ix["pos_idx"]
+    assert neg.shape == (len(ix["rows"]), ng)
+    assert np.isin(neg, cand).all()
+    for r in range(neg.shape[0]):
+        u = ix["row_user"][r]
+        assert not np.isin(neg[r], cand[idx[ptr[u]:ptr[u + 1]]]).any()
+        assert len(set(neg[r].tolist())) == ng
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_device_sampler_layout_and_support(g, train):
+    test, total = eval_frame_cols(g, "test"), eval_frame_cols(g, "total")
+    ds = pkg.TourDataset(test, total, train, "rating", device=DEV, seed=11)
+    key = "train" if train else "test"
+    ref_u, ref_i = g.raw[f"sampler/{key}_users"], g.raw[f"sampler/{key}_items"]
+    assert ds.users.dtype == torch.int64 and ds.items.dtype == torch.int64
+    assert np.array_equal(ds.users.numpy(), ref_u) and ds.items.shape == ref_i.shape
+    ix = sampler.index_frame(test, total["itemid"], "rating")
+    it = ds.items.numpy()
+    if train:
+        assert np.array_equal(it[:, 0], ref_i[:, 0])
+        _check_draws(ix, it[:, 1:], 1)
+        assert len(ds[3]) == 9 and int(ds[3][7]) == ref_i[3, 0]
+    else:
+        it = it.reshape(-1, 25)
+        assert np.array_equal(it[:, 0], ref_i.reshape(-1, 25)[:, 0])
+        _check_draws(ix, it[:, 1:], 24)
+        assert len(ds[30]) == 9 and int(ds[30][8]) == it.reshape(-1)[30]
+    again = pkg.TourDataset(test, total, train, "rating", device=DEV, seed=11)
+    other = pkg.TourDataset(test, total, train, "rating", device=DEV, seed=12)
+    assert torch.equal(again.items, ds.items) and not torch.equal(other.items, ds.items)
+    # the sampled rows feed the drop-in evaluation loop unchanged
+    if not train:
+        assert len(eval_test_batches(g, ds.users, ds.items)) == len(ds) // 25
+
+
+def test_device_sampler_distribution_and_population_error():
+    """One user with positives {1, 4, 5, 9} of 12 candidates (ids 100..111): every draw position is uniform over the
+    8 free ids (ordered sample without replacement, like np.random.choice(..., replace=False)), pairs are uniform
+    over ordered pairs; asking for more than the 8 free ids raises numpy's error."""
+    cand = torch.arange(100, 112)
+    ptr = torch.tensor([0, 4], dtype=torch.int32)
+    idx = torch.tensor([1, 4, 5, 9], dtype=torch.int32)
+    R = 200_000
+    rows = torch.zeros(R, dtype=torch.int64, device=DEV)
+    neg = pkg.sample_negatives(ptr, idx, rows, cand, 3, seed=5).cpu().numpy()
+    free = np.array([100, 102, 103, 106, 107, 108, 110, 111])
+    assert np.isin(neg, free).all()
+    assert (neg[:, 0] != neg[:, 1]).all() and (neg[:, 0] != neg[:, 2]).all() and (neg[:, 1] != neg[:, 2]).all()
+    for j in range(3):
+        cnt = np.array([(neg[:, j] == f).sum() for f in free])
+        chi2 = ((cnt - R / 8) ** 2 / (R / 8)).sum()
+        assert chi2 < 40.0, (j, cnt)                      # 7 dof: p(chi2 > 40) ~ 1e-6
+    pair = np.searchsorted(free, neg[:, 0]) * 8 + np.searchsorted(free, neg[:, 1])
+    cnt = np.bincount(pair, minlength=64)
+    assert (cnt.reshape(8, 8).diagonal() == 0).all()
+    off = cnt[cnt > 0]
+    assert off.size == 56 and (((off - R / 56) ** 2) / (R / 56)).sum() < 130.0      # 55 dof
+    full = pkg.sample_negatives(ptr, idx, rows[:1000], cand, 8, seed=1).cpu().numpy()
+    assert (np.sort(full, axis=1) == free).all()          # ng == population: a permutation of all free ids
+    with pytest.raises(ValueError, match="larger sample than population"):
+        pkg.sample_negatives(ptr, idx, rows[:10], cand, 9, seed=1)
+
+
+def test_device_sampler_at_gowalla_shape():
+    """1.03 M positive rows of the Gowalla-shaped synthetic graph in one launch: support and distinctness checked
+    with vectorised set arithmetic (size-independent properties)."""
+    n_user, n_item, n_edges, _, _ = synth.SHAPES["gowalla"]
+    u, i, _ = synth.powerlaw_bipartite(n_user, n_item, n_edges, alpha=0.8, seed=0)
+    cols = {c: np.zeros(n_edges, dtype=np.int64) for c in sampler.CONTEXT_COLS}
+    cols.update(userid=u.astype(np.int64), itemid=i.astype(np.int64), rating=np.ones(n_edges))
+    ix = sampler.index_frame(cols, np.arange(n_item), "rating")
+    neg = pkg.sample_negatives(torch.from_numpy(ix["pos_ptr"]), torch.from_numpy(ix["pos_idx"]),
+                               torch.from_numpy(ix["row_user"]).to(DEV), torch.from_numpy(ix["candidates"]), 4, seed=3)
+    neg = neg.cpu().numpy()
+    assert neg.min() >= 0 and neg.max() < n_item
+    pos_keys = ix["row_user"].astype(np.int64) * n_item + cols["itemid"][ix["rows"]]
+    all_pos = np.unique(pos_keys)
+    neg_keys = (ix["row_user"].astype(np.int64)[:, None] * n_item + neg).reshape(-1)
+    assert not np.isin(neg_keys, all_pos).any()
+    s = np.sort(neg, axis=1)
+    assert (np.diff(s, axis=1) > 0).all()
+    assert len(np.unique(neg)) > 0.9 * n_item               # draws reach (almost) every item
