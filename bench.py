@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="gowalla")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the measured whole-epoch leg")
     ap.add_argument("--eager", action="store_true", help="time the eager drop-in path only (no CUDA graph)")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
     return ap.parse_args()
@@ -308,6 +309,7 @@ def run_ours(args):
     # ---- the reference's whole training iteration (experiment.py:45-58): the step above + Adam (main.py:74) -----------
     # reported beside the metric, not in it (BASELINE.json's metric is fwd + bwd + BPR)
     with_adam = None
+    gstep_opt = None
     if gstep is not None and world == 1:
         try:
             gstep_opt = pkg.GraphedStep(model, crit, BATCH, node_flag=True, optimizer=pkg.Adam(model.parameters(), lr=5e-5))
@@ -321,6 +323,17 @@ def run_ours(args):
                          "adam_algorithmic_bytes": 28 * sum(p.numel() for p in model.parameters() if p.grad is not None)}
         except Exception as e:
             log(f"[bench] step + Adam graph failed ({type(e).__name__}: {e})")
+
+    # ---- one WHOLE epoch, measured instead of extrapolated: the reference's Experiment.train loop for one epoch
+    # (experiment.py:36-60) over triples drawn by the device sampler, host batches, Adam in the step ---------------------
+    measured_epoch = None
+    if gstep_opt is not None and with_adam is not None and not args.no_epoch:
+        try:
+            w0 = time.time()
+            measured_epoch = run_epoch(pkg, gstep_opt, info, dev)
+            windows.append((w0, time.time()))
+        except Exception as e:
+            log(f"[bench] measured epoch failed ({type(e).__name__}: {e})")
 
     # ---- roofline of the dominant kernel: the propagation SpMM of layer 0 exactly as the step runs it (this step's
     # node-dropout survivors, compacted), timed alone, cold L2 ----------------------------------------------------------
@@ -432,6 +445,7 @@ def run_ours(args):
         "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
         "gpu_launches_note": "library kernels per step (captured once, replayed per step under GraphedStep)",
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "training_iteration_with_adam": with_adam,
+        "measured_epoch": measured_epoch,
     }
     if breakdown:
         out["breakdown"] = breakdown
@@ -439,6 +453,64 @@ def run_ours(args):
     if world > 1:
         sys.stderr.flush()
         os._exit(0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# a whole measured epoch through the drop-in sampler + GraphedStep(optimizer=Adam)
+# ------------------------------------------------------------------------------------------------------------
+def run_epoch(pkg, gstep_opt, info, dev):
+    """main.py:34-42 + experiment.py:36-60 for ONE epoch: TourDataset(train=True) negatives (device sampler), a
+    shuffled drop_last loader of 1024-row HOST batches, and per batch forward + BPR + backward + Adam; the epoch's
+    loss sum is read back once at the end (experiment.py:59,62)."""
+    from seoul_tourism_recommendation_ngcf_b200 import sampler as S, synth
+    from seoul_tourism_recommendation_ngcf_b200.graph import FIELDS
+    n_user, n_item, E = info["n_user"], info["n_item"], info["interactions"]
+    u, i, _ = synth.powerlaw_bipartite(n_user, n_item, E, alpha=0.8, seed=0)          # the bench graph's edges
+    nd = synth.num_dict_for(n_user, n_item)
+    rng = np.random.default_rng(5)
+    feat = {k: rng.integers(0, nd[c], n_user) for k, c in (("age", "age"), ("sex", "sex"), ("month", "month"),
+                                                          ("day", "day"), ("dow", "dayofweek"))}   # id -> features
+    cols = {"userid": u.astype(np.int64), "itemid": i.astype(np.int64), "rating": np.ones(E, dtype=np.float32)}
+    t0 = time.time()
+    ix = S.index_frame(cols, np.arange(n_item), "rating")
+    t_index = time.time() - t0
+    d = {k: torch.from_numpy(v).to(dev) for k, v in ix.items()}
+    user_d, item_d = torch.from_numpy(cols["userid"]).to(dev), torch.from_numpy(cols["itemid"]).to(dev)
+    feat_d = {k: torch.from_numpy(v).to(dev) for k, v in feat.items()}
+    torch.cuda.synchronize()
+    t0 = time.time()
+    neg = pkg.sample_negatives(d["pos_ptr"], d["pos_idx"], d["row_user"], d["candidates"], 1, seed=1)[:, 0]
+    perm = torch.randperm(E, device=dev)                                              # DataLoader(shuffle=True)
+    rows = d["rows"][perm]
+    uid = user_d[rows]
+    by_field = {"u_id": uid, "pos_item": item_d[rows], "neg_item": neg[perm]}
+    by_field.update({k: feat_d[k][uid] for k in feat_d})
+    table = torch.stack([by_field[k] for k in FIELDS]).cpu().pin_memory()             # [8, E] host, like the loader's
+    t_sample = time.time() - t0
+    steps = E // BATCH                                                                # drop_last=True, main.py:39-42
+    year = torch.full((BATCH,), 18, dtype=torch.int64)
+    losses = torch.zeros(steps, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    for s in range(steps):
+        b = {k: table[j, s * BATCH:(s + 1) * BATCH] for j, k in enumerate(FIELDS)}
+        b["year"] = year
+        losses[s] = gstep_opt(b).detach()
+    total = float(losses.sum())                                                       # the epoch's one read-back
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    ls = losses.cpu().numpy()
+    return {"steps": steps, "seconds": round(e0.elapsed_time(e1) / 1e3, 4), "wall_seconds": round(wall, 4),
+            "ms_per_step": round(e0.elapsed_time(e1) / steps, 5), "sampler_and_shuffle_seconds": round(t_sample, 4),
+            "host_index_seconds": round(t_index, 3), "train_bpr": total / steps,
+            "loss_first_50": float(ls[:50].mean()), "loss_last_50": float(ls[-50:].mean()),
+            "h2d_bytes_per_step": 8 * BATCH * 8,
+            "what": "one full epoch as experiment.py:36-60 runs it: device-sampled negatives (TourDataset), shuffled "
+                    "drop_last batches of 1024 from pinned host memory, forward + BPR + backward + Adam(lr=5e-5) per "
+                    "batch (GraphedStep), no L2 flush, CUDA events around the whole loop"}
 
 
 # ------------------------------------------------------------------------------------------------------------
