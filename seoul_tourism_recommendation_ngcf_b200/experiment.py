@@ -69,7 +69,7 @@ class Experiment(nn.Module):
     ``nn.Module``'s like the reference's do."""
 
     def __init__(self, model, optimizer, criterion, test_criterion, train_dataloader, test_dataloader, epochs: int,
-                 ks: int, device, eval_mode: str = "reference", verbose: bool = True):
+                 ks: int, device, eval_mode: str = "reference", verbose: bool = True, graphed: bool = False):
         super().__init__()
         if eval_mode not in ("reference", "batched"):
             raise ValueError("eval_mode is 'reference' or 'batched'")
@@ -84,6 +84,10 @@ class Experiment(nn.Module):
         self.device = device
         self.eval_mode = eval_mode
         self.verbose = verbose
+        # graphed=True: each training batch is one replay of graph.GraphedStep (forward + BPR + backward + optimizer
+        # in one CUDA graph); needs ngcf_b200.Adam as the optimizer and a drop_last loader (main.py:39-42 has one)
+        self.graphed = graphed
+        self._gstep = None
 
     # experiment.py:32-64
     def train(self):
@@ -91,12 +95,16 @@ class Experiment(nn.Module):
         for epoch in range(self.epochs):
             total_loss = torch.zeros((), device=self.device)
             for year, u_id, age, sex, month, day, dow, pos_item, neg_item in self.train_dataloader:
-                u, p, n = self.model(year=year, u_id=u_id, age=age, sex=sex, month=month, day=day, dow=dow,
-                                     pos_item=pos_item, neg_item=neg_item, node_flag=True)
-                self.optimizer.zero_grad()
-                loss = self.criterion(u, p, n)
-                loss.backward()
-                self.optimizer.step()
+                if self.graphed:
+                    loss = self._graphed_step(dict(year=year, u_id=u_id, age=age, sex=sex, month=month, day=day,
+                                                   dow=dow, pos_item=pos_item, neg_item=neg_item))
+                else:
+                    u, p, n = self.model(year=year, u_id=u_id, age=age, sex=sex, month=month, day=day, dow=dow,
+                                         pos_item=pos_item, neg_item=neg_item, node_flag=True)
+                    self.optimizer.zero_grad()
+                    loss = self.criterion(u, p, n)
+                    loss.backward()
+                    self.optimizer.step()
                 total_loss += loss.detach()
             BPR, HR, NDCG, RMSE = self.eval()
             train_bpr = float(total_loss) / len(self.train_dataloader)
@@ -104,6 +112,15 @@ class Experiment(nn.Module):
             if self.verbose:
                 print(f"epoch {epoch + 1}, Train BPR: {train_bpr}, Test BPR: {BPR}, HR:{HR}, NDCG:{NDCG}, RMSE:{RMSE}")
         return history
+
+    def _graphed_step(self, batch):
+        from .graph import GraphedStep
+        training = self.model.training
+        if self._gstep is None or self._gstep[0] != training:      # train/eval mode is frozen into a capture
+            self._gstep = (training, GraphedStep(self.model, self.criterion, batch["u_id"].numel(), node_flag=True,
+                                                 optimizer=self.optimizer))
+        batch["year"] = batch["year"].cpu()
+        return self._gstep[1](batch)
 
     def _forward(self, b):
         u, p, _ = self.model(year=b[0], u_id=b[1], age=b[2], sex=b[3], month=b[4], day=b[5], dow=b[6],

@@ -127,6 +127,42 @@ def test_batched_eval_equals_reference_on_a_mixed_table(g):
     _close_metrics(exp.eval(), g.out("metrics_pass2"), n_groups)
 
 
+def test_experiment_train_eager_and_graphed_agree(g):
+    """Experiment.train (experiment.py:32-64) over the reference's sampled training rows: the eager loop with
+    torch.optim.Adam and the graphed loop with the fused Adam reach the same parameters and the same history
+    (dropout off so both see the same gradients; the first eval() leaves the model in eval mode, as in the reference)."""
+    cfg = g.cfg
+    users, items = torch.from_numpy(g.raw["sampler/train_users"]), torch.from_numpy(g.raw["sampler/train_items"])
+
+    class TrainSet(torch.utils.data.Dataset):
+        def __len__(self):
+            return len(users)
+
+        def __getitem__(self, k):
+            u = users[k]
+            return u[0], u[1], u[2], u[3], u[4], u[5], u[6], items[k][0], items[k][1]
+
+    test = _TestSet(torch.from_numpy(g.raw["sampler/test_users"][:250]), torch.from_numpy(g.raw["sampler/test_items"][:250]))
+    hist, models = [], []
+    for graphed in (False, True):
+        m = pkg.NGCF(cfg["emb"], cfg["layers"], 0.0, [0.0, 0.0], cfg["emb_ratio"], g.lap_list(),
+                     synth.num_dict_for(cfg["n_user"], cfg["n_item"]), 32, torch.device(DEV))
+        m.load_state_dict(g.params())
+        m = m.to(DEV)
+        opt = pkg.Adam(m.parameters(), lr=1e-2) if graphed else torch.optim.Adam(m.parameters(), lr=1e-2)
+        tr = torch.utils.data.DataLoader(TrainSet(), batch_size=32, shuffle=False, drop_last=True)
+        te = torch.utils.data.DataLoader(test, batch_size=25, shuffle=False, drop_last=True)
+        exp = pkg.Experiment(m, opt, pkg.BPR(0.025, 32), pkg.BPR(0.025, 25), tr, te, 2, cfg["ks"], torch.device(DEV),
+                             verbose=False, graphed=graphed)
+        hist.append(np.array(exp.train()))
+        models.append(m)
+    assert hist[0].shape == (2, 5) and np.isfinite(hist[0]).all()
+    assert np.allclose(hist[0][:, [0, 1, 4]], hist[1][:, [0, 1, 4]], rtol=2e-4), (hist[0], hist[1])
+    for (k, a), (_, c) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert np.abs(a.detach().cpu().numpy() - c.detach().cpu().numpy()).max() <= \
+            2e-4 * max(1e-30, np.abs(a.detach().cpu().numpy()).max()), k
+
+
 def _check_draws(ix, neg, ng):
     cand, ptr, idx = ix["candidates"], ix["pos_ptr"], ix["pos_idx"]
     assert neg.shape == (len(ix["rows"]), ng)
