@@ -17,6 +17,7 @@ constexpr int EV_MAX_GROUP = 128;
 // One CTA per test group (grid-stride).  Rows base .. base+group-1 of `u` / `it` (base = g*group, or group_ptr[g]
 // for ragged groups) are what NGCF.forward returned for the group's batch: u_embeds and pos_i_embeds, row 0 = the
 // positive, rows 1.. = the negatives.
+template <bool VEC4>
 __global__ void __launch_bounds__(EV_THREADS)
 eval_groups_kernel(const float* __restrict__ u, const float* __restrict__ it, const int64_t* __restrict__ ids,
                    const float* __restrict__ rating, const int64_t* __restrict__ group_ptr, int64_t n_groups,
@@ -44,13 +45,27 @@ eval_groups_kernel(const float* __restrict__ u, const float* __restrict__ it, co
             const float* pb = it + (base + b) * D;
             const float* nbp = it + (base + nb) * D;
             float sc = 0.f, up = 0.f, un = 0.f, nu = 0.f, ni = 0.f;
-            for (int c = lane; c < D; c += 32) {
-                const float x = ub[c], y = pb[c];
-                sc = fmaf(u0[c], y, sc);            // pred_ratings[0, b], experiment.py:93
-                up = fmaf(x, p0[c], up);            // x_upos, bprloss.py:16 (positive row broadcast)
-                un = fmaf(x, nbp[c], un);           // x_uneg, bprloss.py:17
-                nu = fmaf(x, x, nu);
-                ni = fmaf(y, y, ni);
+            // sc: pred_ratings[0, b], experiment.py:93; up: x_upos, bprloss.py:16 (positive row broadcast);
+            // un: x_uneg, bprloss.py:17; nu / ni: the squared norms of bprloss.py:20-21
+            if (VEC4) {                             // D % 4 == 0 and 16-byte aligned rows: 128-bit loads
+                for (int c = lane; c < (D >> 2); c += 32) {
+                    const float4 x = ld_stream_f4(ub + 4 * c), y = ld_f4(pb + 4 * c);
+                    const float4 a = ld_f4(u0 + 4 * c), p = ld_f4(p0 + 4 * c), n = ld_f4(nbp + 4 * c);
+                    sc = fmaf(a.x, y.x, fmaf(a.y, y.y, fmaf(a.z, y.z, fmaf(a.w, y.w, sc))));
+                    up = fmaf(x.x, p.x, fmaf(x.y, p.y, fmaf(x.z, p.z, fmaf(x.w, p.w, up))));
+                    un = fmaf(x.x, n.x, fmaf(x.y, n.y, fmaf(x.z, n.z, fmaf(x.w, n.w, un))));
+                    nu = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, nu))));
+                    ni = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, ni))));
+                }
+            } else {
+                for (int c = lane; c < D; c += 32) {
+                    const float x = ub[c], y = pb[c];
+                    sc = fmaf(u0[c], y, sc);
+                    up = fmaf(x, p0[c], up);
+                    un = fmaf(x, nbp[c], un);
+                    nu = fmaf(x, x, nu);
+                    ni = fmaf(y, y, ni);
+                }
             }
             sc = warp_sum(sc); up = warp_sum(up); un = warp_sum(un); nu = warp_sum(nu); ni = warp_sum(ni);
             if (lane == 0) { s_score[b] = sc; s_up[b] = up; s_un[b] = un; s_nu[b] = nu; s_ni[b] = ni; }
@@ -170,9 +185,15 @@ extern "C" int ngcf_eval_groups(const float* u, const float* items, const int64_
     if (n_groups == 0) return NGCF_OK;
     cudaStream_t st = as_stream(stream);
     const int64_t grid = n_groups < (int64_t)ngcf_num_sms() * 8 ? n_groups : (int64_t)ngcf_num_sms() * 8;
-    eval_groups_kernel<<<(unsigned)grid, EV_THREADS, 0, st>>>(u, items, item_ids, rating, group_ptr, n_groups, group, D, k_hr,
-                                                              k_ndcg, weight_decay, 1.f / batch_size_ctor, bpr, hit,
-                                                              ndcg, rmse, scores);
+    const bool vec4 = (D % 4 == 0) && (((uintptr_t)u | (uintptr_t)items) % 16 == 0);
+    if (vec4)
+        eval_groups_kernel<true><<<(unsigned)grid, EV_THREADS, 0, st>>>(
+            u, items, item_ids, rating, group_ptr, n_groups, group, D, k_hr, k_ndcg, weight_decay,
+            1.f / batch_size_ctor, bpr, hit, ndcg, rmse, scores);
+    else
+        eval_groups_kernel<false><<<(unsigned)grid, EV_THREADS, 0, st>>>(
+            u, items, item_ids, rating, group_ptr, n_groups, group, D, k_hr, k_ndcg, weight_decay,
+            1.f / batch_size_ctor, bpr, hit, ndcg, rmse, scores);
     NGCF_LAUNCH_OK("eval_groups_kernel");
     if (totals) {
         eval_reduce_kernel<<<1, 256, 0, st>>>(bpr, hit, ndcg, rmse, n_groups, totals);
