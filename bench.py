@@ -185,6 +185,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout, where the one JSON line goes: keep them on stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl")
     lib = _lib.load()
     L, batches, info = make_workload(args.shape)
