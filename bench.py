@@ -51,6 +51,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_json_out = None
+
+
+def protect_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under
+    NCCL_DEBUG=VERSION, for one) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    f = _json_out or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------------------
@@ -185,8 +204,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout, where the one JSON line goes: keep them on stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl")
     lib = _lib.load()
     L, batches, info = make_workload(args.shape)
@@ -451,7 +468,7 @@ def run_ours(args):
     }
     if breakdown:
         out["breakdown"] = breakdown
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         sys.stderr.flush()
         os._exit(0)
@@ -563,11 +580,12 @@ def run_reference(args):
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 if __name__ == "__main__":
     a = parse_args()
+    protect_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
