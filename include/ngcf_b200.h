@@ -286,6 +286,16 @@ int ngcf_sample_negatives(const int32_t* pos_ptr, const int32_t* pos_idx, const 
                           const int64_t* candidates, int n_candidates, int ng_ratio, uint64_t seed, int64_t* out,
                           int32_t* n_short, void* stream);
 
+/* ---- Laplacian builder on the device: matrix.py:41-62 restricted to the non-zeros ----------
+ * From n_pairs DISTINCT (user, item, rating != 0) pairs: deg[N] = number of non-zeros per row of A = [[0,R],[R^T,0]]
+ * (matrix.py:55), then the 2*n_pairs entries of L = D^-1/2 A D^-1/2 (matrix.py:56-62): entry e -> (user, n_user+item),
+ * entry n_pairs+e -> (n_user+item, user), value = float(d_row * (rating * d_col)) with d = float32(deg^-1/2), the product
+ * in double like the reference's float64 multi_dot.  Unsorted; the caller sorts row-major (matrix.py:79-83 emits sorted
+ * indices) or feeds ngcf_coo_to_csr directly.  deg is cleared by the call. */
+int ngcf_laplacian_entries(const int64_t* user, const int64_t* item, const float* rating, int64_t n_pairs,
+                           int64_t n_user, int64_t n_item, int32_t* deg, int64_t* row, int64_t* col, float* val,
+                           void* stream);
+
 /* ---- debugging aids (tools/bwd_timeline.py, fwd_timeline.py, spmm_timeline.py); not part of the product path --------
  * ngcf_debug_bwd_timeline: switches the in-kernel SM-clock stamps of CTA 0 of the tcgen05 dense kernels on/off and
  * copies them back (out_host: int64[4*8*8] or NULL).  ngcf_debug_spmm_timeline: device buffer uint64[n_ctas*4]

@@ -3,7 +3,8 @@
 //                           one launch: scores of row 0 against the group's items, test BPR, HR@3, NDCG@ks, RMSE;
 //   * ngcf_sample_negatives — TourDataset._negative_sampling (utils.py:213-275): for every positive row, ng_ratio
 //                           distinct items the user has no positive feedback for, uniformly, without replacement.
-// Both are small latency/HBM-bound integer + dot-product kernels; no tensor cores.
+//   * ngcf_laplacian_entries — the non-zeros of L = D^-1/2 A D^-1/2 from the rating pairs (matrix.py:41-62), section 8(f) #2.
+// All are small latency/HBM-bound integer + dot-product kernels; no tensor cores.
 #include <limits.h>
 
 #include "common.cuh"
@@ -168,7 +169,49 @@ sample_negatives_kernel(const int32_t* __restrict__ pos_ptr, const int32_t* __re
     }
 }
 
+// ---- Laplacian entries from the rating pairs (matrix.py:41-62, restricted to the non-zeros) -----------------------------
+__global__ void lap_degree_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ item, int64_t n_pairs,
+                                  int64_t n_user, int32_t* __restrict__ deg) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_pairs) return;
+    atomicAdd(&deg[user[e]], 1);                     // np.count_nonzero(adj_mat, axis=1), matrix.py:55
+    atomicAdd(&deg[n_user + item[e]], 1);
+}
+
+// d^-1/2 as float32 (np.power(diag, -0.5, dtype=np.float32), matrix.py:56; inf -> 0, :57): the correctly rounded
+// float of the exact value (numpy's SIMD float32 power is within ~3e-7 relative of it, not bit-identical)
+__device__ __forceinline__ double lap_dinv(int32_t d) { return d > 0 ? (double)(float)(1.0 / sqrt((double)d)) : 0.0; }
+
+__global__ void lap_entries_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ item,
+                                   const float* __restrict__ rating, int64_t n_pairs, int64_t n_user,
+                                   const int32_t* __restrict__ deg, int64_t* __restrict__ row,
+                                   int64_t* __restrict__ col, float* __restrict__ val) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_pairs) return;
+    const int64_t u = user[e], i = n_user + item[e];
+    const double a = (double)rating[e], du = lap_dinv(deg[u]), di = lap_dinv(deg[i]);
+    row[e] = u; col[e] = i; val[e] = (float)(du * (a * di));                        // A = [[0, R], [R^T, 0]], :49-53
+    row[n_pairs + e] = i; col[n_pairs + e] = u; val[n_pairs + e] = (float)(di * (a * du));   // D^-1/2 A D^-1/2, :62
+}
+
 }  // namespace
+
+extern "C" int ngcf_laplacian_entries(const int64_t* user, const int64_t* item, const float* rating, int64_t n_pairs,
+                                      int64_t n_user, int64_t n_item, int32_t* deg, int64_t* row, int64_t* col,
+                                      float* val, void* stream) {
+    NGCF_REQUIRE(n_pairs >= 0 && n_user > 0 && n_item > 0, "laplacian_entries: bad sizes");
+    NGCF_REQUIRE(deg, "laplacian_entries: null degree buffer");
+    cudaStream_t st = as_stream(stream);
+    NGCF_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (size_t)(n_user + n_item), st));
+    if (n_pairs == 0) return NGCF_OK;
+    NGCF_REQUIRE(user && item && rating && row && col && val, "laplacian_entries: null pointer");
+    const unsigned grid = (unsigned)ceil_div64(n_pairs, 256);
+    lap_degree_kernel<<<grid, 256, 0, st>>>(user, item, n_pairs, n_user, deg);
+    NGCF_LAUNCH_OK("lap_degree_kernel");
+    lap_entries_kernel<<<grid, 256, 0, st>>>(user, item, rating, n_pairs, n_user, deg, row, col, val);
+    NGCF_LAUNCH_OK("lap_entries_kernel");
+    return NGCF_OK;
+}
 
 extern "C" int ngcf_eval_groups(const float* u, const float* items, const int64_t* item_ids, const float* rating,
                                 const int64_t* group_ptr, int64_t n_groups, int group, int D, int k_hr, int k_ndcg, float weight_decay,

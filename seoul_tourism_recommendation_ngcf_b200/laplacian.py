@@ -37,7 +37,36 @@ def laplacian_coo(users, items, ratings, n_user: int, n_item: int) -> torch.Tens
     return torch.sparse_coo_tensor(idx, val, (N, N), is_coalesced=False, check_invariants=False)
 
 
-def build_lap_list(years, users, items, ratings, n_user: int, n_item: int) -> list:
+def laplacian_coo_device(users, items, ratings, n_user: int, n_item: int, device) -> torch.Tensor:
+    """Same result as ``laplacian_coo`` built on the GPU (``ngcf_laplacian_entries``: degree count + normalisation of
+    the 2·nnz entries in two launches; the row-major order of matrix.py:79-83 by one device sort).  Values agree with the
+    host builder's to 5e-7 relative (numpy's SIMD float32 power is not correctly rounded; the device value is).  CUDA only."""
+    from . import _lib
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("laplacian_coo_device builds on a CUDA device only; use laplacian_coo on the host")
+    lib = _lib.load()
+    u = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(device)
+    i = torch.as_tensor(np.asarray(items, dtype=np.int64)).to(device)
+    r = torch.as_tensor(np.asarray(ratings, dtype=np.float32)).to(device)
+    nz = r != 0                                                  # zero ratings are not edges (dok_matrix drops them)
+    u, i, r = u[nz].contiguous(), i[nz].contiguous(), r[nz].contiguous()
+    n, N = u.numel(), n_user + n_item
+    deg = torch.empty(N, dtype=torch.int32, device=device)
+    row = torch.empty(2 * n, dtype=torch.int64, device=device)
+    col = torch.empty(2 * n, dtype=torch.int64, device=device)
+    val = torch.empty(2 * n, dtype=torch.float32, device=device)
+    _lib.check(lib.ngcf_laplacian_entries(u.data_ptr(), i.data_ptr(), r.data_ptr(), n, n_user, n_item, deg.data_ptr(),
+                                          row.data_ptr(), col.data_ptr(), val.data_ptr(), _lib.current_stream()),
+               "laplacian_entries")
+    keep = val != 0
+    row, col, val = row[keep], col[keep], val[keep]
+    order = torch.argsort(row * N + col)
+    idx = torch.stack([row[order], col[order]])
+    return torch.sparse_coo_tensor(idx, val[order], (N, N), is_coalesced=False, check_invariants=False)
+
+
+def build_lap_list(years, users, items, ratings, n_user: int, n_item: int, device=None) -> list:
     """Year loop of Matrix.create_matrix (matrix.py:41-67): R is never reset, so each year's graph is the
     previous one overwritten by that year's ratings; the slot is ``year % 18``."""
     years = np.asarray(years)
@@ -54,5 +83,8 @@ def build_lap_list(years, users, items, ratings, n_user: int, n_item: int) -> li
             acc[k] = r
         keys = np.fromiter(acc.keys(), dtype=np.int64, count=len(acc))
         vals = np.fromiter(acc.values(), dtype=np.float32, count=len(acc))
-        lap_list[y % 18] = laplacian_coo(keys // n_item, keys % n_item, vals, n_user, n_item)
+        if device is not None and torch.device(device).type == "cuda":
+            lap_list[y % 18] = laplacian_coo_device(keys // n_item, keys % n_item, vals, n_user, n_item, device)
+        else:
+            lap_list[y % 18] = laplacian_coo(keys // n_item, keys % n_item, vals, n_user, n_item)
     return lap_list

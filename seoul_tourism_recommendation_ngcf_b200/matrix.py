@@ -21,7 +21,7 @@ from .laplacian import build_lap_list
 
 class Matrix(nn.Module):
     def __init__(self, total_df, cols: list, rating_col: str, num_dict: dict, folder_path: str, save_data: bool, device,
-                 args=None):
+                 args=None, builder: str = "host"):
         super().__init__()
         self.df = total_df[cols]
         self.rating_col = rating_col
@@ -31,12 +31,18 @@ class Matrix(nn.Module):
         self.n_user = num_dict['user']
         self.n_item = num_dict['item']
         self.args = args                  # the reference reads parsers.args for the pickle's file name (matrix.py:72)
+        # "host": numpy, bit-identical to the reference's values; "device": ngcf_laplacian_entries on `device` (CUDA),
+        # equal to 5e-7 relative (d^-1/2 correctly rounded instead of numpy's float32 power) — for graphs where even the O(nnz) host pass is the slow part
+        if builder not in ("host", "device"):
+            raise ValueError("builder is 'host' or 'device'")
+        self.builder = builder
         self.lap_list = [[] for _ in self.df['year'].unique()]
 
     def create_matrix(self):
         df = self.df
         laps = build_lap_list(df['year'].to_numpy(), df['userid'].to_numpy(), df['itemid'].to_numpy(),
-                              df[self.rating_col].to_numpy(), self.n_user, self.n_item)
+                              df[self.rating_col].to_numpy(), self.n_user, self.n_item,
+                              device=self.device if self.builder == "device" else None)
         self.lap_list = [L.to(self.device) if not isinstance(L, list) else L for L in laps]
         print('Laplacian Matrix Created!')
         if self.save_data:
