@@ -78,3 +78,63 @@ def test_product_eval_and_sampler_refuse_cpu(g):
     test, total = eval_frame_cols(g, "test"), eval_frame_cols(g, "total")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pkg.TourDataset(test, total, True, "rating", device="cpu")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_index_row_order_matches_oracle_on_random_frames(seed):
+    """Random frames (repeated (user, item) rows, zero ratings, users without positives, item ids with gaps): the
+    sampler's host index emits the same rows in the same order as the restated reference loop, and every negative the
+    reference draws lies in the index's free-candidate set of that row's user."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    ids = np.sort(rng.choice(1000, size=int(rng.integers(3, 40)), replace=False))        # item ids with gaps
+    cols = {"year": rng.integers(18, 20, n), "userid": rng.integers(0, 25, n), "itemid": rng.choice(ids[:-2], n),
+            "age": rng.integers(0, 70, n), "sex": rng.integers(0, 2, n), "month": rng.integers(1, 13, n),
+            "day": rng.integers(1, 29, n), "dayofweek": rng.integers(0, 7, n),
+            "rating": (rng.integers(0, 4, n) * (rng.random(n) < 0.7)).astype(np.int64)}
+    ix = sampler.index_frame(cols, ids, "rating")
+    np.random.seed(seed)
+    users, items = O.negative_sampling(cols, ids, train=True)
+    rows = ix["rows"]
+    assert len(users) == rows.size
+    if rows.size == 0:
+        return
+    assert np.array_equal(np.stack([cols[c][rows] for c in sampler.CONTEXT_COLS], axis=1), users.numpy())
+    assert np.array_equal(cols["itemid"][rows], items.numpy()[:, 0])
+    cand, ptr, idx = ix["candidates"], ix["pos_ptr"], ix["pos_idx"]
+    assert np.array_equal(cand, ids)
+    for r in range(rows.size):
+        u = ix["row_user"][r]
+        pos = cand[idx[ptr[u]:ptr[u + 1]]]
+        want = np.unique(cols["itemid"][(cols["userid"] == cols["userid"][rows[r]]) & (cols["rating"] > 0)])
+        assert np.array_equal(pos, want)
+        assert items.numpy()[r, 1] in np.setdiff1d(cand, pos)
+
+
+def test_oracle_group_metrics_against_independent_float64():
+    """eval_group_metrics (the torch restatement of experiment.py:92-116) against a from-scratch float64 evaluation,
+    including a ground-truth id that also appears further down the batch (``pred_items.index(gt)`` takes the
+    best-ranked occurrence)."""
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        n, D, ks = 25, 33, 10
+        u = rng.standard_normal((n, D)).astype(np.float32) * 0.4
+        p = rng.standard_normal((n, D)).astype(np.float32) * 0.4
+        ids = rng.permutation(500)[:n]
+        if trial % 3 == 0:
+            ids[5] = ids[0]
+        rating = rng.integers(0, 6, n)
+        bpr, hit, ndcg, rmse, sc = O.eval_group_metrics(torch.from_numpy(u), torch.from_numpy(p), torch.from_numpy(ids),
+                                                        torch.from_numpy(rating), 0.025, 25, ks)
+        U, P = u.astype(np.float64), p.astype(np.float64)
+        s = P @ U[0]
+        neg = np.concatenate([P[1:], P[1:2]])
+        x = np.abs(U @ P[0]) - np.abs((U * neg).sum(1))
+        want_bpr = (-(np.minimum(x, 0) - np.log1p(np.exp(-np.abs(x)))).sum()
+                    + 0.025 * ((U ** 2).sum() + (P[0] ** 2).sum() + (neg ** 2).sum())) / 25
+        order = np.argsort(-s, kind="stable")
+        ranked = ids[order].tolist()
+        pos = ranked.index(ids[0])
+        assert abs(float(bpr) - want_bpr) <= 1e-5 * abs(want_bpr)
+        assert hit == int(pos < 3) and abs(ndcg - (1 / np.log2(pos + 2) if pos < ks else 0.0)) <= 1e-12
+        assert abs(float(rmse) - abs(s[0] - rating[0])) <= 1e-5 and np.allclose(sc.numpy(), s, atol=1e-5)
