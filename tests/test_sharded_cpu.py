@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from seoul_tourism_recommendation_ngcf_b200 import laplacian, synth
-from seoul_tourism_recommendation_ngcf_b200.sharded import RowShards, all_gather_rows, shard_coo
+from seoul_tourism_recommendation_ngcf_b200.sharded import DealtShards, RowShards, all_gather_rows, shard_coo
 
 
 def test_row_shards_cover_all_rows():
@@ -50,7 +50,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, dealt=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -62,26 +62,28 @@ def _worker(rank, world, port, ret):
         row, col = g.integers(0, N, nnz), g.integers(0, N, nnz)
         val = torch.from_numpy(g.standard_normal(nnz).astype(np.float32))
         L = torch.sparse_coo_tensor(torch.from_numpy(np.stack([row, col])), val, (N, N))
-        sh = RowShards(N, world, rank)
+        sh = (DealtShards if dealt else RowShards)(N, world, rank)
+        where = sh.position(torch.arange(N))                       # node -> row of the gathered [N_pad, d] tensors
         (rf, cf, pf), (rb, cb, pb) = shard_coo(L, sh)
         Lf = torch.sparse_coo_tensor(torch.stack([rf, cf]), val[pf], (sh.rows, sh.N_pad)).coalesce()
         Lb = torch.sparse_coo_tensor(torch.stack([rb, cb]), val[pb], (sh.rows, sh.N_pad)).coalesce()
         torch.manual_seed(1)                                       # same on every rank: replicated tables
         X = torch.randn(N, d)
         Xpad = torch.zeros(sh.N_pad, d)
-        Xpad[:N] = X
+        Xpad[where] = X
         # forward layer: local rows of S = L X, then the all-gather every rank needs for the next layer
         S_loc = torch.sparse.mm(Lf, Xpad)
         S_all = all_gather_rows(torch.empty(sh.N_pad, d), S_loc)
         want = torch.sparse.mm(L.coalesce(), X)
-        ok = torch.allclose(S_all[:N], want, atol=1e-5) and float(S_all[N:].abs().max() if sh.N_pad > N else 0) == 0
+        pad = sh.node(torch.arange(sh.N_pad)) < 0
+        ok = torch.allclose(S_all[where], want, atol=1e-5) and float(S_all[pad].abs().max() if pad.any() else 0) == 0
         # backward: gE rows = (L^T gS)[rows] from the all-gathered gS and the L^T shard
         gS_loc = torch.randn(sh.rows, d, generator=torch.Generator().manual_seed(10 + rank))
         gS_all = all_gather_rows(torch.empty(sh.N_pad, d), gS_loc)
         gE_loc = torch.sparse.mm(Lb, gS_all)
         gE_all = all_gather_rows(torch.empty(sh.N_pad, d), gE_loc)
-        want_b = torch.sparse.mm(L.coalesce().t().coalesce(), gS_all[:N])
-        ok = ok and torch.allclose(gE_all[:N], want_b, atol=1e-5)
+        want_b = torch.sparse.mm(L.coalesce().t().coalesce(), gS_all[where])
+        ok = ok and torch.allclose(gE_all[where], want_b, atol=1e-5)
         # W/b gradients: sum of per-rank partial sums over the row blocks
         part = (S_loc[:sh.valid] ** 2).sum(0)
         dist.all_reduce(part)
@@ -96,3 +98,39 @@ def test_sharded_products_match_unsharded_over_gloo(world):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret.get(r) is True for r in range(world)), dict(ret)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dealt_shards_products_match_unsharded_over_gloo(world):
+    """The entry-balanced (round-robin dealt) partition: same products after the position <-> node relabelling."""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret, True), nprocs=world, join=True)
+    assert all(ret.get(r) is True for r in range(world)), dict(ret)
+
+
+def test_dealt_shards_cover_nodes_and_balance_entries():
+    for N, world in ((10, 1), (10, 3), (70839, 8), (7, 8)):
+        shards = [DealtShards(N, world, r) for r in range(world)]
+        pos = shards[0].position(torch.arange(N))
+        assert pos.unique().numel() == N and int(pos.max()) < shards[0].N_pad
+        assert torch.equal(shards[0].node(pos), torch.arange(N))
+        assert int((shards[0].node(torch.arange(shards[0].N_pad)) < 0).sum()) == shards[0].N_pad - N
+        for s in shards:
+            lo, hi = s.bounds(s.rank)
+            mine = pos[(pos >= s.r0) & (pos < s.r0 + s.rows)]
+            assert hi - lo == s.valid == mine.numel() and (mine.numel() == 0 or (int(mine.min()) == lo and int(mine.max()) == hi - 1))
+    # Gowalla-shaped graph, 8 ranks: contiguous equal row blocks vs dealt blocks (entries per rank, max / mean)
+    n_user, n_item, n_edges, _, _ = synth.SHAPES["gowalla"]
+    u, i, r = synth.powerlaw_bipartite(n_user, n_item, n_edges, alpha=0.8, seed=0)
+    rows = torch.from_numpy(np.concatenate([u, i + n_user]))
+    N, W = n_user + n_item, 8
+    def imbalance(cls):
+        sh = cls(N, W, 0)
+        per = torch.bincount(sh.position(rows) // sh.rows, minlength=W).double()
+        return float(per.max() / per.mean())
+    assert imbalance(DealtShards) < 1.06 < 1.15 < imbalance(RowShards)      # measured 1.05 vs 1.21
+    # ids sorted by popularity (heavy rows first), as real interaction dumps often are: contiguous blocks collapse
+    order = np.argsort(-np.bincount(rows.numpy(), minlength=N), kind="stable")
+    rank_of = np.empty(N, dtype=np.int64); rank_of[order] = np.arange(N)
+    rows = torch.from_numpy(rank_of[rows.numpy()])
+    assert imbalance(RowShards) > 3.0 and imbalance(DealtShards) < 1.06
