@@ -560,8 +560,20 @@ def time_oracle(L, batches, info, max_steps, warmup, budget_s):
         if time.time() - t_start > budget_s and len(ts) >= 1:
             break
     s = statistics.mean(ts)
+    cores = torch.get_num_threads()
+    # the reference's COO SpMM does not scale with threads: a short single-thread sample too
+    single = None
+    if cores > 1:
+        torch.set_num_threads(1)
+        t1 = []
+        for j in range(2):
+            t0 = time.time()
+            one(warmup + len(ts) + j)
+            t1.append(time.time() - t0)
+        torch.set_num_threads(cores)
+        single = {"ms_per_step": round(min(t1) * 1e3, 2), "cores": 1, "sample": "best of 2 steps"}
     return {"value": round(s * info["steps_per_epoch"], 3), "unit": "s/epoch", "ms_per_step": round(s * 1e3, 2),
-            "cores": torch.get_num_threads(), "kind": "port",
+            "cores": cores, "kind": "port", "single_thread": single,
             "sample": f"{len(ts)} full training steps (of {info['steps_per_epoch']} per epoch) of the same workload, "
                       f"{warmup} warm-up; oracle/ngcf_oracle.py = the reference's torch.sparse CPU path incl. its host "
                       f"float64 node-dropout mask"}
