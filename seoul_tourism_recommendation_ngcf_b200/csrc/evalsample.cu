@@ -3,7 +3,8 @@
 //                           one launch: scores of row 0 against the group's items, test BPR, HR@3, NDCG@ks, RMSE;
 //   * ngcf_sample_negatives — TourDataset._negative_sampling (utils.py:213-275): for every positive row, ng_ratio
 //                           distinct items the user has no positive feedback for, uniformly, without replacement.
-//   * ngcf_laplacian_entries — the non-zeros of L = D^-1/2 A D^-1/2 from the rating pairs (matrix.py:41-62), section 8(f) #2.
+//   * ngcf_laplacian_entries — the non-zeros of L = D^-1/2 A D^-1/2 from the rating pairs (matrix.py:41-62),
+//                           section 8(f) #2.
 // All are small latency/HBM-bound integer + dot-product kernels; no tensor cores.
 #include <limits.h>
 
@@ -169,7 +170,7 @@ sample_negatives_kernel(const int32_t* __restrict__ pos_ptr, const int32_t* __re
     }
 }
 
-// ---- Laplacian entries from the rating pairs (matrix.py:41-62, restricted to the non-zeros) -----------------------------
+// ---- Laplacian entries from the rating pairs (matrix.py:41-62, restricted to the non-zeros) ------------------------
 __global__ void lap_degree_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ item, int64_t n_pairs,
                                   int64_t n_user, int32_t* __restrict__ deg) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,9 +215,9 @@ extern "C" int ngcf_laplacian_entries(const int64_t* user, const int64_t* item, 
 }
 
 extern "C" int ngcf_eval_groups(const float* u, const float* items, const int64_t* item_ids, const float* rating,
-                                const int64_t* group_ptr, int64_t n_groups, int group, int D, int k_hr, int k_ndcg, float weight_decay,
-                                float batch_size_ctor, float* bpr, float* hit, float* ndcg, float* rmse,
-                                float* scores, float* totals, void* stream) {
+                                const int64_t* group_ptr, int64_t n_groups, int group, int D, int k_hr, int k_ndcg,
+                                float weight_decay, float batch_size_ctor, float* bpr, float* hit, float* ndcg,
+                                float* rmse, float* scores, float* totals, void* stream) {
     NGCF_REQUIRE(u && items && item_ids && rating && bpr && hit && ndcg && rmse, "eval_groups: null pointer");
     NGCF_REQUIRE(n_groups >= 0 && D > 0, "eval_groups: bad sizes (n_groups %lld, D %d)", (long long)n_groups, D);
     NGCF_REQUIRE(group >= 2 && group <= EV_MAX_GROUP, "eval_groups: group size %d outside [2, %d]", group,
