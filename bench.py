@@ -224,6 +224,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- N > 1: the sharded step must BE the 1-GPU step before any of its timings mean anything -------
+    parity = None
+    if world > 1:
+        from seoul_tourism_recommendation_ngcf_b200 import synth
+        from seoul_tourism_recommendation_ngcf_b200.sharded import parity_vs_unsharded
+        pb = {k: torch.from_numpy(v) for k, v in batches[0].items()}
+        res = parity_vs_unsharded(info["emb"], [info["emb"]] * info["layers"], L,
+                                  synth.num_dict_for(info["n_user"], info["n_item"]), pb, BATCH, dev,
+                                  node_p=NODE_P, mess_p=MESS_P, weight_decay=WEIGHT_DECAY)
+        worst = torch.tensor([res["out"], res["loss"], res["all_E"], res["worst_grad"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)                 # the worst rank's figures
+        parity = {"out": float(worst[0]), "loss": float(worst[1]), "all_E": float(worst[2]),
+                  "worst_grad": float(worst[3]), "tolerance": 1e-5,
+                  "what": "one training step (node + message dropout ON, device RNG) row-sharded over all ranks vs the same "
+                          "step unsharded on each rank's own GPU; max|a-b|/max|b| of the batch outputs, the loss, "
+                          "all_users/items_emb and the worst parameter gradient; max over ranks"}
+        log(f"[bench] parity_vs_1gpu: {parity}")
+        if max(parity["out"], parity["loss"], parity["all_E"], parity["worst_grad"]) > 1e-5:
+            if rank == 0:
+                emit({"metric": METRIC, "error": "row-sharded step differs from the 1-GPU step", "n_gpus": world,
+                      "parity_vs_1gpu": parity})
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(3)
+        torch.cuda.empty_cache()
+
     crit = pkg.BPR(WEIGHT_DECAY, BATCH)
     dbatches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in batches]
     hbatches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
@@ -399,15 +425,19 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes of this kernel come from an ncu --set full capture (never from a timed run): the committed figure of the
+    # same launch at N = 1; a row shard at N > 1 is a different launch and has no capture, so it reports null
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.shape)
+    if os.path.exists(tpath) and world == 1:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get(args.shape), tj.get("source")
     roofline = {"kernel": "spmm_tile_kernel<16> (hub-chunk tiles + row tiles in one launch) = one ngcf_spmm call: "
                           "layer 0 of the step, node-dropout survivors (p = 0.3) compacted"
                           + (f", row shard of rank 0 of {world}" if world > 1 else ""),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": alg_bytes,
                 "entries_gathered": nnz_kept, "kernel_ms": round(k_ms, 5), "peak_source": peak_src,
                 "timing": "CUDA events around the call, cold L2 (flushed), mean of 20",
                 "l2_gather_tb_s": round(nnz_kept * 4 * d / (k_ms * 1e-3) / 1e12, 2),
@@ -434,9 +464,14 @@ def run_ours(args):
             log(f"[breakdown] {k:28s} {v['ms_per_step']:8.4f} ms/step  x{v['calls_per_step']:.0f}")
 
     # ---- CPU baseline beside it ------------------------------------------------------------------------------
-    cpu = None
+    cpu, torch_cuda = None, None
     if not args.no_cpu_baseline and world == 1:
-        cpu = time_oracle(L, batches, info, max_steps=40, warmup=1, budget_s=15.0)
+        try:
+            torch_cuda = time_torch_cuda(L, batches, info, dev)
+            torch_cuda["speedup_of_value"] = round(torch_cuda["ms_per_step"] / ms_per_step, 2)
+        except Exception as e:
+            log(f"[bench] torch-CUDA baseline failed ({type(e).__name__}: {e})")
+        cpu = time_cpu_reference(L, batches, info, max_steps=40, warmup=1, budget_s=15.0)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -451,11 +486,13 @@ def run_ours(args):
         "metric": METRIC, "value": round(ms_per_step * spe / 1e3, 6), "unit": "s/epoch", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": info["workload"], "steps_per_epoch": spe, "nnz": int(L._nnz()), "N": int(L.shape[0]),
-                   "parallelism": "single GPU" if world == 1 else
-                   f"row-sharded x{world} (equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads)",
-                   "rng": "device (counter-based hash); node-dropout survivors compacted once per step", "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
-                   "api": api},
+        "config": {"workload": info["workload"], "steps_per_epoch": spe},       # the same dict in both arms
+        "run": {"nnz": int(L._nnz()), "N": int(L.shape[0]),
+                "parallelism": "single GPU" if world == 1 else
+                f"row-sharded x{world} ({model.exchange_description()})",
+                "rng": "device (counter-based hash); node-dropout survivors compacted once per step",
+                "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)", "api": api},
+        "parity_vs_1gpu": parity,
         "e2e": {"value": round(ms_e2e * spe / 1e3, 6), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 5),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_val},
         "warm_ms_per_step": round(ms_warm, 5),
@@ -463,7 +500,8 @@ def run_ours(args):
                   "api": "drop-in NGCF.forward + BPR + loss.backward() issued eagerly from Python"},
         "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
         "gpu_launches_note": "library kernels per step (captured once, replayed per step under GraphedStep)",
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "training_iteration_with_adam": with_adam,
+        "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": torch_cuda, "clocks": clocks,
+        "training_iteration_with_adam": with_adam,
         "measured_epoch": measured_epoch,
     }
     if breakdown:
@@ -533,8 +571,132 @@ def run_epoch(pkg, gstep_opt, info, dev):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference's CPU torch.sparse path
+# reference arm / CPU baseline / torch-CUDA bar
 # ------------------------------------------------------------------------------------------------------------
+def load_reference_modules():
+    """(NGCF, BPR) classes of the UNMODIFIED reference from baseline/_ref/model (installed by baseline/install_ref.py at
+    build time; it ships to the GPU box), or None when that install is absent."""
+    import importlib.util
+    from baseline.install_ref import ref_dir
+    d = ref_dir()
+    if d is None:
+        return None
+    out = []
+    for name, cls in (("NGCF", "NGCF"), ("bprloss", "BPR")):
+        spec = importlib.util.spec_from_file_location("ngcf_reference_" + name, os.path.join(d, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out.append(getattr(mod, cls))
+    return tuple(out)
+
+
+def time_reference_modules(mods, L, batches, info, device, max_steps, warmup, budget_s, threads=None):
+    """The reference's own training step (experiment.py:45-57: model(...), criterion, zero_grad, backward) issued through
+    its unmodified NGCF / BPR modules on ``device``.  emb % 5 != 0 crashes the stock module (NGCF.py:110-114), so — as for
+    the golden vectors — the dow table of the INSTANCE is widened to absorb the remainder; the
+    reference's forward then runs unmodified."""
+    import torch.nn as nn
+    from seoul_tourism_recommendation_ngcf_b200 import synth
+    RefNGCF, RefBPR = mods
+    if threads:
+        torch.set_num_threads(threads)
+    emb, K = info["emb"], info["layers"]
+    dev = torch.device(device)
+    torch.manual_seed(0)
+    Ld = L.to(dev)
+    m = RefNGCF(emb, [emb] * K, NODE_P, [MESS_P] * K, 1.0, [Ld, Ld], synth.num_dict_for(info["n_user"], info["n_item"]),
+                BATCH, dev)
+    if emb % 5:
+        m.dow_emb = nn.Embedding(synth.FEATURE_CARD["dayofweek"], emb - 4 * (emb // 5))
+        nn.init.kaiming_uniform_(m.dow_emb.weight)
+    m = m.to(dev).train()
+    crit = RefBPR(WEIGHT_DECAY, BATCH).to(dev)
+
+    def one(j):
+        b = {k: torch.from_numpy(v).to(dev) for k, v in batches[j % len(batches)].items()}
+        u, p, n = m(year=b["year"], u_id=b["u_id"], age=b["age"], sex=b["sex"], month=b["month"], day=b["day"],
+                    dow=b["dow"], pos_item=b["pos_item"], neg_item=b["neg_item"], node_flag=True)
+        m.zero_grad()
+        loss = crit(u, p, n)
+        loss.backward()
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        return loss
+
+    t_start = time.time()
+    for j in range(warmup):
+        one(j)
+    ts = []
+    for j in range(max_steps):
+        t0 = time.time()
+        one(warmup + j)
+        ts.append(time.time() - t0)
+        if time.time() - t_start > budget_s and len(ts) >= 1:
+            break
+    return statistics.mean(ts), len(ts)
+
+
+def time_cpu_reference(L, batches, info, max_steps, warmup, budget_s):
+    """CPU arm: the unmodified reference modules when installed (kind "reference"), else the oracle port ("port")."""
+    mods = None
+    try:
+        mods = load_reference_modules()
+    except Exception as e:
+        log(f"[bench] reference modules not loadable ({type(e).__name__}: {e}); using the oracle port")
+    if mods is None:
+        return time_oracle(L, batches, info, max_steps, warmup, budget_s)
+    cores = os.cpu_count() or 1
+    s, n = time_reference_modules(mods, L, batches, info, "cpu", max_steps, warmup, budget_s, threads=cores)
+    single = None
+    if cores > 1:                    # the reference's COO SpMM does not scale with threads (SURVEY.md section 8(d))
+        s1, _ = time_reference_modules(mods, L, batches, info, "cpu", 2, 0, 1e9, threads=1)
+        torch.set_num_threads(cores)
+        single = {"ms_per_step": round(s1 * 1e3, 2), "cores": 1, "sample": "mean of 2 steps"}
+    return {"value": round(s * info["steps_per_epoch"], 3), "unit": "s/epoch", "ms_per_step": round(s * 1e3, 2),
+            "cores": cores, "kind": "reference", "single_thread": single,
+            "sample": f"{n} full training steps (of {info['steps_per_epoch']} per epoch) of the same workload, {warmup} "
+                      f"warm-up; the reference's unmodified NGCF.py / bprloss.py (baseline/_ref) on device='cpu': "
+                      f"torch.sparse COO mm + host float64 node-dropout mask + autograd"}
+
+
+def time_torch_cuda(L, batches, info, dev, steps=20, warmup=3):
+    """"the reference on the same B200 (device='cuda', cuSPARSE path) - the bar the kernels must
+    beat".  The unmodified reference modules on the GPU when installed and runnable there, else the oracle's restatement
+    of the same torch calls with its tensors on the GPU."""
+    try:
+        mods = load_reference_modules()
+        if mods is not None:
+            s, n = time_reference_modules(mods, L, batches, info, dev, steps, warmup, 60.0)
+            return {"ms_per_step": round(s * 1e3, 4), "value": round(s * info["steps_per_epoch"], 4), "unit": "s/epoch",
+                    "kind": "reference", "steps": n,
+                    "what": "the reference's unmodified NGCF.py / bprloss.py with device='cuda' (lap_list resident on the "
+                            "GPU): host float64 node mask + index ops, coalesce + cusparse SpMM, cuBLAS Linear, autograd; "
+                            "wall clock per step with a device sync, same batches and shapes as `value`"}
+    except Exception as e:
+        log(f"[bench] reference modules on cuda failed ({type(e).__name__}: {e}); timing the oracle restatement on cuda")
+    from oracle import ngcf_oracle as O
+    model = make_model(info, L, torch.device("cpu"))
+    params = {k: v.detach().clone().to(dev) for k, v in model.state_dict().items()}
+    K, N = info["layers"], info["n_user"] + info["n_item"]
+    Ld = L.to(dev)
+    ts = []
+    for j in range(warmup + steps):
+        b = {k: torch.from_numpy(v).to(dev) for k, v in batches[j % len(batches)].items()}
+        t0 = time.time()
+        keep, mult = O.reference_dropout_draws(L._nnz(), N, [info["emb"]] * K, NODE_P, [MESS_P] * K, True, True)
+        keep = [k_.to(dev) for k_ in keep] if keep is not None else None
+        mult = [m_.to(dev) for m_ in mult] if mult is not None else None
+        O.train_step(params, Ld, b, emb_ratio=1.0, weight_decay=WEIGHT_DECAY, batch_size_ctor=BATCH, edge_keep=keep,
+                     mess_mult=mult)
+        torch.cuda.synchronize(dev)
+        if j >= warmup:
+            ts.append(time.time() - t0)
+    s = statistics.mean(ts)
+    return {"ms_per_step": round(s * 1e3, 4), "value": round(s * info["steps_per_epoch"], 4), "unit": "s/epoch",
+            "kind": "port", "steps": len(ts),
+            "what": "oracle/ngcf_oracle.py (the reference's torch calls, line by line) with its tensors on the GPU"}
+
+
 def time_oracle(L, batches, info, max_steps, warmup, budget_s):
     from oracle import ngcf_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
@@ -583,12 +745,13 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     L, batches, info = make_workload(args.shape)
-    res = time_oracle(L, batches, info, max_steps=args.steps, warmup=min(args.warmup, 2), budget_s=200.0)
+    res = time_cpu_reference(L, batches, info, max_steps=args.steps, warmup=min(args.warmup, 2), budget_s=200.0)
     spe = info["steps_per_epoch"]
     out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "s/epoch", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": False,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": info["workload"], "steps_per_epoch": spe, "device": "cpu"},
+           "config": {"workload": info["workload"], "steps_per_epoch": spe},
+           "run": {"device": "cpu", "kind": res["kind"], "cores": res["cores"]},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

@@ -29,8 +29,8 @@ def _stream() -> int:
 
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
-    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "comp_b_stream", "mess_bits",
-                 "rows", "offsets", "W1", "W2")
+    __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
+                 "rows", "offsets", "W1", "W2", "fresh_key")
 
 
 class _Propagate(torch.autograd.Function):
@@ -51,31 +51,20 @@ class _Propagate(torch.autograd.Function):
         N = mod.n_user + mod.n_item
         r0, nloc, nv = (sh.r0, sh.rows, sh.valid) if sh is not None else (0, N, N)
         X0 = mod._packed_table()                                       # [N(_pad), d0] = cat(user, item), NGCF.py:120
+        if mod._snapshot:                                              # the reference's cat() is a copy: opt-in here
+            X0 = X0.clone()
         st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
-        st.bits_f = st.bits_b = st.comp_f = st.comp_b = st.comp_b_stream = None
+        st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
             # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
             # deletes the dropped entries like NGCF.sparse_dropout does, so layer k gathers (1-p)^(k+1) of the rows
             shared = st.plan.side(True, False) is side
             if mod._node_mode == "compact":
-                if mod._overlap and torch.is_grad_enabled():
-                    # the forward needs L's survivors now; L^T's are first used by the backward, so that half of the
-                    # pass runs on a side stream next to the forward (joined in backward)
-                    main = torch.cuda.current_stream()
-                    if mod._side_stream is None:
-                        mod._side_stream = torch.cuda.Stream()
-                    mod._side_stream.wait_stream(main)
-                    with torch.cuda.stream(mod._side_stream):
-                        _, st.comp_b = node_dropout_compact(st.plan.side(True, False), st.drop_p, st.seed, st.seed_dev, K,
-                                                            r0, as_L=False, as_Lt=True)
-                    st.comp_b_stream = mod._side_stream
-                    st.comp_f, _ = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=False)
-                else:
-                    st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
-                    if shared:
-                        st.comp_b = ct
+                st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
+                if shared:
+                    st.comp_b = ct
             elif mod._node_mode == "bits":
                 st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
                 if shared:
@@ -134,6 +123,7 @@ class _Propagate(torch.autograd.Function):
     def backward(ctx, *gouts):
         lib = _lib.load()
         st, mod, n_sets = ctx.st, ctx.mod, ctx.n_sets
+        mod._check_fresh(st, "loss.backward()")
         K, dims = mod.n_layer, st.dims
         dev = st.E[0].device
         sh = mod._shard
@@ -164,9 +154,6 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
-        if st.comp_b_stream is not None:                              # L^T's survivors were compacted next to the forward
-            torch.cuda.current_stream().wait_stream(st.comp_b_stream)
-            st.comp_b_stream = None
         if st.drop_p > 0 and mod._node_mode == "compact" and st.comp_b is None:
             _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         if st.drop_p > 0 and mod._node_mode == "bits" and st.bits_b is None:
@@ -221,10 +208,14 @@ class NGCF(nn.Module):
     rng : "device" (default) draws node- and message-dropout decisions in-kernel from a counter-based hash stream keyed
           on a per-forward seed taken from torch's CPU generator;  "reference" reproduces the reference's host
           float64 ``nn.Dropout`` node mask bit for bit (NGCF.py:94) at its host cost.
+    snapshot : False (default) keeps E_0 = the live parameter table (zero copy); a second forward or an optimizer step
+          before ``backward()`` / before reading ``all_users_emb`` then raises.  True copies the table per forward, which
+          is what the reference's ``torch.cat`` (NGCF.py:120) does, and lifts that restriction.
     """
 
     def __init__(self, embed_size: int, layer_size: list, node_dropout: float, mess_dropout: list,
-                 emb_ratio: float, lap_list: list, num_dict: dict, batch_size: int, device, *, rng: str = "device"):
+                 emb_ratio: float, lap_list: list, num_dict: dict, batch_size: int, device, *, rng: str = "device",
+                 snapshot: bool = False):
         super().__init__()
         if rng not in ("device", "reference"):
             raise ValueError("rng must be 'device' or 'reference'")
@@ -264,10 +255,14 @@ class NGCF(nn.Module):
         self._all_E = None
         self._mess_bits = os.environ.get("NGCF_B200_MESS_BITS", "0") == "1"   # precompute message-dropout bits per step
         self._node_mode = "compact"   # device-RNG node dropout: "compact" (survivors only), "bits", or "inkernel"
-        # L^T's half of the compaction pass on a side stream next to the forward: measured SLOWER (650 vs 632 us per
-        # step at Gowalla shape: the forward's kernels are throughput-bound, the extra pass re-reads the entries)
-        self._overlap = os.environ.get("NGCF_B200_OVERLAP", "0") == "1"
-        self._side_stream = None
+        # E_0 of a forward is the LIVE packed table, not a copy (the reference's torch.cat at NGCF.py:120 copies 2 x 18 MB
+        # per step at Gowalla shape).  A later forward (its feature mix rewrites user rows) or an optimizer step changes it
+        # under a pending backward / under all_users_emb: that is detected and refused (_check_fresh).  snapshot=True (or
+        # NGCF_B200_SNAPSHOT=1) copies the table per forward instead and lifts the restriction.
+        self._snapshot = bool(snapshot) or os.environ.get("NGCF_B200_SNAPSHOT", "0") == "1"
+        self._mix_count = 0
+        self._seed_gen = None    # rng="reference": private generator for the device-RNG key (message dropout), so the
+                                 # CPU generator is consumed by the node masks only, exactly like the reference's stream
         self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None
@@ -313,6 +308,11 @@ class NGCF(nn.Module):
         self._group = group
         self._plans, self._table, self._slot = {}, None, None
         return self
+
+    def exchange_description(self) -> str:
+        if self._shard is None:
+            return "single GPU"
+        return "equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads"
 
     # ---- internal buffers ---------------------------------------------------------------------------
     def _packed_table(self) -> torch.Tensor:
@@ -361,6 +361,7 @@ class NGCF(nn.Module):
         return out
 
     # ---- forward ---------------------------------------------------------------------------------------
+    @_lib.on_device
     def forward(self, year, u_id, age, sex, month, day, dow, pos_item, neg_item, node_flag):
         lib = _lib.load()
         dev = self.user_embedding.weight.device
@@ -387,7 +388,9 @@ class NGCF(nn.Module):
                                         u_id.numel(), float(self.emb_ratio), self._winner.data_ptr(), _stream()),
                    "feature_mix")                                            # NGCF.py:103-115
 
+        self._mix_count += 1
         st = _Ctx()
+        st.fresh_key = self._fresh_key()
         st.plan = plan = self._plan(year_idx, dev)
         if self._shard is not None and "edge_keep" in (self._inject or {}):
             raise ValueError("explicit edge masks are not supported in row-sharded mode")
@@ -418,7 +421,14 @@ class NGCF(nn.Module):
         # per-forward RNG key from torch's CPU generator (reproducible under torch.manual_seed); drawn only when
         # a device-RNG stream is live and only after the reference-mode mask draws, whose RNG stream it must not shift
         need_seed = st.drop_p > 0 or any(p > 0 for p in st.mess_p)
-        st.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0
+        if not need_seed:
+            st.seed = 0
+        elif self.rng == "reference":
+            if self._seed_gen is None:
+                self._seed_gen = torch.Generator().manual_seed(torch.initial_seed() & (2 ** 63 - 1))
+            st.seed = int(torch.randint(0, 2 ** 62, (1,), generator=self._seed_gen).item())
+        else:
+            st.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         # CUDA-graph mode (graph.GraphedStep): the launches are frozen, so the per-step key comes from a device counter
         st.seed_dev = self._seed_dev if need_seed else None
         if masks is not None:
@@ -436,10 +446,26 @@ class NGCF(nn.Module):
         return u_embeddings, pos_i_embeddings, neg_i_embeddings
 
     # ---- attributes the reference sets in forward (NGCF.py:147-149), materialised on first read ---------
+    def _fresh_key(self):
+        return (self._mix_count, _lib.param_epoch(), self.user_embedding.weight._version,
+                self.item_embedding.weight._version)
+
+    def _check_fresh(self, st, what: str):
+        """E_0 of a forward is the live table (see __init__): refuse to use it once something changed the table."""
+        if self._snapshot or st.fresh_key == self._fresh_key():
+            return
+        why = "the step that produced it also ran the optimizer" if st.fresh_key is None else \
+            "another forward (feature mix) or an optimizer step ran since"
+        raise RuntimeError(f"NGCF (B200): {what} needs the embedding table as the forward left it, but {why}. "
+                           "Run the forward again, or construct the module with snapshot=True to keep a per-forward "
+                           "copy like the reference's torch.cat (NGCF.py:120).")
+
+    @_lib.on_device
     def _materialize(self):
         if self._last is None:
             raise AttributeError("all_users_emb / all_items_emb exist after the first forward (NGCF.py:148-149)")
         if self._all_E is None:
+            self._check_fresh(self._last, "all_users_emb / all_items_emb")
             st, lib = self._last, _lib.load()
             N, D = self.n_user + self.n_item, sum(st.dims)
             out = torch.empty(N, D, dtype=torch.float32, device=st.E[0].device)

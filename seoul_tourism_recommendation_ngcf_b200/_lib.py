@@ -115,6 +115,48 @@ def i64_array(vals):
     return (_i64 * len(vals))(*[int(v) for v in vals])
 
 
+# bumped by every in-place parameter update this package performs behind torch's back (Adam through raw pointers, a
+# CUDA-graph replay that contains it): NGCF compares it between forward and backward / all_*_emb (NGCF._check_fresh)
+_param_epoch = 0
+
+
+def bump_param_epoch() -> None:
+    global _param_epoch
+    _param_epoch += 1
+
+
+def param_epoch() -> int:
+    return _param_epoch
+
+
+def on_device(fn):
+    """Decorator for the kernel-launching entry points: runs ``fn`` with the CUDA device of its first CUDA tensor (or
+    module) argument current.  Kernels launch on, and ``current_stream()`` reads, the CURRENT device — a module built on
+    cuda:1 must not launch on cuda:0 just because that is torch's current device."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor):
+                if a.device.type == "cuda":
+                    dev = a.device
+                    break
+            elif isinstance(a, torch.nn.Module):
+                q = next(a.parameters(), None)
+                if q is not None and q.device.type == "cuda":
+                    dev = q.device
+                    break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def current_stream() -> int:
     """Raw cudaStream_t of torch's current stream on the current device.  (torch.cuda.current_stream() resolves the
     device through several Python layers: ~24 calls per eager step were a quarter of its host time.)"""

@@ -37,6 +37,7 @@ class BPR(nn.Module):
         self.weight_decay = weight_decay
         self.batch_size = batch_size          # the divisor is this ctor value, not the row count (bprloss.py:22)
 
+    @_lib.on_device
     def forward(self, u_idx, pos_idx, neg_idx):
         if u_idx.device.type != "cuda":
             raise RuntimeError("BPR (B200) runs on CUDA tensors only; there is no CPU fallback")

@@ -20,6 +20,7 @@ import torch.nn as nn
 from . import _lib
 
 
+@_lib.on_device
 def eval_groups(u_embeds, item_embeds, item_ids, rating, *, group=None, group_ptr=None, ks, weight_decay, batch_size,
                 k_hr=3, return_per_group=False):
     """The metric block of experiment.py:92-116 for every test batch at once.

@@ -32,7 +32,12 @@ class GraphedStep:
         # joins the graph, so a replay is the reference's whole training iteration
         self.optimizer = optimizer
         self.static_idx = torch.zeros(len(FIELDS), self.B, dtype=torch.int64, device=dev)
-        self.stage = torch.zeros(len(FIELDS), self.B, dtype=torch.int64).pin_memory()
+        # pinned staging buffers for host batches, rotated: the H2D copy below is asynchronous, so a buffer may only be
+        # rewritten once the copy that read it has run (its event); with one buffer a host running ahead of the GPU
+        # would overwrite a batch that is still waiting to be copied
+        self.stages = [torch.zeros(len(FIELDS), self.B, dtype=torch.int64).pin_memory() for _ in range(3)]
+        self.stage_events = [None] * len(self.stages)
+        self._stage_i = 0
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.graphs = {}
         self.launches_per_step = None
@@ -79,16 +84,29 @@ class GraphedStep:
         year = batch["year"]
         if year.device.type != "cpu":
             raise ValueError("GraphedStep: pass `year` as a host tensor (it is only used to pick lap_list[year % 18])")
+        on_host = [batch[k].device.type == "cpu" for k in FIELDS]
+        stage = None
+        if any(on_host):
+            j = self._stage_i
+            self._stage_i = (j + 1) % len(self.stages)
+            if self.stage_events[j] is not None:
+                self.stage_events[j].synchronize()                    # the copy that last read this buffer has run
+            stage = self.stages[j]
         for i, k in enumerate(FIELDS):
             t = batch[k]
             if t.numel() != self.B:
                 raise ValueError(f"GraphedStep was built for batches of {self.B} rows, got {t.numel()} for {k}")
-            if t.device.type == "cpu":
-                self.stage[i].copy_(t)
-            else:
-                self.static_idx[i].copy_(t, non_blocking=True)
-        if batch["u_id"].device.type == "cpu":
-            self.static_idx.copy_(self.stage, non_blocking=True)      # one pinned H2D copy for the whole batch
+            if on_host[i]:
+                stage[i].copy_(t)
+        if all(on_host):
+            self.static_idx.copy_(stage, non_blocking=True)           # one pinned H2D copy for the whole batch
+        else:
+            for i, k in enumerate(FIELDS):
+                self.static_idx[i].copy_(stage[i] if on_host[i] else batch[k], non_blocking=True)
+        if stage is not None:
+            if self.stage_events[j] is None:
+                self.stage_events[j] = torch.cuda.Event()
+            self.stage_events[j].record()
         key = int(year.min()) % 18
         entry = self.graphs.get(key)
         if entry is None:                                             # first batch of this Laplacian: `warmup` eager
@@ -96,6 +114,13 @@ class GraphedStep:
         g, loss, grads, last = entry
         g.replay()
         self.model._last, self.model._all_E = last, None              # all_users_emb / all_items_emb: rebuild on read
+        if self.optimizer is not None:
+            from . import _lib
+            _lib.bump_param_epoch()                                   # the replay stepped the parameters
+            last.fresh_key = None                                     # ... so E_0 (the live table) no longer matches H_k
+        else:
+            self.model._mix_count += 1                                # the replay ran the feature mix
+            last.fresh_key = self.model._fresh_key()
         for k, p in self.model.named_parameters():                    # survive an optimizer.zero_grad(set_to_none=True)
             if k in grads and p.grad is not grads[k]:
                 p.grad = grads[k]

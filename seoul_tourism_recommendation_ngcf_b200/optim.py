@@ -45,34 +45,46 @@ class Adam(torch.optim.Optimizer):
                 loss = closure()
         lib = _lib.load()
         capturing = torch.cuda.is_current_stream_capturing() if torch.cuda.is_available() else False
-        for group in self.param_groups:
-            ps = [p for p in group["params"] if p.grad is not None]
-            if not ps:
-                continue
-            dev = ps[0].device
-            if dev.type != "cuda":
-                raise RuntimeError("ngcf_b200 Adam runs on CUDA parameters only (no CPU fallback)")
-            if self._step_dev is None or self._step_dev.device != dev:
-                done = int(self.state[ps[0]]["step"]) if self.state[ps[0]] else 0
-                self._step_dev = torch.full((1,), done, dtype=torch.int64, device=dev)
-            self._step_dev.add_(1)                                    # t of this update, on the device
-            for i in range(0, len(ps), 32):
-                chunk = ps[i:i + 32]
-                sts = [self._state(p) for p in chunk]
-                for p in chunk:
-                    if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                        raise RuntimeError("ngcf_b200 Adam needs contiguous fp32 parameters and gradients")
-                _lib.check(lib.ngcf_adam_step(_lib.ptr_array(chunk), _lib.ptr_array([p.grad for p in chunk]),
-                                              _lib.ptr_array([s["exp_avg"] for s in sts]),
-                                              _lib.ptr_array([s["exp_avg_sq"] for s in sts]),
-                                              _lib.i64_array([p.numel() for p in chunk]), len(chunk),
-                                              float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
-                                              float(group["eps"]), float(group["weight_decay"]), 0,
-                                              self._step_dev.data_ptr(), int(zero_grads),
-                                              _lib.current_stream()), "adam_step")
-            if not capturing:
-                for p in ps:
-                    self.state[p]["step"] += 1
+        groups = [(g, [p for p in g["params"] if p.grad is not None]) for g in self.param_groups]
+        live = [p for _, ps in groups for p in ps]
+        if not live:
+            return loss
+        dev = live[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("ngcf_b200 Adam runs on CUDA parameters only (no CPU fallback)")
+        # ONE step counter for the whole optimizer (it lives on the device so that a captured CUDA graph advances it on
+        # every replay): torch.optim.Adam keeps `step` per parameter, which only differs from a shared counter when a
+        # parameter receives its first gradient later than the others — refused here rather than silently mis-corrected
+        done = {int(self.state[p]["step"]) if self.state[p] else 0 for p in live}
+        if len(done) > 1 and not capturing:
+            raise RuntimeError("ngcf_b200 Adam keeps one step count for all parameters, but the parameters that carry "
+                               f"gradients have been stepped {sorted(done)} times (a parameter whose first gradient "
+                               "arrives late needs torch.optim.Adam)")
+        if self._step_dev is None or self._step_dev.device != dev:
+            self._step_dev = torch.full((1,), max(done), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            self._step_dev.add_(1)                                    # t of this update: once per step(), not per group
+            for group, ps in groups:
+                for i in range(0, len(ps), 32):
+                    chunk = ps[i:i + 32]
+                    sts = [self._state(p) for p in chunk]
+                    for p in chunk:
+                        if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                            raise RuntimeError("ngcf_b200 Adam needs contiguous fp32 parameters and gradients")
+                        if p.device != dev:
+                            raise RuntimeError("ngcf_b200 Adam: all parameters must live on one CUDA device")
+                    _lib.check(lib.ngcf_adam_step(_lib.ptr_array(chunk), _lib.ptr_array([p.grad for p in chunk]),
+                                                  _lib.ptr_array([s["exp_avg"] for s in sts]),
+                                                  _lib.ptr_array([s["exp_avg_sq"] for s in sts]),
+                                                  _lib.i64_array([p.numel() for p in chunk]), len(chunk),
+                                                  float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
+                                                  float(group["eps"]), float(group["weight_decay"]), 0,
+                                                  self._step_dev.data_ptr(), int(zero_grads),
+                                                  _lib.current_stream()), "adam_step")
+        _lib.bump_param_epoch()                                       # forwards still waiting for their backward are stale
+        if not capturing:
+            for p in live:
+                self.state[p]["step"] += 1
         return loss
 
     def state_dict(self):

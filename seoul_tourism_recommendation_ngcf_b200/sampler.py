@@ -22,6 +22,7 @@ from . import _lib
 CONTEXT_COLS = ("year", "userid", "age", "sex", "month", "day", "dayofweek")      # utils.py:242-248
 
 
+@_lib.on_device
 def sample_negatives(pos_ptr, pos_idx, row_user, candidates, ng_ratio: int, seed: int):
     """out[r, :] = ng_ratio distinct entries of ``candidates`` outside user row_user[r]'s positive list
     (pos_idx[pos_ptr[u]:pos_ptr[u+1]] = ascending unique candidate indices).  CUDA tensors in, CUDA int64 [R, ng] out."""

@@ -9,6 +9,7 @@ import torch
 from . import _lib
 
 
+@_lib.on_device
 def score_topk(u_embeds: torch.Tensor, item_embeds: torch.Tensor, k: int):
     """Returns (values [U,k] fp32, indices [U,k] int64), descending, like ``torch.topk(u @ items.T, k)``."""
     if u_embeds.device.type != "cuda" or item_embeds.device.type != "cuda":

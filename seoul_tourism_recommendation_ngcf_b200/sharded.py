@@ -88,3 +88,38 @@ def all_gather_rows(out: torch.Tensor, shard: torch.Tensor, group=None):
         rows = shard.shape[0]
         dist.all_gather([out[r * rows:(r + 1) * rows] for r in range(world)], shard, group=group)
     return out
+
+
+def parity_vs_unsharded(emb: int, layers: list, L: torch.Tensor, num_dict: dict, batch: dict, batch_size: int, device,
+                        node_p: float = 0.3, mess_p: float = 0.1, weight_decay: float = 0.025, group=None) -> dict:
+    """Runs ONE training step (forward + BPR + backward, node and message dropout ON, device RNG) twice on this rank's
+    GPU — unsharded, and row-sharded over the ranks of ``group`` — and returns the relative differences
+    ``{out, loss, all_E, worst_grad}`` (max|a-b| / max|b|).  The dropout keys are global coordinates, so both runs draw
+    the same masks and the sharded step must reproduce the 1-GPU step (reference semantics: NGCF.py:102-156 computed
+    once over the whole graph).  Collective: every rank of the group must call it with the same arguments."""
+    from .NGCF import NGCF
+    from .bprloss import BPR
+    res = []
+    b = {k: (v if k == "year" else v.to(device)) for k, v in batch.items()}
+    for sharded in (False, True):
+        torch.manual_seed(0)
+        m = NGCF(emb, list(layers), node_p, [mess_p] * len(layers), 1.0, [L, L], num_dict, batch_size, device).to(device)
+        if sharded:
+            m.shard(group)
+        m.train()
+        torch.manual_seed(7)
+        uu, pp, nn_ = m(b["year"], b["u_id"], b["age"], b["sex"], b["month"], b["day"], b["dow"], b["pos_item"],
+                        b["neg_item"], True)
+        loss = BPR(weight_decay, batch_size)(uu, pp, nn_)
+        loss.backward()
+        torch.cuda.synchronize(device)
+        res.append((uu.detach(), float(loss), {k: p.grad for k, p in m.named_parameters() if p.grad is not None},
+                    m.all_users_emb.clone(), m.all_items_emb.clone()))
+        del m
+
+    def rel(a, c):
+        return float((a - c).abs().max() / c.abs().max().clamp_min(1e-30))
+    (u0, l0, g0, a0, i0), (u1, l1, g1, a1, i1) = res
+    return {"out": rel(u1, u0), "loss": abs(l1 - l0) / max(abs(l0), 1e-30),
+            "all_E": max(rel(a1, a0), rel(i1, i0)), "worst_grad": max(rel(g1[k], g0[k]) for k in g0),
+            "loss_value": l0, "world": dist.get_world_size(group) if dist.is_initialized() else 1}
