@@ -12,8 +12,10 @@
 // completed (tcgen05.commit -> empty[kb]); the accumulator is double buffered in TMEM so the epilogue of tile t
 // overlaps the loads and MMAs of tile t+1.
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc.cuh"
+#include "tmap.h"
 
 namespace {
 
@@ -88,6 +90,92 @@ static inline int mess_mode(const float* mess_mult, const uint32_t* mess_bits, f
     return mess_mult ? MM_MULT : (mess_p > 0.f ? (mess_bits ? MM_BITS : MM_HASH) : MM_NONE);
 }
 
+// ======================= forward epilogue role (8 warps) =================================================================
+// TMEM lane = tile row, so a thread holds one row of its chunk; the 32x32 block goes through a per-warp transposition
+// buffer so that bias + LeakyReLU + dropout run, and the stores are issued, in a coalesced layout.
+template <int MM>
+__device__ __forceinline__ void fwd_epilogue_role(const FwdTcArgs& a, float* stage, const float* bias_s, uint64_t* tmem_full,
+                                                  uint64_t* tmem_empty, uint32_t tmem_base, int n_my, int warp, int lane,
+                                                  bool dbg) {
+    const int d_out = a.d_out;
+    // ======================= epilogue =======================================================================
+    // TMEM lane = tile row, so a thread holds one row of its chunk; bias + LeakyReLU + dropout are applied in that
+    // layout, then the 32x32 block goes through a per-warp transposition buffer so the stores are coalesced.
+    const uint64_t seed = MM == MM_HASH ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
+    const uint32_t thr = ngcf_threshold16(a.mess_p);
+    float* st = stage + warp * 32 * 32;
+    const int quarter = warp & 3, c = warp >> 2;                      // TMEM lanes 32*quarter.., columns 32*c..
+    const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
+    const bool has_chunk = c * 32 < d_out;
+    const float inv_keep = 1.0f / (1.0f - a.mess_p);
+    for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int buf = it & 1;
+        BWD_STAMP(0, it, 0);
+        mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+        BWD_STAMP(0, it, 1);
+        tc_fence_after_sync();
+        float v[32];
+        if (has_chunk) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 64 + c * 32, v);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);           // accumulator drained: next tile may reuse it
+        if (!has_chunk) continue;
+        const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
+        // raw accumulators through the per-warp transposition buffer; everything else happens in the coalesced
+        // layout (thread = 4 consecutive columns of rows i * 4 + rr): partial sums of an earlier K block, bias,
+        // LeakyReLU, dropout (one RNG call = exactly the thread's four columns), store
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            st_f4(st + stage_off(lane, j >> 2), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        __syncwarp();
+        float4 r4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + stage_off(i * 4 + rr, c4));
+        __syncwarp();
+        const int col = c * 32 + c4 * 4;                              // within the block's d_out columns
+        if (col < d_out) {
+            const int gcol = a.out_off + col;                         // within the layer's d_out_full columns
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
+            const int words = (a.d_out_full + 31) >> 5;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = row_base + i * 4 + rr;
+                if (row >= a.n_rows) continue;
+                float* dst = a.E_out + row * a.d_out_full + gcol;
+                float4 x = r4[i];
+                if (a.mode == FW_PARTIAL) {
+                    st_f4(dst, x);
+                    continue;
+                }
+                if (a.mode == FW_FINAL) {
+                    const float4 prev = ld_f4(dst);
+                    x.x += prev.x; x.y += prev.y; x.z += prev.z; x.w += prev.w;
+                }
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                x.x = x.x > 0.f ? x.x : a.slope * x.x;                // LeakyReLU, NGCF.py:140
+                x.y = x.y > 0.f ? x.y : a.slope * x.y;
+                x.z = x.z > 0.f ? x.z : a.slope * x.z;
+                x.w = x.w > 0.f ? x.w : a.slope * x.w;
+                if (MM == MM_BITS) {
+                    const uint32_t w = a.mess_bits[row * words + (gcol >> 5)] >> (gcol & 31);
+                    x.x = w & 1u ? x.x * inv_keep : 0.f; x.y = w & 2u ? x.y * inv_keep : 0.f;
+                    x.z = w & 4u ? x.z * inv_keep : 0.f; x.w = w & 8u ? x.w * inv_keep : 0.f;
+                } else if (MM == MM_HASH) {
+                    const float4 mm = mess_multiplier4_pre(thr, inv_keep, seed, a.layer,
+                                                           (uint64_t)((row + a.row_off) * a.d_out_full + gcol) >> 2);
+                    x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+                } else if (MM == MM_MULT) {
+                    const float4 mm = ld_f4(a.mess_mult + row * a.d_out_full + gcol);
+                    x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+                }
+                st_f4(dst, x);
+            }
+        }
+        BWD_STAMP(0, it, 2);
+    }
+}
+
 template <int MM>
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -149,82 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();
 
     if (warp < FW_EPI_WARPS) {
-        // ======================= epilogue =======================================================================
-        // TMEM lane = tile row, so a thread holds one row of its chunk; bias + LeakyReLU + dropout are applied in that
-        // layout, then the 32x32 block goes through a per-warp transposition buffer so the stores are coalesced.
-        const uint64_t seed = MM == MM_HASH ? ngcf_seed(a.seed, a.seed_dev) : 0ull;
-        const uint32_t thr = ngcf_threshold16(a.mess_p);
-        float* st = stage + warp * 32 * 32;
-        const int quarter = warp & 3, c = warp >> 2;                      // TMEM lanes 32*quarter.., columns 32*c..
-        const int rr = lane >> 3, c4 = lane & 7;                          // read-back mapping: 4 rows x 8 float4
-        const bool has_chunk = c * 32 < d_out;
-        const float inv_keep = 1.0f / (1.0f - a.mess_p);
-        for (int it = 0; it < n_my; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int buf = it & 1;
-            BWD_STAMP(0, it, 0);
-            mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
-            BWD_STAMP(0, it, 1);
-            tc_fence_after_sync();
-            float v[32];
-            if (has_chunk) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 64 + c * 32, v);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);           // accumulator drained: next tile may reuse it
-            if (!has_chunk) continue;
-            const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
-            // raw accumulators through the per-warp transposition buffer; everything else happens in the coalesced
-            // layout (thread = 4 consecutive columns of rows i * 4 + rr): partial sums of an earlier K block, bias,
-            // LeakyReLU, dropout (one RNG call = exactly the thread's four columns), store
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                st_f4(st + stage_off(lane, j >> 2), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            __syncwarp();
-            float4 r4[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + stage_off(i * 4 + rr, c4));
-            __syncwarp();
-            const int col = c * 32 + c4 * 4;                              // within the block's d_out columns
-            if (col < d_out) {
-                const int gcol = a.out_off + col;                         // within the layer's d_out_full columns
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
-                const int words = (a.d_out_full + 31) >> 5;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t row = row_base + i * 4 + rr;
-                    if (row >= a.n_rows) continue;
-                    float* dst = a.E_out + row * a.d_out_full + gcol;
-                    float4 x = r4[i];
-                    if (a.mode == FW_PARTIAL) {
-                        st_f4(dst, x);
-                        continue;
-                    }
-                    if (a.mode == FW_FINAL) {
-                        const float4 prev = ld_f4(dst);
-                        x.x += prev.x; x.y += prev.y; x.z += prev.z; x.w += prev.w;
-                    }
-                    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                    x.x = x.x > 0.f ? x.x : a.slope * x.x;                // LeakyReLU, NGCF.py:140
-                    x.y = x.y > 0.f ? x.y : a.slope * x.y;
-                    x.z = x.z > 0.f ? x.z : a.slope * x.z;
-                    x.w = x.w > 0.f ? x.w : a.slope * x.w;
-                    if (MM == MM_BITS) {
-                        const uint32_t w = a.mess_bits[row * words + (gcol >> 5)] >> (gcol & 31);
-                        x.x = w & 1u ? x.x * inv_keep : 0.f; x.y = w & 2u ? x.y * inv_keep : 0.f;
-                        x.z = w & 4u ? x.z * inv_keep : 0.f; x.w = w & 8u ? x.w * inv_keep : 0.f;
-                    } else if (MM == MM_HASH) {
-                        const float4 mm = mess_multiplier4_pre(thr, inv_keep, seed, a.layer,
-                                                               (uint64_t)((row + a.row_off) * a.d_out_full + gcol) >> 2);
-                        x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
-                    } else if (MM == MM_MULT) {
-                        const float4 mm = ld_f4(a.mess_mult + row * a.d_out_full + gcol);
-                        x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
-                    }
-                    st_f4(dst, x);
-                }
-            }
-            BWD_STAMP(0, it, 2);
-        }
+        fwd_epilogue_role<MM>(a, stage, bias_s, bars->tmem_full, bars->tmem_empty, tmem_base, n_my, warp, lane, dbg);
     } else if (warp == FW_MMA_WARP) {
         // ======================= MMA issuer =====================================================================
         const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 0, 0);
@@ -332,6 +345,219 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_fwd_tc_kernel(FwdTcArgs a
     tc_fence_before_sync();
     __syncthreads();
     if (dbg && lane == 0 && warp == 0) g_bwd_dbg[1][7][7] = clock64();
+    if (warp == FW_MMA_WARP) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+
+// ====================================================================================================================
+// Round 2: the same forward with its S / E traffic on TMA.  ncu on the kernel above: 30 % of the HBM peak with nothing
+// saturated — four loader warps holding their loads in registers keep ~16 KB in flight per SM, a third of what Little's
+// law asks for.  Here ONE thread streams the tile's S and E blocks (128 rows x 32 columns, 16 KB each, 128-byte
+// swizzled by the tensor map = already in the UMMA K-major operand layout) into a raw shared-memory ring with
+// cp.async.bulk.tensor; four converter warps read a raw stage at the very byte offsets they then write (S+E and S*E,
+// split into TF32 hi / lo) in a two-slot operand ring; the MMA issuer and the epilogue are unchanged.  Up to 64 KB of
+// loads are in flight per SM whatever the converters do.
+//
+// Warp roles (448 threads): 0-7 epilogue, 8 MMA issuer + TMEM, 9 TMA producer (one lane), 10-13 converters.
+// ====================================================================================================================
+constexpr int F2_CONV_WARPS = 4;
+constexpr int F2_TMA_WARP = FW_EPI_WARPS + 1;
+constexpr int F2_THREADS = (FW_EPI_WARPS + 2 + F2_CONV_WARPS) * 32;
+constexpr int F2_RAW_STAGES = 2;             // raw ring: stage = S block + E block = 32 KB
+constexpr int F2_A_SLOTS = 2;                // operand ring: slot = one K block, hi + lo = 32 KB
+constexpr int F2_RAW_BYTES = 2 * TC_A_BLOCK;
+
+struct FwdTmaArgs {
+    FwdTcArgs b;
+    alignas(64) CUtensorMap tmS;
+    alignas(64) CUtensorMap tmE;
+};
+
+struct Bars2 {
+    uint64_t raw_full[F2_RAW_STAGES], raw_empty[F2_RAW_STAGES];
+    uint64_t a_full[F2_A_SLOTS], a_empty[F2_A_SLOTS];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int MM>
+__global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __grid_constant__ FwdTmaArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    const FwdTcArgs& a = p.b;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // TMA / UMMA tiles need 1024-byte alignment
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int d_in = a.d_in, d_out = a.d_out;
+    const int KBH = d_in / 32, KB = 2 * KBH;
+    const int b_block = d_out * 128;
+    uint8_t* RAW = smem;                                                  // [stage][S block | E block]
+    uint8_t* AOP = RAW + F2_RAW_STAGES * F2_RAW_BYTES;                    // [slot][hi | lo]
+    uint8_t* B_hi = AOP + F2_A_SLOTS * 2 * TC_A_BLOCK;
+    uint8_t* B_lo = B_hi + KB * b_block;
+    float* bias_s = reinterpret_cast<float*>(B_lo + KB * b_block);
+    float* stage = bias_s + 64;
+    Bars2* bars = reinterpret_cast<Bars2*>(stage + FW_EPI_WARPS * 32 * 32);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int i = 0; i < F2_RAW_STAGES; ++i) {
+            mbar_init(&bars->raw_full[i], 1);
+            mbar_init(&bars->raw_empty[i], F2_CONV_WARPS);
+        }
+        for (int i = 0; i < F2_A_SLOTS; ++i) {
+            mbar_init(&bars->a_full[i], F2_CONV_WARPS);
+            mbar_init(&bars->a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->tmem_full[i], 1);
+            mbar_init(&bars->tmem_empty[i], FW_EPI_WARPS);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&p.tmS);
+        tma_prefetch_desc(&p.tmE);
+    }
+    if (warp == FW_MMA_WARP) tmem_alloc(&bars->tmem_base, 128);
+    pdl_wait();      // wcat / bias_eff come from ngcf_pack_weights, S from the SpMM right before this launch
+    for (int i = tid; i < d_out * KB * 8; i += F2_THREADS) {
+        const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
+        float4 w;
+        const int k = kb * 32 + c * 4;
+        const int wrow = k < d_in ? a.w_row1 + k : a.w_row2 + (k - d_in);
+        const float* src = a.wcat + (int64_t)wrow * a.d_out_full + a.out_off + n;
+        w.x = src[0]; w.y = src[a.d_out_full]; w.z = src[2 * a.d_out_full]; w.w = src[3 * a.d_out_full];
+        float4 hi, lo;
+        split_tf32(w, hi, lo);
+        const uint32_t off = kb * b_block + sw128_offset(n, c);
+        *reinterpret_cast<float4*>(B_hi + off) = hi;
+        *reinterpret_cast<float4*>(B_lo + off) = lo;
+    }
+    for (int i = tid; i < 64; i += F2_THREADS) bias_s[i] = i < d_out ? a.bias_eff[a.out_off + i] : 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_q = n_my * KBH;                                           // raw stages this CTA consumes
+    const bool dbg = false;
+
+    if (warp < FW_EPI_WARPS) {
+        fwd_epilogue_role<MM>(a, stage, bias_s, bars->tmem_full, bars->tmem_empty, tmem_base, n_my, warp, lane, dbg);
+    } else if (warp == FW_MMA_WARP) {
+        // ======================= MMA issuer: one operand slot = one K block ========================================
+        const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 0, 0);
+        int j = 0;                                                        // running index of the operand slot in use
+        for (int it = 0; it < n_my; ++it) {
+            const int buf = it & 1;
+            mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t tmem_d = tmem_base + buf * 64;
+            uint32_t accumulate = 0;
+            for (int hh = 0; hh < KBH; ++hh)
+                for (int part = 0; part < 2; ++part, ++j) {
+                    const int slot = j % F2_A_SLOTS;
+                    mbar_wait(&bars->a_full[slot], (j / F2_A_SLOTS) & 1);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const int kb = part * KBH + hh;                   // K block of [W1 | W2] this slot multiplies
+                        const uint32_t a_hi = smem_u32(AOP + slot * 2 * TC_A_BLOCK), a_lo = a_hi + TC_A_BLOCK;
+                        const uint32_t b_hi = smem_u32(B_hi + kb * b_block), b_lo = smem_u32(B_lo + kb * b_block);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+                            const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+                            const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                            const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+                            umma_tf32(tmem_d, dah, dbh, idesc, accumulate);
+                            umma_tf32(tmem_d, dal, dbh, idesc, 1);
+                            umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                            accumulate = 1;
+                        }
+                        umma_commit(&bars->a_empty[slot]);
+                    }
+                    __syncwarp();
+                }
+            if (lane == 0) umma_commit(&bars->tmem_full[buf]);
+            __syncwarp();
+        }
+    } else if (warp == F2_TMA_WARP) {
+        // ======================= TMA producer ======================================================================
+        if (lane == 0) {
+            for (int q = 0; q < n_q; ++q) {
+                const int it = q / KBH, hh = q % KBH, s = q % F2_RAW_STAGES;
+                const int tile = blockIdx.x + it * gridDim.x;
+                mbar_wait(&bars->raw_empty[s], ((q / F2_RAW_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&bars->raw_full[s], F2_RAW_BYTES);
+                const uint32_t dst = smem_u32(RAW + s * F2_RAW_BYTES);
+                tma_load_2d(dst, &p.tmS, a.in_off + hh * 32, tile * TC_ROWS, &bars->raw_full[s]);
+                tma_load_2d(dst + TC_A_BLOCK, &p.tmE, a.in_off + hh * 32, tile * TC_ROWS, &bars->raw_full[s]);
+            }
+        }
+    } else {
+        // ======================= converters ========================================================================
+        // raw S / E blocks arrive in the operand layout, so a thread reads and writes the same byte offsets
+        const int lt = tid - (FW_EPI_WARPS + 2) * 32;                     // 0 .. 127
+        constexpr int LT = F2_CONV_WARPS * 32;
+        constexpr int NQ = TC_A_BLOCK / 16 / LT;                          // float4 per thread per block = 8
+        int j = 0;
+        for (int q = 0; q < n_q; ++q, j += 2) {
+            const int s = q % F2_RAW_STAGES;
+            mbar_wait(&bars->raw_full[s], (q / F2_RAW_STAGES) & 1);
+            const uint8_t* rs = RAW + s * F2_RAW_BYTES;
+            float4 sv[NQ], ev[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const uint32_t off = (uint32_t)(i * LT + lt) * 16u;
+                sv[i] = *reinterpret_cast<const float4*>(rs + off);
+                ev[i] = *reinterpret_cast<const float4*>(rs + TC_A_BLOCK + off);
+            }
+            // first operand slot: S + E
+            {
+                const int slot = j % F2_A_SLOTS;
+                mbar_wait(&bars->a_empty[slot], ((j / F2_A_SLOTS) & 1) ^ 1);
+                uint8_t* hi_p = AOP + slot * 2 * TC_A_BLOCK;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    const uint32_t off = (uint32_t)(i * LT + lt) * 16u;
+                    const float4 x = make_float4(sv[i].x + ev[i].x, sv[i].y + ev[i].y, sv[i].z + ev[i].z, sv[i].w + ev[i].w);
+                    float4 hi, lo;
+                    split_tf32_trunc(x, hi, lo);
+                    *reinterpret_cast<float4*>(hi_p + off) = hi;
+                    *reinterpret_cast<float4*>(hi_p + TC_A_BLOCK + off) = lo;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->raw_empty[s]);                     // the raw stage now lives in registers
+                    mbar_arrive(&bars->a_full[slot]);
+                }
+            }
+            // second operand slot: S * E
+            {
+                const int slot = (j + 1) % F2_A_SLOTS;
+                mbar_wait(&bars->a_empty[slot], (((j + 1) / F2_A_SLOTS) & 1) ^ 1);
+                uint8_t* hi_p = AOP + slot * 2 * TC_A_BLOCK;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    const uint32_t off = (uint32_t)(i * LT + lt) * 16u;
+                    const float4 x = make_float4(sv[i].x * ev[i].x, sv[i].y * ev[i].y, sv[i].z * ev[i].z, sv[i].w * ev[i].w);
+                    float4 hi, lo;
+                    split_tf32_trunc(x, hi, lo);
+                    *reinterpret_cast<float4*>(hi_p + off) = hi;
+                    *reinterpret_cast<float4*>(hi_p + TC_A_BLOCK + off) = lo;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_full[slot]);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
     if (warp == FW_MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 128);
@@ -929,6 +1155,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
 
 }  // namespace
 
+// NGCF_B200_DENSE=tc_v1 selects the register-staged loaders of round 1 (A/B comparisons); default: TMA loaders
+static bool fwd_use_tma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NGCF_B200_DENSE");
+        v = !(e && strcmp(e, "tc_v1") == 0);
+    }
+    return v == 1;
+}
+
 // widths up to 64 are one block; 128 is decomposed into 64-wide blocks of the same kernel (K halves accumulate through
 // the partial sums parked in E_out, N halves are independent)
 bool ngcf_dense_fwd_tc_eligible(int d_in, int d_out) {
@@ -943,6 +1179,10 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                       cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_MULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_MULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tc_kernel<MM_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -954,8 +1194,22 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     const int n_tiles = (int)ceil_div64(n_rows, TC_ROWS);
     const int grid = (int)min((int64_t)n_tiles, (int64_t)ngcf_num_sms());
     const int KB = 2 * bk / 32;
-    const size_t smem = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * bn * 128) + 64 * sizeof(float) +
-                        FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
+    const bool use_tma = fwd_use_tma();
+    const size_t smem_v1 = 1024 + (size_t)KB * (2 * TC_A_BLOCK + 2 * bn * 128) + 64 * sizeof(float) +
+                           FW_EPI_WARPS * 32 * 32 * sizeof(float) + sizeof(Bars);
+    const size_t smem_v2 = 1024 + (size_t)F2_RAW_STAGES * F2_RAW_BYTES + (size_t)F2_A_SLOTS * 2 * TC_A_BLOCK +
+                           (size_t)KB * 2 * bn * 128 + 64 * sizeof(float) + FW_EPI_WARPS * 32 * 32 * sizeof(float) +
+                           sizeof(Bars2);
+    FwdTmaArgs p{};
+    if (use_tma) {
+        // S / E as [n_rows, d_in] fp32 with boxes of 128 rows x 32 columns, 128-byte swizzle; rows past the end read as 0
+        int rc = ngcf_encode_tmap_2d(&p.tmS, S, (uint64_t)n_rows, (uint64_t)d_in, (uint64_t)d_in, 32, TC_ROWS,
+                                     CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == 0)
+            rc = ngcf_encode_tmap_2d(&p.tmE, E, (uint64_t)n_rows, (uint64_t)d_in, (uint64_t)d_in, 32, TC_ROWS,
+                                     CU_TENSOR_MAP_SWIZZLE_128B);
+        NGCF_REQUIRE(rc == 0, "dense_fwd: cuTensorMapEncodeTiled failed (%d)", rc);
+    }
     for (int nh = 0; nh < NH; ++nh)
         for (int kh = 0; kh < KH; ++kh) {
             FwdTcArgs a{S, E, n_rows, bk, bn, wcat, bias_eff, slope, mess_mult, mess_bits, mess_p, seed, seed_dev, layer,
@@ -965,11 +1219,22 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
             a.out_off = nh * bn; a.d_out_full = d_out;
             a.mode = KH == 1 ? FW_SINGLE : (kh == 0 ? FW_PARTIAL : FW_FINAL);
             const int mm = a.mode == FW_PARTIAL ? MM_NONE : mess_mode(mess_mult, mess_bits, mess_p);
+            if (use_tma) {
+                p.b = a;
+                switch (mm) {
+                    case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tma_kernel<MM_NONE>, dim3(grid), dim3(F2_THREADS), smem_v2, st, p)); break;
+                    case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tma_kernel<MM_MULT>, dim3(grid), dim3(F2_THREADS), smem_v2, st, p)); break;
+                    case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tma_kernel<MM_BITS>, dim3(grid), dim3(F2_THREADS), smem_v2, st, p)); break;
+                    default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tma_kernel<MM_HASH>, dim3(grid), dim3(F2_THREADS), smem_v2, st, p)); break;
+                }
+                NGCF_LAUNCH_OK("dense_fwd_tma_kernel");
+                continue;
+            }
             switch (mm) {
-                case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_NONE>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-                case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_MULT>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-                case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_BITS>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
-                default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_HASH>, dim3(grid), dim3(TC_THREADS), smem, st, a)); break;
+                case MM_NONE: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_NONE>, dim3(grid), dim3(TC_THREADS), smem_v1, st, a)); break;
+                case MM_MULT: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_MULT>, dim3(grid), dim3(TC_THREADS), smem_v1, st, a)); break;
+                case MM_BITS: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_BITS>, dim3(grid), dim3(TC_THREADS), smem_v1, st, a)); break;
+                default: NGCF_CUDA(ngcf_launch_pdl(dense_fwd_tc_kernel<MM_HASH>, dim3(grid), dim3(TC_THREADS), smem_v1, st, a)); break;
             }
             NGCF_LAUNCH_OK("dense_fwd_tc_kernel");
         }

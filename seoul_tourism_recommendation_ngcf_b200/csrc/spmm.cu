@@ -8,6 +8,7 @@
 // dependent load plus the narrow tail batches as 4-8 exposed round trips per 16-row tile, and the two launches
 // each paid their own tail.)  One CTA (8 warps) per tile; the hardware block scheduler balances the tiles.
 #include <stdlib.h>
+#include <string.h>
 
 #include "spmm_core.cuh"
 
@@ -220,6 +221,186 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_tile_kernel(S
     if (a.dbg) stamp_done(a.dbg);
 }
 
+// ---- streaming version (round 2) -------------------------------------------------------------------------------------
+// tools/l2_gather_bench.cu: 40 resident warps that do nothing but gather random 256-byte rows of an 18-MB table, 4 in
+// flight per lane group, move 17.9 TB/s out of L2 on a B200; the row-per-warp kernel above reached 9.9 TB/s on the same
+// gathers, because its warps are in that state only about half of the time: the typical row of these graphs has 7-20
+// entries, i.e. one or two (mostly partial) batches followed by a shuffle reduction, a store and the next row's set-up.
+// Here the tile's entries are ONE stream, cut into equal contiguous ranges for the CTA's lane groups; a group runs full
+// batches over its range whatever the row lengths are, and every entry names its row (top bits of the column word, see
+// spmm_core.cuh), so a change of row just parks the running sum in a shared-memory row buffer.  A row that straddles two
+// ranges is completed in fixed order afterwards (no float atomics: results stay bit-reproducible): each group parks
+// the sum of the FIRST row it meets in its own slot `pf` (that row may have started in an earlier range), every later
+// row of its range starts inside the range, is therefore owned by this group alone and goes to `ysum`; the write-out
+// adds, per row, ysum and the pf slots that name the row, in group order.
+template <int G>
+__global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel(SpmmArgs a) {
+    constexpr int NGRP = SP_THREADS / G;                              // lane groups of the CTA
+    __shared__ __align__(16) int2 ent_s[SP_TILE_ENT];
+    __shared__ __align__(16) float ysum[SP_TILE_ROWS * G * 4];
+    __shared__ __align__(16) float pf[SP_THREADS * 4];                // [NGRP][G * 4]
+    __shared__ int rp_s[SP_TILE_ROWS + 1];
+    __shared__ int hub_s[SP_TILE_ROWS];
+    __shared__ int first_row[NGRP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid / G, l = tid % G;
+    pdl_launch_dependents();
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
+    const bool chunk_side = (int)blockIdx.x < a.n_chunk_tiles;
+    const TileSide& sd = chunk_side ? a.chunks : a.rows;
+    const int t = chunk_side ? (int)blockIdx.x : (int)blockIdx.x - a.n_chunk_tiles;
+    const int4 raw = *reinterpret_cast<const int4*>(sd.tiles + t);
+    const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
+    const int nr = ti.r1 - ti.r0;
+    if (tid < nr)
+        hub_s[tid] = chunk_side ? a.hub_of_row[sd.row_key[ti.r0 + tid]] : (a.hub_of_row ? a.hub_of_row[ti.r0 + tid] : -1);
+    for (int i = tid; i < nr * G; i += SP_THREADS) reinterpret_cast<float4*>(ysum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
+    int cnt;
+    if (sd.ctrp) {
+        cnt = sd.ctrp[(size_t)t * (SP_TILE_ROWS + 1) + nr];           // this step's survivors of the tile, compacted at e0
+        for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(sd.cent + ti.e0 + i);
+        __syncthreads();
+    } else {
+        cnt = ti.e1 - ti.e0;
+        DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
+                    a.row_off, sd.bits};
+        stage_tile<SP_THREADS>(ti, sd.rowptr, sd.ent, sd.row_key, dr, rp_s, ent_s, tid, CtaSync());
+    }
+    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 1] = gtime_ns();
+
+    {
+        const int per = (cnt + NGRP - 1) / NGRP;
+        int j = min(grp * per, cnt);
+        const int end = min(j + per, cnt);
+        const char* xl = reinterpret_cast<const char*>(a.X + ((l * 4) < a.d ? l * 4 : 0));
+        const uint32_t row_bytes = a.ldx * 4u;
+        float* const pf_l = pf + grp * (G * 4) + l * 4;
+        float* const ys_l = ysum + l * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = -1, frow = -1;
+        bool isfirst = true;
+        auto step = [&](const int2 e, const float4 x) {
+            const int lr = ent_lrow(e.x);
+            if (lr != cur) {                                          // the previous row of this range is complete
+                if (cur >= 0) {
+                    st_f4(isfirst ? pf_l : ys_l + cur * (G * 4), acc);
+                    if (isfirst) frow = cur;
+                    isfirst = false;
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                cur = lr;
+            }
+            const float w = __int_as_float(e.y);
+            acc.x = fmaf(w, x.x, acc.x);
+            acc.y = fmaf(w, x.y, acc.y);
+            acc.z = fmaf(w, x.z, acc.z);
+            acc.w = fmaf(w, x.w, acc.w);
+        };
+        for (; j + UNROLL <= end; j += UNROLL) {
+            int2 e[UNROLL];
+            float4 x[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) e[u] = ent_s[j + u];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)ent_col(e[u].x) * row_bytes));
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) step(e[u], x[u]);
+        }
+        if (j < end) {                                                // one predicated batch per range
+            int2 e[UNROLL];
+            float4 x[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                e[u] = make_int2(0, 0);
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j + u < end) {
+                    e[u] = ent_s[j + u];
+                    x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)ent_col(e[u].x) * row_bytes));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                if (j + u < end) step(e[u], x[u]);
+        }
+        if (cur >= 0) {
+            st_f4(isfirst ? pf_l : ys_l + cur * (G * 4), acc);
+            if (isfirst) frow = cur;
+        }
+        if (l == 0) first_row[grp] = frow;
+    }
+    __syncthreads();
+
+    // the completed sum of tile row i for this lane's four columns
+    auto row_sum = [&](int i, int ll) {
+        float4 y = ld_f4(ysum + i * (G * 4) + ll * 4);
+#pragma unroll
+        for (int q = 0; q < NGRP; ++q)
+            if (first_row[q] == i) {
+                const float4 p = ld_f4(pf + q * (G * 4) + ll * 4);
+                y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+            }
+        return y;
+    };
+
+    if (chunk_side) {
+        // a "row" here is a chunk of a hub row: its sum goes to hub_partial; the warp that stores a hub's LAST chunk
+        // completes the row from the partial sums, in chunk order (same protocol as spmm_tile_kernel)
+        for (int i = warp; i < nr; i += SP_WARPS) {
+            const int64_t chunk = ti.r0 + i;
+            const int h = hub_s[i];
+            const bool ok = lane < G && lane * 4 < a.d;
+            if (ok) st_f4(sd.Y + chunk * sd.ldy + lane * 4, row_sum(i, lane));
+            __threadfence();
+            __syncwarp();
+            const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(a.hub_done + h, 1) + 1 == c1 - c0);
+            last = __shfl_sync(FULL_MASK, last, 0);
+            if (!last) continue;
+            __threadfence();
+            if (lane == 0) a.hub_done[h] = 0;                         // ready for the next product
+            const int64_t row = sd.row_key[chunk];
+            const int s = a.slot ? a.slot[row] : -1;
+            float4 sum = sum_partials_split<G>(sd.Y, c0, c1, a.d, lane);
+            if (ok) {
+                const int c = lane * 4;
+                if (a.addend) {
+                    const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
+                    sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
+                }
+                if (s >= 0) {
+                    const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
+                    sum.x += gs.x; sum.y += gs.y; sum.z += gs.z; sum.w += gs.w;
+                }
+                st_f4(a.Yrows + row * a.ld_yrows + c, sum);
+            }
+        }
+        if (a.dbg) stamp_done(a.dbg);
+        return;
+    }
+
+    // ordinary rows (hub rows are written by the chunk side); a lane group writes one row: coalesced 16 * G bytes
+    const bool ok = l * 4 < a.d;
+    for (int i = grp; i < nr; i += NGRP) {
+        if (hub_s[i] >= 0 || !ok) continue;
+        const int64_t row = ti.r0 + i;
+        float4 y = row_sum(i, l);
+        if (a.addend) {
+            const float4 ad = ld_f4(a.addend + row * a.ld_add + l * 4);
+            y.x += ad.x; y.y += ad.y; y.z += ad.z; y.w += ad.w;
+        }
+        const int s = a.slot ? a.slot[row] : -1;
+        if (s >= 0) {
+            const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + l * 4);
+            y.x += gs.x; y.y += gs.y; y.z += gs.z; y.w += gs.w;
+        }
+        st_f4(sd.Y + row * sd.ldy + l * 4, y);
+    }
+    if (a.dbg) stamp_done(a.dbg);
+}
+
 // Node-dropout decisions of one step for every entry of a tile list, all layers at once (bit k = survives layer k).
 // out_f: keyed on (row, col) = this CSR read as L; out_t: keyed on (col, row) = the same CSR read as L^T (a
 // symmetric L shares one CSR for both directions).  Either may be NULL.
@@ -252,7 +433,7 @@ __global__ void __launch_bounds__(BITS_THREADS) dropout_bits_kernel(BitsArgs a, 
     __syncthreads();
     const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
     for (int i = tid; i < cnt; i += BITS_THREADS) {
-        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + e0 + i).x;
+        const uint32_t c = ent_col(ld_stream_i2(a.ent + e0 + i).x);
         int lo = 0, hi = nr - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -285,7 +466,7 @@ __global__ void __launch_bounds__(BITS_THREADS) entry_keys_kernel(KeyArgs a, int
     for (int i = tid; i <= nr; i += BITS_THREADS) rp_s[i] = a.rowptr[r0 + i] - e0;
     __syncthreads();
     for (int i = tid; i < cnt; i += BITS_THREADS) {
-        const uint32_t c = (uint32_t)ld_stream_i2(a.ent + e0 + i).x;
+        const uint32_t c = ent_col(ld_stream_i2(a.ent + e0 + i).x);
         int lo = 0, hi = nr - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -375,8 +556,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
                     if (rp_s[mid] <= p) lo = mid; else hi = mid - 1;
                 }
                 const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
-                kl[q] = ngcf_node_key(r, (uint32_t)e[q].x);
-                kt[q] = ngcf_node_key((uint32_t)e[q].x, r);
+                kl[q] = ngcf_node_key(r, ent_col(e[q].x));
+                kt[q] = ngcf_node_key(ent_col(e[q].x), r);
             }
             if (want_l) keep[q] = node_keep_bits_key(thr, seed, K, kl[q]);
             if (want_t) keep[q] |= node_keep_bits_key(thr, seed, K, kt[q]) << K;
@@ -422,9 +603,26 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
     if (a.dbg) stamp_done(a.dbg);
 }
 
+// NGCF_B200_SPMM=rows selects the row-per-warp kernel (A/B comparisons); default: the streaming kernel for vector widths
+bool spmm_use_stream() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NGCF_B200_SPMM");
+        v = !(e && strcmp(e, "rows") == 0);
+    }
+    return v == 1;
+}
+
 template <int G>
 int launch(const SpmmArgs& a, int n_ctas, cudaStream_t st) {
     if (n_ctas <= 0) return NGCF_OK;
+    if constexpr (G > 0) {
+        if (spmm_use_stream()) {
+            NGCF_CUDA(ngcf_launch_pdl(spmm_stream_kernel<G>, dim3((unsigned)n_ctas), dim3(SP_THREADS), 0, st, a));
+            NGCF_LAUNCH_OK("spmm_stream_kernel");
+            return NGCF_OK;
+        }
+    }
     NGCF_CUDA(ngcf_launch_pdl(spmm_tile_kernel<G>, dim3((unsigned)n_ctas), dim3(SP_THREADS), 0, st, a));
     NGCF_LAUNCH_OK("spmm_tile_kernel");
     return NGCF_OK;

@@ -30,6 +30,15 @@ static_assert(SP_TILE_ENT >= SPLIT, "a tile must hold the longest ordinary row")
 #endif
 constexpr int UNROLL = NGCF_SPMM_UNROLL;           // gathered rows in flight per lane group
 
+// An entry's 32-bit column word also carries, in its top 5 bits, the index of the entry's row inside its tile (packed
+// once by plan.py; the per-step compaction copies entries verbatim, so it survives node dropout): the streaming
+// kernel needs no row pointers to know where a row ends.  Column ids therefore have 27 bits (N < 134 M nodes).
+constexpr int LR_SHIFT = 27;
+constexpr uint32_t COL_MASK = (1u << LR_SHIFT) - 1u;
+static_assert(NGCF_SPMM_TILE_ROWS <= 32, "the local row index of an entry has 5 bits");
+__device__ __forceinline__ uint32_t ent_col(int x) { return (uint32_t)x & COL_MASK; }
+__device__ __forceinline__ int ent_lrow(int x) { return (int)((uint32_t)x >> LR_SHIFT); }
+
 struct TileInfo {                   // int4: rows [r0, r1), entries [e0, e1) of one tile
     int r0, r1, e0, e1;
 };
@@ -74,8 +83,8 @@ __device__ __forceinline__ void stage_tile(const TileInfo ti, const int32_t* __r
                 if (rp_s[mid] <= i) lo = mid; else hi = mid - 1;
             }
             const uint32_t r = (uint32_t)(row_key ? row_key[ti.r0 + lo] : ti.r0 + lo) + dr.row_off;
-            const uint32_t r0 = dr.transposed ? (uint32_t)e.x : r;
-            const uint32_t c0 = dr.transposed ? r : (uint32_t)e.x;
+            const uint32_t r0 = dr.transposed ? ent_col(e.x) : r;
+            const uint32_t c0 = dr.transposed ? r : ent_col(e.x);
             if (!node_keep(dr.p, dr.seed, dr.layer, r0, c0)) e.y = 0;
             ent_s[i] = e;
         }
@@ -109,7 +118,7 @@ __device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b
         for (int u = 0; u < UNROLL; ++u) e[u] = p[u * NG];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)(uint32_t)e[u].x * row_bytes));
+            x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)ent_col(e[u].x) * row_bytes));
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const float w = __int_as_float(e[u].y);
@@ -130,7 +139,7 @@ __device__ __forceinline__ float4 gather_row_vec(const int2* ent_s, int a, int b
             if (ok) e = ent_s[idx];
             w[u] = __int_as_float(e.y);
             x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)(uint32_t)e.x * row_bytes));
+            if (ok) x[u] = ld_f4(reinterpret_cast<const float*>(xl + (uint64_t)ent_col(e.x) * row_bytes));
         }
 #pragma unroll
         for (int u = 0; u < TAIL; ++u) {
@@ -226,7 +235,7 @@ __device__ __forceinline__ void gather_row_sc(const int2* ent_s, int a, int b, c
             int2 e = make_int2(0, 0);
             if (ok) e = ent_s[idx];
             w[u] = __int_as_float(e.y);
-            const float* xr = X + (uint64_t)(uint32_t)e.x * ldx;
+            const float* xr = X + (uint64_t)ent_col(e.x) * ldx;
 #pragma unroll
             for (int q = 0; q < SC_MAXQ; ++q) {
                 const int col = lane + 32 * q;

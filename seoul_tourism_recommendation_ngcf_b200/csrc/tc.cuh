@@ -38,6 +38,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 28)) __trap();
     }
 }
+// transaction-count arrival: the barrier's phase completes once this arrival AND `bytes` of async-copy data have landed
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// ---- TMA (cp.async.bulk.tensor): one thread copies a whole 2-D box global -> shared memory, swizzled as the tensor map
+// says, completion signalled on an mbarrier in bytes; out-of-range rows of the box are zero-filled.  The tensor map is a
+// __grid_constant__ kernel parameter built on the host (tmap.h).
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 #ifdef NGCF_NO_PROXY_FENCE
 __device__ __forceinline__ void fence_proxy_async_smem() {}

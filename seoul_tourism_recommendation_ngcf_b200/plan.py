@@ -96,11 +96,33 @@ class CsrSide:
                                                              lib.ngcf_spmm_tile_entries())).to(dev)
         else:
             self.chunk_tiles = None
+        self._pack_local_rows()
         self.ent = None          # base entry pairs, set by LaplacianPlan
         self.key_l = self.key_t = None   # static node-dropout keys (ensure_keys)
         self.key_row_offset = 0
         self._partial = {}
         self._struct_cache = {}
+
+    LR_SHIFT = 27            # spmm_core.cuh: column ids have 27 bits, the 5 bits above them name the entry's row in its tile
+
+    def _pack_local_rows(self):
+        """Writes, into the top bits of every entry's column word, the index of the entry's row inside its SpMM tile
+        (hub entries: of its chunk inside its chunk tile).  The streaming SpMM kernel reads a tile's entries as one
+        stream and needs no row pointers; the per-step node-dropout compaction copies entries verbatim, so the tag
+        survives it."""
+        dev = self.rowptr.device
+        if self.nnz_short:
+            pos = torch.arange(self.nnz_short, device=dev)
+            row = torch.searchsorted(self.rowptr.to(torch.int64), pos, right=True) - 1
+            t0 = self.tiles[:, 0].to(torch.int64).contiguous()
+            lr = row - t0[torch.searchsorted(t0, row, right=True) - 1]
+            self.colidx[:self.nnz_short] |= (lr << self.LR_SHIFT).to(torch.int32)
+        if self.n_chunks:
+            pos = torch.arange(self.nnz_hub, device=dev)
+            chunk = torch.searchsorted(self.chunk_ptr.to(torch.int64), pos, right=True) - 1
+            t0 = self.chunk_tiles[:, 0].to(torch.int64).contiguous()
+            lr = chunk - t0[torch.searchsorted(t0, chunk, right=True) - 1]
+            self.colidx[self.nnz_short:self.nnz] |= (lr << self.LR_SHIFT).to(torch.int32)
 
     def descriptor(self, ent: torch.Tensor | None = None) -> "_lib.NgcfCsr":
         """``ngcf_csr`` over this side's arrays; ``ent`` = alternative [nnz, 2] entry pairs (masked values)."""
@@ -175,6 +197,10 @@ class LaplacianPlan:
         self.nnz = int(self.coo_val.numel())
         if self.nnz and (int(idx.min()) < 0 or int(idx.max()) >= self.N):
             raise ValueError("Laplacian indices out of range")
+        if (shard.N_pad if shard is not None else self.N) >= (1 << CsrSide.LR_SHIFT):
+            raise ValueError(f"graphs of up to {1 << CsrSide.LR_SHIFT} nodes are supported (27-bit column ids)")
+        if lib.ngcf_spmm_tile_rows() > 16:
+            raise RuntimeError("the local row tag of an entry assumes SpMM tiles of at most 16 rows")
         if shard is None:
             n_rows = n_cols = self.N
             pos = torch.arange(self.nnz, device=device)

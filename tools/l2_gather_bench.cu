@@ -150,7 +150,7 @@ float time_ms(F launch, int reps) {
     return ms / reps;
 }
 
-int main() {
+int main(int argc, char** argv) {
     const int N = 70839;
     const int n_sm = 148;
     std::vector<float> hE((size_t)N * D, 1.0f);
@@ -164,6 +164,23 @@ int main() {
         s ^= s << 13; s ^= s >> 7; s ^= s << 17;
         hidx[i] = (int)(s % N);
     }
+    // optional: a file of int32 row ids (e.g. the column stream of the real graph's SpMM, execution order), repeated to M
+    const char* src = "uniform random";
+    if (argc > 1) {
+        FILE* f = fopen(argv[1], "rb");
+        if (f) {
+            std::vector<int> file;
+            int buf[4096];
+            size_t n;
+            while ((n = fread(buf, 4, 4096, f)) > 0) file.insert(file.end(), buf, buf + n);
+            fclose(f);
+            if (!file.empty()) {
+                for (size_t i = 0; i < M; ++i) hidx[i] = file[i % file.size()] % N;
+                src = argv[1];
+            }
+        }
+    }
+    printf("row ids: %s\n", src);
     int* idx;
     CK(cudaMalloc(&idx, M * 4));
     CK(cudaMemcpy(idx, hidx.data(), M * 4, cudaMemcpyHostToDevice));
