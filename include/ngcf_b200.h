@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NGCF_B200_ABI_VERSION 3
+#define NGCF_B200_ABI_VERSION 4
 #define NGCF_MAX_LAYERS 8
 #define NGCF_MAX_WIDTH 128          /* widest embedding / layer size the kernels accept */
 #define NGCF_ADAM_MAX_TENSORS 32     /* parameter tensors one ngcf_adam_step call updates */
@@ -83,6 +83,8 @@ typedef struct ngcf_csr {
     int64_t key_row_offset;         /* the row_offset the keys were computed for */
     int32_t n_tiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
+    const uint32_t* tile_hubmask;   /* [n_tiles] bit i = row r0 + i of the tile is a hub row; may be NULL when n_hub == 0 */
+    int32_t* work_ctr;              /* [2] work counters of the warp-streaming ngcf_spmm kernel: zero between calls */
 } ngcf_csr;
 
 int ngcf_spmm_split_threshold(void);
@@ -110,8 +112,11 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
 
 /* ---- SpMM: torch.mm(L, E), NGCF.py:130, and its backward L^T·gS (autograd MmBackward0) ----------
  * Y[i,:] = sum_t val[t] * X[col[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
- * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in chunk order by the warp
- * that completes the hub's last chunk, so the result is deterministic (no float atomics).
+ * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in chunk order, so the
+ * result is deterministic (no float atomics on shared sums).  Widths that are multiples of 4 run the persistent
+ * warp-streaming kernel: it ADDS its row sums to Y after Y := addend (pass addend == Y to accumulate in place and
+ * save the copy); other widths run the row-per-warp kernel.  The column word of an entry carries, above its 27-bit
+ * column id, the index of the entry's row inside its tile (see plan.py).
  *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
  *               (the IndexBackward scatter of NGCF.py:151-155 folded into the last backward SpMM).
  *   drop_p > 0: device-RNG node dropout (NGCF.py:93-100,124-126) evaluated in-kernel: entry (r,c) of L survives
@@ -120,9 +125,9 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
  *               this CSR holds L^T, so both directions drop the same entries of L.
  *               seed_dev: optional device uint64 added to seed (graph-replay safe).
  *   keep_bits : optional output of ngcf_node_dropout_bits for this direction; when given, drop_p/seed are unused.
- *   c_ent/c_trp: optional output of ngcf_node_dropout_compact for this direction AND layer (the step's surviving
- *               entries, compacted per tile); when given, keep_bits/drop_p/seed are unused and only survivors are
- *               staged and gathered.
+ *   c_ent/c_cnt: optional output of ngcf_node_dropout_compact for this direction AND layer (the step's surviving
+ *               entries, compacted per tile, and their number per tile); when given, keep_bits/drop_p/seed are unused
+ *               and only survivors are staged and gathered (width % 4 == 0 only).
  *   row_offset: global index of row 0 of this CSR.  RNG keys use global coordinates, so a row shard (rows
  *               [row_offset, row_offset + n_rows) of L, all columns) draws exactly the single-GPU decisions. */
 int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
@@ -130,7 +135,7 @@ int ngcf_spmm(const ngcf_csr* csr_host, const float* X, int64_t ldx, int d,
               const int32_t* slot, const float* gsum, int64_t ld_gsum,
               float* hub_partial,
               float drop_p, uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
-              const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_trp,
+              const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_cnt,
               float* Y, int64_t ldy, void* stream);
 
 /* One step's node-dropout decisions for every entry and every layer at once (bit k of a byte = the entry survives
@@ -144,14 +149,14 @@ int ngcf_node_dropout_bits(const ngcf_csr* csr_host, float drop_p, uint64_t seed
 /* The same decisions applied the way the reference applies them (NGCF.sparse_dropout, NGCF.py:93-100, DELETES the
  * dropped entries, cumulatively over the layers): one pass per step writes, for every layer k and for the CSR read
  * as L and/or as L^T, the surviving (col, value) pairs of each SpMM tile {r0,r1,e0,e1} compacted in their original
- * order at [e0, e0 + kept) of ent_*[k] (int32[2*nnz], indexed like ent then hub_ent) and the tile-relative row
- * pointers trp_*[k][tile * (ngcf_spmm_tile_rows()+1) + i], i = 0..r1-r0 (tiles first, then chunk_tiles).
- * ent_*_host / trp_*_host are HOST arrays of n_layers device pointers; pass NULL for a direction that is not needed.
+ * order at [e0, e0 + kept) of ent_*[k] (int32[2*nnz], indexed like ent then hub_ent) and `kept` to
+ * cnt_*[k][tile] (tiles first, then chunk_tiles).
+ * ent_*_host / cnt_*_host are HOST arrays of n_layers device pointers; pass NULL for a direction that is not needed.
  * Products given these arrays gather only the survivors: (1-p)^(k+1) of the entries at layer k. */
 int ngcf_node_dropout_compact(const ngcf_csr* csr_host, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                               int n_layers, int64_t row_offset,
-                              int32_t* const* ent_as_L_host, int32_t* const* trp_as_L_host,
-                              int32_t* const* ent_as_Lt_host, int32_t* const* trp_as_Lt_host, void* stream);
+                              int32_t* const* ent_as_L_host, int32_t* const* cnt_as_L_host,
+                              int32_t* const* ent_as_Lt_host, int32_t* const* cnt_as_Lt_host, void* stream);
 
 /* Static per-entry node-dropout keys (plan time, once per csr): key_l[t] / key_t[t] for entry t in execution order
  * (ent then hub_ent), the CSR read as L / as L^T.  With them in the descriptor ngcf_node_dropout_compact needs no row

@@ -30,7 +30,7 @@ def _stream() -> int:
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
     __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
-                 "rows", "offsets", "W1", "W2", "fresh_key")
+                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode")
 
 
 class _Propagate(torch.autograd.Function):
@@ -56,16 +56,22 @@ class _Propagate(torch.autograd.Function):
         st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
         st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
+        st.node_mode = mod._node_mode
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
             # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
             # deletes the dropped entries like NGCF.sparse_dropout does, so layer k gathers (1-p)^(k+1) of the rows
             shared = st.plan.side(True, False) is side
-            if mod._node_mode == "compact":
+            # compacted survivor lists are read by the streaming SpMM (widths that are multiples of 4); the reference's
+            # own width 65 runs the row-per-warp kernel from per-step decision bytes instead
+            # (every width, the last one too: the batch-row gradient rows of the final backward product are D_total wide)
+            node_mode = mod._node_mode if all(d % 4 == 0 for d in st.dims) or mod._node_mode == "inkernel" else "bits"
+            st.node_mode = node_mode
+            if node_mode == "compact":
                 st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
                 if shared:
                     st.comp_b = ct
-            elif mod._node_mode == "bits":
+            elif node_mode == "bits":
                 st.bits_f, bt = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
                 if shared:
                     st.bits_b = bt
@@ -154,9 +160,9 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
-        if st.drop_p > 0 and mod._node_mode == "compact" and st.comp_b is None:
+        if st.drop_p > 0 and st.node_mode == "compact" and st.comp_b is None:
             _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
-        if st.drop_p > 0 and mod._node_mode == "bits" and st.bits_b is None:
+        if st.drop_p > 0 and st.node_mode == "bits" and st.bits_b is None:
             _, st.bits_b = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         gE_next = None
         col_off = D

@@ -21,7 +21,7 @@ class NgcfCsr(C.Structure):
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
                 ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp), ("key_l", _vp), ("key_t", _vp), ("key_row_offset", _i64),
                 ("n_tiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
-                ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32)]
+                ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32), ("tile_hubmask", _vp), ("work_ctr", _vp)]
 
 
 _csr_p = C.POINTER(NgcfCsr)

@@ -120,6 +120,7 @@ __device__ __forceinline__ void fwd_epilogue_role(const FwdTcArgs& a, float* sta
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);           // accumulator drained: next tile may reuse it
+        BWD_STAMP(0, it, 3);
         if (!has_chunk) continue;
         const int64_t row_base = (int64_t)tile * TC_ROWS + quarter * 32;
         // raw accumulators through the per-warp transposition buffer; everything else happens in the coalesced
@@ -133,6 +134,7 @@ __device__ __forceinline__ void fwd_epilogue_role(const FwdTcArgs& a, float* sta
 #pragma unroll
         for (int i = 0; i < 8; ++i) r4[i] = ld_f4(st + stage_off(i * 4 + rr, c4));
         __syncwarp();
+        BWD_STAMP(0, it, 4);
         const int col = c * 32 + c4 * 4;                              // within the block's d_out columns
         if (col < d_out) {
             const int gcol = a.out_off + col;                         // within the layer's d_out_full columns
@@ -380,6 +382,7 @@ struct Bars2 {
     uint64_t raw_full[F2_RAW_STAGES], raw_empty[F2_RAW_STAGES];
     uint64_t a_full[F2_A_SLOTS], a_empty[F2_A_SLOTS];
     uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t b_ready;
     uint32_t tmem_base;
 };
 
@@ -415,44 +418,69 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
             mbar_init(&bars->tmem_full[i], 1);
             mbar_init(&bars->tmem_empty[i], FW_EPI_WARPS);
         }
+        mbar_init(&bars->b_ready, FW_EPI_WARPS);
         fence_mbar_init();
         tma_prefetch_desc(&p.tmS);
         tma_prefetch_desc(&p.tmE);
     }
     if (warp == FW_MMA_WARP) tmem_alloc(&bars->tmem_base, 128);
-    pdl_wait();      // wcat / bias_eff come from ngcf_pack_weights, S from the SpMM right before this launch
-    for (int i = tid; i < d_out * KB * 8; i += F2_THREADS) {
-        const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
-        float4 w;
-        const int k = kb * 32 + c * 4;
-        const int wrow = k < d_in ? a.w_row1 + k : a.w_row2 + (k - d_in);
-        const float* src = a.wcat + (int64_t)wrow * a.d_out_full + a.out_off + n;
-        w.x = src[0]; w.y = src[a.d_out_full]; w.z = src[2 * a.d_out_full]; w.w = src[3 * a.d_out_full];
-        float4 hi, lo;
-        split_tf32(w, hi, lo);
-        const uint32_t off = kb * b_block + sw128_offset(n, c);
-        *reinterpret_cast<float4*>(B_hi + off) = hi;
-        *reinterpret_cast<float4*>(B_lo + off) = lo;
-    }
-    for (int i = tid; i < 64; i += F2_THREADS) bias_s[i] = i < d_out ? a.bias_eff[a.out_off + i] : 0.f;
-    fence_proxy_async_smem();
     tc_fence_before_sync();
-    __syncthreads();
+    __syncthreads();                                                      // barriers + TMEM address visible to every role
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_q = n_my * KBH;                                           // raw stages this CTA consumes
-    const bool dbg = false;
+    const bool dbg = g_bwd_dbg_on == 1 && blockIdx.x == 0 && (warp == 0 || warp >= FW_MMA_WARP);
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][7] = clock64();
+    pdl_wait();      // wcat / bias_eff come from ngcf_pack_weights, S from the SpMM right before this launch
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[0][7][6] = clock64();
 
     if (warp < FW_EPI_WARPS) {
+        // the epilogue warps have nothing to do until the first accumulator is complete: they stage [W1 | W2] (split and
+        // swizzled: B[n][k] = wcat[k][n]) and the bias while the first S / E tiles are already in flight
+        constexpr int ET = FW_EPI_WARPS * 32;
+        constexpr int WMAX = 64 * TC_MAX_KB * 8 / ET;                     // items (float4 of 4 consecutive k) per thread
+        float4 wv[WMAX];
+        const int n_items = d_out * KB * 8;
+#pragma unroll
+        for (int q = 0; q < WMAX; ++q) {                                  // every load in flight before the first use
+            const int i = q * ET + tid;
+            wv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_items) {
+                const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
+                const int k = kb * 32 + c * 4;
+                const int wrow = k < d_in ? a.w_row1 + k : a.w_row2 + (k - d_in);
+                const float* src = a.wcat + (int64_t)wrow * a.d_out_full + a.out_off + n;
+                wv[q] = make_float4(src[0], src[a.d_out_full], src[2 * a.d_out_full], src[3 * a.d_out_full]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < WMAX; ++q) {
+            const int i = q * ET + tid;
+            if (i < n_items) {
+                const int n = i % d_out, c = (i / d_out) & 7, kb = i / (d_out * 8);
+                float4 hi, lo;
+                split_tf32(wv[q], hi, lo);
+                const uint32_t off = kb * b_block + sw128_offset(n, c);
+                *reinterpret_cast<float4*>(B_hi + off) = hi;
+                *reinterpret_cast<float4*>(B_lo + off) = lo;
+            }
+        }
+        for (int i = tid; i < 64; i += ET) bias_s[i] = i < d_out ? a.bias_eff[a.out_off + i] : 0.f;
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");             // bias visible to all epilogue warps
+        if (lane == 0) mbar_arrive(&bars->b_ready);
+        if (dbg && lane == 0) g_bwd_dbg[0][7][5] = clock64();
         fwd_epilogue_role<MM>(a, stage, bias_s, bars->tmem_full, bars->tmem_empty, tmem_base, n_my, warp, lane, dbg);
     } else if (warp == FW_MMA_WARP) {
         // ======================= MMA issuer: one operand slot = one K block ========================================
         const uint32_t idesc = umma_idesc_tf32(TC_ROWS, d_out, 0, 0);
         int j = 0;                                                        // running index of the operand slot in use
+        mbar_wait(&bars->b_ready, 0);                                     // [W1 | W2] tiles staged
         for (int it = 0; it < n_my; ++it) {
             const int buf = it & 1;
             mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            BWD_STAMP(1, it, 0);
             tc_fence_after_sync();
             const uint32_t tmem_d = tmem_base + buf * 64;
             uint32_t accumulate = 0;
@@ -460,6 +488,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
                 for (int part = 0; part < 2; ++part, ++j) {
                     const int slot = j % F2_A_SLOTS;
                     mbar_wait(&bars->a_full[slot], (j / F2_A_SLOTS) & 1);
+                    BWD_STAMP(1, it, 1 + hh * 2 + part);
                     tc_fence_after_sync();
                     if (lane == 0) {
                         const int kb = part * KBH + hh;                   // K block of [W1 | W2] this slot multiplies
@@ -490,6 +519,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
                 const int it = q / KBH, hh = q % KBH, s = q % F2_RAW_STAGES;
                 const int tile = blockIdx.x + it * gridDim.x;
                 mbar_wait(&bars->raw_empty[s], ((q / F2_RAW_STAGES) & 1) ^ 1);
+                BWD_STAMP(3, it, hh);
                 mbar_expect_tx(&bars->raw_full[s], F2_RAW_BYTES);
                 const uint32_t dst = smem_u32(RAW + s * F2_RAW_BYTES);
                 tma_load_2d(dst, &p.tmS, a.in_off + hh * 32, tile * TC_ROWS, &bars->raw_full[s]);
@@ -506,6 +536,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
         for (int q = 0; q < n_q; ++q, j += 2) {
             const int s = q % F2_RAW_STAGES;
             mbar_wait(&bars->raw_full[s], (q / F2_RAW_STAGES) & 1);
+            if (dbg && lane == 0 && warp == F2_TMA_WARP + 1 && q / KBH < 8) g_bwd_dbg[2][q / KBH][(q % KBH) * 3] = clock64();
             const uint8_t* rs = RAW + s * F2_RAW_BYTES;
             float4 sv[NQ], ev[NQ];
 #pragma unroll
@@ -518,6 +549,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
             {
                 const int slot = j % F2_A_SLOTS;
                 mbar_wait(&bars->a_empty[slot], ((j / F2_A_SLOTS) & 1) ^ 1);
+                if (dbg && lane == 0 && warp == F2_TMA_WARP + 1 && q / KBH < 8) g_bwd_dbg[2][q / KBH][(q % KBH) * 3 + 1] = clock64();
                 uint8_t* hi_p = AOP + slot * 2 * TC_A_BLOCK;
 #pragma unroll
                 for (int i = 0; i < NQ; ++i) {
@@ -552,12 +584,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) dense_fwd_tma_kernel(const __gr
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_full[slot]);
+                if (dbg && lane == 0 && warp == F2_TMA_WARP + 1 && q / KBH < 8) g_bwd_dbg[2][q / KBH][(q % KBH) * 3 + 2] = clock64();
             }
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (dbg && lane == 0 && warp == 0) g_bwd_dbg[1][7][7] = clock64();
     if (warp == FW_MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 128);

@@ -29,7 +29,7 @@ struct TileSide {                   // one tile list: the ordinary rows, or the 
     const int32_t* row_key;         // chunk side: row of each chunk (dropout key); row side: NULL
     const uint8_t* bits;            // optional decision bytes (ngcf_node_dropout_bits), indexed like `ent`
     const int2* cent;               // optional: this layer's compacted entries (ngcf_node_dropout_compact), tile t at e0
-    const int32_t* ctrp;            // ... and its tile-relative row pointers [n_tiles][SP_TILE_ROWS + 1]
+    const int32_t* ccnt;            // ... and the number of survivors of each tile [n_tiles]
     float* Y;                       // output rows (chunk side: hub_partial, one row per chunk)
     int64_t ldy;
 };
@@ -59,6 +59,13 @@ struct SpmmArgs {
     int transposed;
     uint32_t row_off;
     unsigned long long* dbg;        // optional [n_ctas][4] = {start, staged, done, smid} in globaltimer ns (tools/spmm_timeline.py)
+    // warp-streaming kernel
+    const uint32_t* tile_hubmask;   // [n_row_tiles] bit i = row i of the tile is a hub (written by hub_finish_kernel); NULL: no hubs
+    int32_t* work_ctr;              // [2] = {next tile, warps done}; zero between launches
+    int n_row_tiles;
+    int add_mode;                   // Y already holds the addend: row sums are ADDED to it (red.global.add)
+    const int32_t* hub_rows;        // [n_hub]
+    int n_hub;
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -103,14 +110,7 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_tile_kernel(S
     // everything above is the plan's static layout; entries (possibly this step's compacted survivors), X, addend and
     // the outputs belong to the stream order
     pdl_wait();
-    if (sd.ctrp) {
-        // node dropout already applied for this step and layer: the tile's surviving entries sit compacted at e0
-        const int32_t* trp = sd.ctrp + (size_t)t * (SP_TILE_ROWS + 1);
-        if (tid <= nr) rp_s[tid] = trp[tid];
-        const int cnt = trp[nr];
-        for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(sd.cent + ti.e0 + i);
-        __syncthreads();
-    } else {
+    {
         DropArgs dr{a.drop_p, a.drop_p > 0.f ? ngcf_seed(a.seed, a.seed_dev) : 0ull, a.layer, a.transposed,
                     a.row_off, sd.bits};
         stage_tile<SP_THREADS>(ti, sd.rowptr, sd.ent, sd.row_key, dr, rp_s, ent_s, tid, CtaSync());
@@ -221,12 +221,20 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_tile_kernel(S
     if (a.dbg) stamp_done(a.dbg);
 }
 
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- streaming version (round 2) -------------------------------------------------------------------------------------
-// tools/l2_gather_bench.cu: 40 resident warps that do nothing but gather random 256-byte rows of an 18-MB table, 4 in
-// flight per lane group, move 17.9 TB/s out of L2 on a B200; the row-per-warp kernel above reached 9.9 TB/s on the same
-// gathers, because its warps are in that state only about half of the time: the typical row of these graphs has 7-20
-// entries, i.e. one or two (mostly partial) batches followed by a shuffle reduction, a store and the next row's set-up.
-// Here the tile's entries are ONE stream, cut into equal contiguous ranges for the CTA's lane groups; a group runs full
+// tools/l2_gather_bench.cu: 40 resident warps that do nothing but gather the real column stream of the Gowalla-shaped
+// product, 4 rows in flight per lane group, move 19.6 TB/s out of L2 on a B200 (27 us per product; 32 us with one
+// short-lived CTA per 512-entry tile); the row-per-warp kernel above takes 48-53 us.  An ablation (profiles/
+// r02_spmm_experiments.txt) located the difference in what every short-lived CTA does SERIALLY around its gathers:
+// tile record -> hub flags (a dependent global load) -> entries, the write-out, and the hub completion protocol with
+// its two __threadfence() (each one also invalidates the SM's L1).  This kernel keeps the CTA-per-tile shape but
+// removes those: hub flags are a bit mask in a per-tile word read next to the tile record, hub rows are finished by
+// hub_finish_kernel behind it (no fences or counters here), an addend is not re-read (Y already holds it and the row
+// sums are ADDED with red.global.add.v4), and the tile's entries are ONE stream, cut into equal contiguous ranges for the CTA's lane groups; a group runs full
 // batches over its range whatever the row lengths are, and every entry names its row (top bits of the column word, see
 // spmm_core.cuh), so a change of row just parks the running sum in a shared-memory row buffer.  A row that straddles two
 // ranges is completed in fixed order afterwards (no float atomics: results stay bit-reproducible): each group parks
@@ -240,7 +248,6 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel
     __shared__ __align__(16) float ysum[SP_TILE_ROWS * G * 4];
     __shared__ __align__(16) float pf[SP_THREADS * 4];                // [NGRP][G * 4]
     __shared__ int rp_s[SP_TILE_ROWS + 1];
-    __shared__ int hub_s[SP_TILE_ROWS];
     __shared__ int first_row[NGRP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / G, l = tid % G;
@@ -252,13 +259,13 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel
     const int4 raw = *reinterpret_cast<const int4*>(sd.tiles + t);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
     const int nr = ti.r1 - ti.r0;
-    if (tid < nr)
-        hub_s[tid] = chunk_side ? a.hub_of_row[sd.row_key[ti.r0 + tid]] : (a.hub_of_row ? a.hub_of_row[ti.r0 + tid] : -1);
+    // rows of this tile that are hubs (their entries live in the chunk tiles; hub_finish_kernel writes them)
+    const uint32_t hubmask = (!chunk_side && a.tile_hubmask) ? a.tile_hubmask[t] : 0u;
     for (int i = tid; i < nr * G; i += SP_THREADS) reinterpret_cast<float4*>(ysum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_wait();
     int cnt;
-    if (sd.ctrp) {
-        cnt = sd.ctrp[(size_t)t * (SP_TILE_ROWS + 1) + nr];           // this step's survivors of the tile, compacted at e0
+    if (sd.ccnt) {
+        cnt = sd.ccnt[t];                                             // this step's survivors of the tile, compacted at e0
         for (int i = tid; i < cnt; i += SP_THREADS) ent_s[i] = ld_stream_i2(sd.cent + ti.e0 + i);
         __syncthreads();
     } else {
@@ -345,60 +352,56 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel
     };
 
     if (chunk_side) {
-        // a "row" here is a chunk of a hub row: its sum goes to hub_partial; the warp that stores a hub's LAST chunk
-        // completes the row from the partial sums, in chunk order (same protocol as spmm_tile_kernel)
-        for (int i = warp; i < nr; i += SP_WARPS) {
-            const int64_t chunk = ti.r0 + i;
-            const int h = hub_s[i];
-            const bool ok = lane < G && lane * 4 < a.d;
-            if (ok) st_f4(sd.Y + chunk * sd.ldy + lane * 4, row_sum(i, lane));
-            __threadfence();
-            __syncwarp();
-            const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
-            int last = 0;
-            if (lane == 0) last = (atomicAdd(a.hub_done + h, 1) + 1 == c1 - c0);
-            last = __shfl_sync(FULL_MASK, last, 0);
-            if (!last) continue;
-            __threadfence();
-            if (lane == 0) a.hub_done[h] = 0;                         // ready for the next product
-            const int64_t row = sd.row_key[chunk];
-            const int s = a.slot ? a.slot[row] : -1;
-            float4 sum = sum_partials_split<G>(sd.Y, c0, c1, a.d, lane);
-            if (ok) {
-                const int c = lane * 4;
-                if (a.addend) {
-                    const float4 ad = ld_f4(a.addend + row * a.ld_add + c);
-                    sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
-                }
-                if (s >= 0) {
-                    const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
-                    sum.x += gs.x; sum.y += gs.y; sum.z += gs.z; sum.w += gs.w;
-                }
-                st_f4(a.Yrows + row * a.ld_yrows + c, sum);
-            }
-        }
+        // a "row" here is a chunk of a hub row: its sum goes to hub_partial; hub_finish_kernel adds the partials up
+        const bool okc = l * 4 < a.d;
+        for (int i = grp; i < nr; i += NGRP)
+            if (okc) st_f4(sd.Y + (int64_t)(ti.r0 + i) * sd.ldy + l * 4, row_sum(i, l));
         if (a.dbg) stamp_done(a.dbg);
         return;
     }
 
-    // ordinary rows (hub rows are written by the chunk side); a lane group writes one row: coalesced 16 * G bytes
+    // ordinary rows; a lane group writes one row: coalesced 16 * G bytes.  add_mode: Y already holds the addend
     const bool ok = l * 4 < a.d;
     for (int i = grp; i < nr; i += NGRP) {
-        if (hub_s[i] >= 0 || !ok) continue;
+        if (((hubmask >> i) & 1u) || !ok) continue;
         const int64_t row = ti.r0 + i;
         float4 y = row_sum(i, l);
-        if (a.addend) {
-            const float4 ad = ld_f4(a.addend + row * a.ld_add + l * 4);
-            y.x += ad.x; y.y += ad.y; y.z += ad.z; y.w += ad.w;
-        }
         const int s = a.slot ? a.slot[row] : -1;
         if (s >= 0) {
             const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + l * 4);
             y.x += gs.x; y.y += gs.y; y.z += gs.z; y.w += gs.w;
         }
-        st_f4(sd.Y + row * sd.ldy + l * 4, y);
+        float* dst = sd.Y + row * sd.ldy + l * 4;
+        if (a.add_mode) red_add_f4(dst, y); else st_f4(dst, y);
     }
     if (a.dbg) stamp_done(a.dbg);
+}
+
+// One warp per hub row: the chunk partials (written by spmm_stream_kernel right before) summed in chunk order.
+template <int G>
+__global__ void __launch_bounds__(128) hub_finish_kernel(SpmmArgs a) {
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int h = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    pdl_wait();
+    if (h >= a.n_hub) return;
+    const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
+    const int64_t row = a.hub_rows[h];
+    float4 sum = sum_partials_split<G>(a.chunks.Y, c0, c1, a.d, lane);
+    if (lane < G && lane * 4 < a.d) {
+        const int c = lane * 4;
+        float* dst = a.Yrows + row * a.ld_yrows + c;
+        if (a.add_mode) {                                             // Y holds the addend; this warp owns the row
+            const float4 ad = ld_f4(dst);
+            sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
+        }
+        const int s = a.slot ? a.slot[row] : -1;
+        if (s >= 0) {
+            const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
+            sum.x += gs.x; sum.y += gs.y; sum.z += gs.z; sum.w += gs.w;
+        }
+        st_f4(dst, sum);
+    }
 }
 
 // Node-dropout decisions of one step for every entry of a tile list, all layers at once (bit k = survives layer k).
@@ -482,12 +485,15 @@ __global__ void __launch_bounds__(BITS_THREADS) entry_keys_kernel(KeyArgs a, int
 // The reference's sparse_dropout (NGCF.py:93-100) DELETES the dropped entries, cumulatively over the layers, so its
 // layer-k product walks only (1-p)^(k+1) of the Laplacian.  One pass per step does the same for every layer and both
 // directions at once: the surviving entries of tile t are written, in their original order, to the front of the
-// tile's own slot range [e0, e1) of a per-(direction, layer) entry array, with the tile-relative row pointers next to
-// them.  The products then stage and gather the survivors only (same sums bit for bit: a dropped entry contributed
-// +0.0), which at p = 0.3 halves the gathered bytes of a 3-layer step.
+// tile's own slot range [e0, e1) of a per-(direction, layer) entry array, and their number to a per-tile count array.
+// The products then stage and gather the survivors only (same sums: a dropped entry contributed +0.0), which at
+// p = 0.3 halves the gathered bytes of a 3-layer step.  Entries carry their row (spmm_core.cuh), so no row pointers
+// have to be rebuilt.
+constexpr int WS_PER = SP_TILE_ENT / 32;     // entries of a tile per lane of the compaction warp
+static_assert(WS_PER * 32 == SP_TILE_ENT, "tile entries must be a multiple of the warp size");
+
 struct CompactArgs {
     const TileInfo* tiles;
-    const int32_t* rowptr;
     const int2* ent;
     const int32_t* row_key;
     float p;
@@ -497,39 +503,28 @@ struct CompactArgs {
     uint32_t row_off;
     const uint32_t* key_l;                   // optional static per-entry keys (ngcf_entry_keys), indexed like `ent`:
     const uint32_t* key_t;                   //   ngcf_node_key(row, col) and ngcf_node_key(col, row)
-    unsigned long long* dbg;                 // optional [n_ctas][4] = {start, loaded, decided, done} ns (tools/spmm_timeline.py)
     int2* out_ent[2][NGCF_MAX_LAYERS];       // [0] keyed (row, col) = this CSR read as L, [1] keyed (col, row) = as L^T
-    int32_t* out_trp[2][NGCF_MAX_LAYERS];    // NULL: direction/layer not wanted
+    int32_t* out_cnt[2][NGCF_MAX_LAYERS];    // NULL: direction/layer not wanted
 };
 
-constexpr int CP_THREADS = 128;
-constexpr int CP_PER = SP_TILE_ENT / CP_THREADS;     // entries per thread: entry q * 128 + tid, i.e. segment q * 4 + warp
-constexpr int CP_SEGS = SP_TILE_ENT / 32;            // 32-entry segments of a tile (= one warp ballot each)
-static_assert(CP_PER * CP_THREADS == SP_TILE_ENT, "tile entries must split evenly over the compaction CTA");
-
-// combo c = dir * n_layers + layer.  Order-preserving compaction by warp ballots: entry p of the tile sits in segment
-// p >> 5 at lane p & 31, its position among a combo's survivors is the segment's base + the survivors below its lane.
-// Consecutive lanes write consecutive survivors: the stores are coalesced without a shared-memory copy.
-// (First version: four consecutive entries per thread and packed 16-bit counters in 64-bit words — the bit loops and
-// variable 64-bit shifts of that bookkeeping cost twice the hashes; tools/spmm_timeline.py: 13.6 us per CTA.)
-template <int MAXC>
-__global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
-    __shared__ int rp_s[SP_TILE_ROWS + 1];
-    __shared__ uint32_t mask_s[MAXC][CP_SEGS];        // survivors of each segment, per combo
-    __shared__ int base_s[MAXC][CP_SEGS + 1];         // survivors before each segment; [CP_SEGS] = total
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 0] = gtime_ns();
-    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + blockIdx.x);
+// One WARP per tile (<= 128 entries: WS_PER per lane, entry q * 32 + lane), no barrier.  Order-preserving compaction by
+// warp ballots: the position of an entry among a combo's survivors is the survivors of earlier 32-entry segments plus
+// the survivors below its lane; consecutive lanes write consecutive survivors, so the stores are coalesced.
+constexpr int CW_WARPS = 4;
+__global__ void __launch_bounds__(CW_WARPS * 32) compact_kernel(CompactArgs a, int n_tiles) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * CW_WARPS + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const int4 raw = *reinterpret_cast<const int4*>(a.tiles + t);
     const TileInfo ti{raw.x, raw.y, raw.z, raw.w};
-    const int nr = ti.r1 - ti.r0, cnt = ti.e1 - ti.e0;
-    const int K = a.n_layers, n_combo = 2 * K;
-    for (int i = tid; i <= nr; i += CP_THREADS) rp_s[i] = a.rowptr[ti.r0 + i] - ti.e0;
+    const int cnt = ti.e1 - ti.e0;
+    const int K = a.n_layers;
     const bool want_l = a.out_ent[0][0] != nullptr, want_t = a.out_ent[1][0] != nullptr;
-    int2 e[CP_PER];
-    uint32_t kl[CP_PER], kt[CP_PER];
+    int2 e[WS_PER];
+    uint32_t kl[WS_PER], kt[WS_PER];
 #pragma unroll
-    for (int q = 0; q < CP_PER; ++q) {
-        const int p = q * CP_THREADS + tid;
+    for (int q = 0; q < WS_PER; ++q) {
+        const int p = q * 32 + lane;
         e[q] = make_int2(0, 0);
         kl[q] = kt[q] = 0;
         if (p < cnt) {
@@ -540,22 +535,17 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
             }
         }
     }
-    __syncthreads();
     const uint64_t seed = ngcf_seed(a.seed, a.seed_dev);
     const uint32_t thr = ngcf_threshold16(a.p);
-    uint32_t keep[CP_PER];                            // bit c = the entry survives combo c
+    uint32_t keep[WS_PER];                            // bit c = the entry survives combo c = dir * K + layer
 #pragma unroll
-    for (int q = 0; q < CP_PER; ++q) {
-        const int p = q * CP_THREADS + tid;
+    for (int q = 0; q < WS_PER; ++q) {
+        const int p = q * 32 + lane;
         keep[q] = 0;
         if (p < cnt) {
             if (!a.key_l) {                           // no static keys in the plan: derive them from the coordinates
-                int lo = 0, hi = nr - 1;              // last row with rp_s[row] <= p
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (rp_s[mid] <= p) lo = mid; else hi = mid - 1;
-                }
-                const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lo] : ti.r0 + lo) + a.row_off;
+                const int lr = ent_lrow(e[q].x);
+                const uint32_t r = (uint32_t)(a.row_key ? a.row_key[ti.r0 + lr] : ti.r0 + lr) + a.row_off;
                 kl[q] = ngcf_node_key(r, ent_col(e[q].x));
                 kt[q] = ngcf_node_key(ent_col(e[q].x), r);
             }
@@ -563,47 +553,24 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(CompactArgs a) {
             if (want_t) keep[q] |= node_keep_bits_key(thr, seed, K, kt[q]) << K;
         }
     }
-    if (a.dbg && tid == 0) a.dbg[blockIdx.x * 4 + 1] = gtime_ns();
-#pragma unroll
-    for (int q = 0; q < CP_PER; ++q)
-        for (int c = 0; c < n_combo; ++c) {
-            const uint32_t m = __ballot_sync(FULL_MASK, (keep[q] >> c) & 1u);
-            if (lane == 0) mask_s[c][q * (CP_THREADS / 32) + warp] = m;
-        }
-    __syncthreads();
-    if (tid < n_combo) {                              // 16 segment totals per combo: a serial scan is enough
-        int run = 0;
-        for (int sgm = 0; sgm < CP_SEGS; ++sgm) {
-            base_s[tid][sgm] = run;
-            run += __popc(mask_s[tid][sgm]);
-        }
-        base_s[tid][CP_SEGS] = run;
-    }
-    __syncthreads();
     const uint32_t below = (1u << lane) - 1u;
-#pragma unroll
-    for (int q = 0; q < CP_PER; ++q) {
-        const int sgm = q * (CP_THREADS / 32) + warp;
-        for (uint32_t m = keep[q]; m; m &= m - 1) {
-            const int c = __ffs(m) - 1;
-            const int dir = c >= K, layer = dir ? c - K : c;
-            a.out_ent[dir][layer][ti.e0 + base_s[c][sgm] + __popc(mask_s[c][sgm] & below)] = e[q];
-        }
-    }
-    for (int j = tid; j < (nr + 1) * n_combo; j += CP_THREADS) {
-        const int c = j / (nr + 1), i = j - c * (nr + 1);
+    for (int c = 0; c < 2 * K; ++c) {
         const int dir = c >= K, layer = dir ? c - K : c;
-        int32_t* trp = a.out_trp[dir][layer];
-        if (!trp) continue;
-        const int p = rp_s[i], sgm = p >> 5;          // p <= cnt <= 512: segment 16 = the total
-        int v = base_s[c][sgm];
-        if (sgm < CP_SEGS) v += __popc(mask_s[c][sgm] & ((1u << (p & 31)) - 1u));
-        trp[(size_t)blockIdx.x * (SP_TILE_ROWS + 1) + i] = v;
+        int2* out = a.out_ent[dir][layer];
+        if (!out) continue;
+        int base = 0;
+#pragma unroll
+        for (int q = 0; q < WS_PER; ++q) {
+            const bool k = (keep[q] >> c) & 1u;
+            const uint32_t m = __ballot_sync(FULL_MASK, k);
+            if (k) out[ti.e0 + base + __popc(m & below)] = e[q];
+            base += __popc(m);
+        }
+        if (lane == 0) a.out_cnt[dir][layer][t] = base;
     }
-    if (a.dbg) stamp_done(a.dbg);
 }
 
-// NGCF_B200_SPMM=rows selects the row-per-warp kernel (A/B comparisons); default: the streaming kernel for vector widths
+// NGCF_B200_SPMM=rows selects the row-per-warp kernel (A/B comparisons); default: the warp-streaming kernel
 bool spmm_use_stream() {
     static int v = -1;
     if (v < 0) {
@@ -614,12 +581,16 @@ bool spmm_use_stream() {
 }
 
 template <int G>
-int launch(const SpmmArgs& a, int n_ctas, cudaStream_t st) {
+int launch(const SpmmArgs& a, int n_ctas, bool stream, cudaStream_t st) {
     if (n_ctas <= 0) return NGCF_OK;
     if constexpr (G > 0) {
-        if (spmm_use_stream()) {
+        if (stream) {
             NGCF_CUDA(ngcf_launch_pdl(spmm_stream_kernel<G>, dim3((unsigned)n_ctas), dim3(SP_THREADS), 0, st, a));
             NGCF_LAUNCH_OK("spmm_stream_kernel");
+            if (a.n_hub > 0) {
+                NGCF_CUDA(ngcf_launch_pdl(hub_finish_kernel<G>, dim3((unsigned)ceil_div64(a.n_hub, 4)), dim3(128), 0, st, a));
+                NGCF_LAUNCH_OK("hub_finish_kernel");
+            }
             return NGCF_OK;
         }
     }
@@ -628,15 +599,15 @@ int launch(const SpmmArgs& a, int n_ctas, cudaStream_t st) {
     return NGCF_OK;
 }
 
-int launch_any(const SpmmArgs& a, int n_ctas, bool vec, cudaStream_t st) {
-    if (!vec) return launch<0>(a, n_ctas, st);
+int launch_any(const SpmmArgs& a, int n_ctas, bool vec, bool stream, cudaStream_t st) {
+    if (!vec) return launch<0>(a, n_ctas, false, st);
     const int d4 = a.d / 4;
-    if (d4 <= 1) return launch<1>(a, n_ctas, st);
-    if (d4 <= 2) return launch<2>(a, n_ctas, st);
-    if (d4 <= 4) return launch<4>(a, n_ctas, st);
-    if (d4 <= 8) return launch<8>(a, n_ctas, st);
-    if (d4 <= 16) return launch<16>(a, n_ctas, st);
-    return launch<32>(a, n_ctas, st);
+    if (d4 <= 1) return launch<1>(a, n_ctas, stream, st);
+    if (d4 <= 2) return launch<2>(a, n_ctas, stream, st);
+    if (d4 <= 4) return launch<4>(a, n_ctas, stream, st);
+    if (d4 <= 8) return launch<8>(a, n_ctas, stream, st);
+    if (d4 <= 16) return launch<16>(a, n_ctas, stream, st);
+    return launch<32>(a, n_ctas, stream, st);
 }
 
 unsigned long long* g_spmm_dbg = nullptr;    // host copy of the debug buffer pointer
@@ -663,7 +634,7 @@ int ngcf_check_csr(const ngcf_csr* g, const char* who) {
 extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, const float* addend, int64_t ld_add,
                          const int32_t* slot, const float* gsum, int64_t ld_gsum, float* hub_partial, float drop_p,
                          uint64_t seed, const uint64_t* seed_dev, int layer, int transposed, int64_t row_offset,
-                         const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_trp, float* Y, int64_t ldy,
+                         const uint8_t* keep_bits, const int32_t* c_ent, const int32_t* c_cnt, float* Y, int64_t ldy,
                          void* stream) {
     int rc = ngcf_check_csr(g, "spmm");
     if (rc != NGCF_OK) return rc;
@@ -674,7 +645,7 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     NGCF_REQUIRE(layer >= 0 && layer < NGCF_MAX_LAYERS, "spmm: layer %d", layer);
     NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "spmm: row_offset %lld", (long long)row_offset);
     NGCF_REQUIRE(!slot || gsum, "spmm: slot given without gsum");
-    NGCF_REQUIRE((c_ent == nullptr) == (c_trp == nullptr), "spmm: c_ent and c_trp go together");
+    NGCF_REQUIRE((c_ent == nullptr) == (c_cnt == nullptr), "spmm: c_ent and c_cnt go together");
     NGCF_REQUIRE(g->n_hub == 0 || hub_partial, "spmm: hub_partial scratch missing");
     NGCF_REQUIRE(g->n_tiles == 0 || g->tiles, "spmm: SpMM tiles missing");
     NGCF_REQUIRE(g->n_chunk_tiles == 0 || g->chunk_tiles, "spmm: chunk tiles missing");
@@ -684,17 +655,21 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
                      (!addend || (aligned16(addend) && ld_add % 4 == 0)) &&
                      (!slot || (aligned16(gsum) && ld_gsum % 4 == 0)) && (g->n_hub == 0 || aligned16(hub_partial));
     const bool hubs = g->n_hub > 0 && g->n_chunks > 0;
-    NGCF_REQUIRE(!hubs || g->hub_done, "spmm: hub_done counters missing");
+    // vector widths: the persistent warp-streaming kernel (needs the plan's work counter); NGCF_B200_SPMM=rows or any
+    // other width: the row-per-warp kernel
+    const bool stream_k = vec && spmm_use_stream() && g->work_ctr != nullptr && (!hubs || (g->tile_hubmask && g->hub_rows));
+    NGCF_REQUIRE(stream_k || !c_ent, "spmm: compacted survivor lists need the warp-streaming kernel (width %% 4 == 0)");
+    NGCF_REQUIRE(stream_k || !hubs || g->hub_done, "spmm: hub_done counters missing");
     SpmmArgs a{};
     a.rows = TileSide{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
-                      keep_bits, reinterpret_cast<const int2*>(c_ent), c_trp, Y, ldy};
+                      keep_bits, reinterpret_cast<const int2*>(c_ent), c_cnt, Y, ldy};
     a.n_chunk_tiles = hubs ? g->n_chunk_tiles : 0;
     if (hubs)
         a.chunks = TileSide{reinterpret_cast<const TileInfo*>(g->chunk_tiles), g->chunk_ptr,
                             reinterpret_cast<const int2*>(g->hub_ent), g->chunk_row,
                             keep_bits ? keep_bits + g->rowptr_nnz : nullptr,
                             c_ent ? reinterpret_cast<const int2*>(c_ent) + g->rowptr_nnz : nullptr,
-                            c_trp ? c_trp + (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : nullptr, hub_partial, d};
+                            c_cnt ? c_cnt + g->n_tiles : nullptr, hub_partial, d};
     a.X = X; a.ldx = (uint32_t)ldx; a.d = d;
     a.addend = addend; a.ld_add = ld_add; a.slot = slot; a.gsum = gsum; a.ld_gsum = ld_gsum;
     a.drop_p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.layer = layer; a.transposed = transposed;
@@ -705,7 +680,20 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     a.hub_done = g->hub_done;
     a.Yrows = Y;
     a.ld_yrows = ldy;
-    return launch_any(a, a.n_chunk_tiles + g->n_tiles, vec, st);
+    a.tile_hubmask = hubs ? g->tile_hubmask : nullptr;
+    a.work_ctr = g->work_ctr;
+    a.n_row_tiles = g->n_tiles;
+    a.hub_rows = g->hub_rows;
+    a.n_hub = hubs ? g->n_hub : 0;
+    if (stream_k && addend) {
+        // the streaming kernel ADDS its row sums to a Y that already holds the addend (in place when addend == Y)
+        if (addend != Y)
+            NGCF_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldy * sizeof(float), addend, (size_t)ld_add * sizeof(float),
+                                        (size_t)d * sizeof(float), (size_t)g->n_rows, cudaMemcpyDeviceToDevice, st));
+        a.add_mode = 1;
+        a.addend = nullptr;
+    }
+    return launch_any(a, a.n_chunk_tiles + g->n_tiles, vec, stream_k, st);
 }
 
 extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,
@@ -737,19 +725,19 @@ extern "C" int ngcf_node_dropout_bits(const ngcf_csr* g, float drop_p, uint64_t 
 
 extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64_t seed, const uint64_t* seed_dev,
                                          int n_layers, int64_t row_offset, int32_t* const* ent_as_L_host,
-                                         int32_t* const* trp_as_L_host, int32_t* const* ent_as_Lt_host,
-                                         int32_t* const* trp_as_Lt_host, void* stream) {
+                                         int32_t* const* cnt_as_L_host, int32_t* const* ent_as_Lt_host,
+                                         int32_t* const* cnt_as_Lt_host, void* stream) {
     int rc = ngcf_check_csr(g, "node_dropout_compact");
     if (rc != NGCF_OK) return rc;
     NGCF_REQUIRE(drop_p > 0.f && drop_p < 1.f, "node_dropout_compact: drop_p %f not in (0,1)", drop_p);
     NGCF_REQUIRE(n_layers >= 1 && n_layers <= NGCF_MAX_LAYERS, "node_dropout_compact: n_layers %d", n_layers);
-    NGCF_REQUIRE((ent_as_L_host && trp_as_L_host) || (ent_as_Lt_host && trp_as_Lt_host), "node_dropout_compact: no output");
-    NGCF_REQUIRE((ent_as_L_host == nullptr) == (trp_as_L_host == nullptr) &&
-                 (ent_as_Lt_host == nullptr) == (trp_as_Lt_host == nullptr), "node_dropout_compact: ent/trp go together");
+    NGCF_REQUIRE((ent_as_L_host && cnt_as_L_host) || (ent_as_Lt_host && cnt_as_Lt_host), "node_dropout_compact: no output");
+    NGCF_REQUIRE((ent_as_L_host == nullptr) == (cnt_as_L_host == nullptr) &&
+                 (ent_as_Lt_host == nullptr) == (cnt_as_Lt_host == nullptr), "node_dropout_compact: ent/cnt go together");
     NGCF_REQUIRE(row_offset >= 0 && row_offset < ((int64_t)1 << 31), "node_dropout_compact: row_offset");
     for (int k = 0; k < n_layers; ++k) {
-        NGCF_REQUIRE(!ent_as_L_host || (ent_as_L_host[k] && trp_as_L_host[k]), "node_dropout_compact: null L output %d", k);
-        NGCF_REQUIRE(!ent_as_Lt_host || (ent_as_Lt_host[k] && trp_as_Lt_host[k]), "node_dropout_compact: null L^T output %d", k);
+        NGCF_REQUIRE(!ent_as_L_host || (ent_as_L_host[k] && cnt_as_L_host[k]), "node_dropout_compact: null L output %d", k);
+        NGCF_REQUIRE(!ent_as_Lt_host || (ent_as_Lt_host[k] && cnt_as_Lt_host[k]), "node_dropout_compact: null L^T output %d", k);
     }
     cudaStream_t st = as_stream(stream);
     // pass 0: ordinary rows; pass 1: hub chunks (entry arrays continue after rowptr_nnz, tile arrays after n_tiles)
@@ -758,12 +746,10 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
         if (n_tiles <= 0 || (pass && g->n_hub == 0)) continue;
         CompactArgs a{};
         a.tiles = reinterpret_cast<const TileInfo*>(pass ? g->chunk_tiles : g->tiles);
-        a.rowptr = pass ? g->chunk_ptr : g->rowptr;
         a.ent = reinterpret_cast<const int2*>(pass ? g->hub_ent : g->ent);
         a.row_key = pass ? g->chunk_row : nullptr;
         a.p = drop_p; a.seed = seed; a.seed_dev = seed_dev; a.n_layers = n_layers; a.row_off = (uint32_t)row_offset;
-        const size_t e_off = pass ? (size_t)g->rowptr_nnz : 0, t_off = pass ? (size_t)g->n_tiles * (SP_TILE_ROWS + 1) : 0;
-        a.dbg = pass == 0 ? g_spmm_dbg_compact : nullptr;
+        const size_t e_off = pass ? (size_t)g->rowptr_nnz : 0, t_off = pass ? (size_t)g->n_tiles : 0;
         if (g->key_l && g->key_t && g->key_row_offset == row_offset) {
             a.key_l = g->key_l + e_off;
             a.key_t = g->key_t + e_off;
@@ -771,15 +757,14 @@ extern "C" int ngcf_node_dropout_compact(const ngcf_csr* g, float drop_p, uint64
         for (int k = 0; k < n_layers; ++k) {
             if (ent_as_L_host) {
                 a.out_ent[0][k] = reinterpret_cast<int2*>(ent_as_L_host[k]) + e_off;
-                a.out_trp[0][k] = trp_as_L_host[k] + t_off;
+                a.out_cnt[0][k] = cnt_as_L_host[k] + t_off;
             }
             if (ent_as_Lt_host) {
                 a.out_ent[1][k] = reinterpret_cast<int2*>(ent_as_Lt_host[k]) + e_off;
-                a.out_trp[1][k] = trp_as_Lt_host[k] + t_off;
+                a.out_cnt[1][k] = cnt_as_Lt_host[k] + t_off;
             }
         }
-        if (2 * n_layers <= 8) compact_kernel<8><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
-        else compact_kernel<16><<<(unsigned)n_tiles, CP_THREADS, 0, st>>>(a);
+        compact_kernel<<<(unsigned)ceil_div64(n_tiles, CW_WARPS), CW_WARPS * 32, 0, st>>>(a, n_tiles);
         NGCF_LAUNCH_OK(pass ? "compact_kernel(hub chunks)" : "compact_kernel(rows)");
     }
     return NGCF_OK;

@@ -17,7 +17,7 @@ namespace ngcf {
 constexpr int SPLIT = 128;          // rows with more entries than this are hubs; also the hub chunk size
 #ifndef NGCF_SPMM_TILE_ROWS
 #define NGCF_SPMM_TILE_ROWS 16
-#define NGCF_SPMM_TILE_ENT 512
+#define NGCF_SPMM_TILE_ENT 256
 #endif
 constexpr int SP_TILE_ROWS = NGCF_SPMM_TILE_ROWS;    // SpMM tile: at most this many rows ...
 constexpr int SP_TILE_ENT = NGCF_SPMM_TILE_ENT;   // ... and this many entries (staged in shared memory by one CTA)

@@ -97,6 +97,19 @@ class CsrSide:
         else:
             self.chunk_tiles = None
         self._pack_local_rows()
+        # per row tile: which of its rows are hubs (the streaming kernel must not write those: hub_finish_kernel does)
+        if self.n_hub and self.tiles.shape[0]:
+            hm = torch.zeros(self.n_rows + 32, dtype=torch.int64, device=dev)
+            hm[:self.n_rows] = hub_mask.to(torch.int64)
+            t0 = self.tiles[:, 0].to(torch.int64)
+            nr = (self.tiles[:, 1] - self.tiles[:, 0]).to(torch.int64)
+            bits = torch.zeros(self.tiles.shape[0], dtype=torch.int64, device=dev)
+            for i in range(int(lib.ngcf_spmm_tile_rows())):
+                bits |= (hm[t0 + i] * (i < nr).to(torch.int64)) << i
+            self.tile_hubmask = (bits & 0xFFFFFFFF).to(torch.int32)      # bit pattern of a uint32
+        else:
+            self.tile_hubmask = None
+        self.work_ctr = torch.zeros(2, **i32)    # tile counter + finished-warp counter of the streaming SpMM
         self.ent = None          # base entry pairs, set by LaplacianPlan
         self.key_l = self.key_t = None   # static node-dropout keys (ensure_keys)
         self.key_row_offset = 0
@@ -153,6 +166,8 @@ class CsrSide:
             s.n_chunks = self.n_chunks
             s.n_chunk_tiles = int(self.chunk_tiles.shape[0]) if self.chunk_tiles is not None else 0
             s.rowptr_nnz = self.nnz_short
+            s.tile_hubmask = _lib.ptr(self.tile_hubmask)
+            s.work_ctr = self.work_ctr.data_ptr()
             self._struct_cache[key] = s
         return s
 
@@ -199,8 +214,8 @@ class LaplacianPlan:
             raise ValueError("Laplacian indices out of range")
         if (shard.N_pad if shard is not None else self.N) >= (1 << CsrSide.LR_SHIFT):
             raise ValueError(f"graphs of up to {1 << CsrSide.LR_SHIFT} nodes are supported (27-bit column ids)")
-        if lib.ngcf_spmm_tile_rows() > 16:
-            raise RuntimeError("the local row tag of an entry assumes SpMM tiles of at most 16 rows")
+        if lib.ngcf_spmm_tile_rows() > 32:
+            raise RuntimeError("the local row tag of an entry assumes SpMM tiles of at most 32 rows")
         if shard is None:
             n_rows = n_cols = self.N
             pos = torch.arange(self.nnz, device=device)
@@ -272,7 +287,8 @@ def node_dropout_compact(side: CsrSide, drop_p: float, seed: int, seed_dev, n_la
                          as_L: bool = True, as_Lt: bool = False, static_keys: bool = True):
     """One step's node dropout applied like the reference does it (entries deleted, cumulatively per layer,
     NGCF.py:93-100): per layer the surviving entries of every SpMM tile, compacted, for ``side`` read as L and/or as
-    L^T.  Returns (per-layer list of (ent, trp) or None, same for L^T); pass one pair to ``spmm(compact=...)``."""
+    L^T.  Returns (per-layer list of (ent, cnt) or None, same for L^T): the survivors of tile t, in order, at the front of
+    the tile's slot range of ``ent`` and their number in ``cnt[t]``; pass one pair to ``spmm(compact=...)``."""
     lib = _lib.load()
     dev = side.rowptr.device
     if static_keys:
@@ -281,11 +297,10 @@ def node_dropout_compact(side: CsrSide, drop_p: float, seed: int, seed_dev, n_la
         side.key_l = side.key_t = None
         side._struct_cache.clear()
     n_t = int(side.tiles.shape[0]) + (int(side.chunk_tiles.shape[0]) if side.chunk_tiles is not None else 0)
-    per = lib.ngcf_spmm_tile_rows() + 1
 
     def alloc():
         return [(torch.empty(side.nnz + 2, 2, dtype=torch.int32, device=dev),
-                 torch.empty(n_t * per, dtype=torch.int32, device=dev)) for _ in range(n_layers)]
+                 torch.empty(max(n_t, 1), dtype=torch.int32, device=dev)) for _ in range(n_layers)]
 
     cl = alloc() if as_L else None
     ct = alloc() if as_Lt else None
@@ -307,10 +322,15 @@ def spmm(side: CsrSide, ent, X, d: int, out=None, addend=None, slot=None, gsum=N
          seed: int = 0, seed_dev=None, layer: int = 0, transposed: bool = False, row_offset: int = 0, keep_bits=None,
          compact=None):
     """Y = L·X (+ addend) (+ gsum[slot] rows) through ngcf_spmm; drop_p > 0 = in-kernel device-RNG node dropout;
-    compact = this layer's (ent, trp) pair from node_dropout_compact."""
+    compact = this layer's (ent, cnt) pair from node_dropout_compact.  With ``addend`` and no ``out`` the product is
+    accumulated IN PLACE into ``addend`` (which is returned): the streaming kernel adds its row sums to a Y that already
+    holds the addend, so a separate output would cost a copy."""
     lib = _lib.load()
     if out is None:
-        out = torch.empty(side.n_rows, d, dtype=torch.float32, device=X.device)
+        if addend is not None and d % 4 == 0 and addend.shape[0] == side.n_rows and addend.stride(0) % 4 == 0:
+            out = addend
+        else:
+            out = torch.empty(side.n_rows, d, dtype=torch.float32, device=X.device)
     _lib.check(lib.ngcf_spmm(C.byref(side.descriptor(ent)), X.data_ptr(), X.stride(0), d,
                              _lib.ptr(addend), addend.stride(0) if addend is not None else 0,
                              _lib.ptr(slot), _lib.ptr(gsum), gsum.stride(0) if gsum is not None else 0,

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.ngcf_abi_version() == 3
+    assert lib.ngcf_abi_version() == 4
     assert lib.ngcf_spmm_split_threshold() > 0
     # argument validation happens before any CUDA call
     need = ctypes.c_size_t(0)

@@ -72,6 +72,38 @@ __global__ void __launch_bounds__(64) ldg_kernel(const float* __restrict__ E, co
     if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
 }
 
+// ---- (d) the SpMM's CTA structure: one short-lived CTA per 512-entry tile; optionally the tile's ids are first staged in
+// shared memory by a coalesced read + barrier (what spmm_tile_kernel / spmm_stream_kernel do), then gathered from there;
+// PERSIST: the same tiles, but each CTA of a one-wave grid loops over tiles blockIdx.x, + gridDim.x, ...
+template <int U, bool STAGE, bool PERSIST>
+__global__ void __launch_bounds__(64, 20) tile_kernel(const float* __restrict__ E, const int* __restrict__ idx, int n_tiles,
+                                                      float* out) {
+    __shared__ int ids[512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 4, l = lane & 15;
+    const int grp = warp * 2 + g;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = blockIdx.x; t < n_tiles; t += PERSIST ? gridDim.x : n_tiles) {
+        const int* my = idx + (size_t)t * 512;
+        if (STAGE) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 512; i += 64) ids[i] = my[i];
+            __syncthreads();
+        }
+        const int* src = STAGE ? ids : my;
+        for (int j0 = grp * 128; j0 < (grp + 1) * 128; j0 += U) {      // contiguous quarter of the tile per lane group
+            int c[U];
+            float4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = src[j0 + u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = *reinterpret_cast<const float4*>(E + (size_t)c[u] * D + l * 4);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+
 // ---- (b) cp.async.bulk, one 256-byte copy per row; (c) gather4 -------------------------------------------------------
 // One producer warp issues the copies of a stage (ROWS rows) against the stage's mbarrier; CONS consumer warps wait, read
 // one word per row and release the stage.
@@ -197,6 +229,25 @@ int main(int argc, char** argv) {
         float ms16 = time_ms([&] { ldg_kernel<16><<<grid, 64>>>(E, idx, per, out); }, 5);
         printf("ldg   ctas/sm=%2d  U=4: %7.2f TB/s  U=8: %7.2f TB/s  U=16: %7.2f TB/s\n", cps, b / ms4 / 1e9, b / ms8 / 1e9,
                b / ms16 / 1e9);
+    }
+    CK(cudaGetLastError());
+    {
+        const int n_tiles = (int)(M / 512);
+        const double b = (double)n_tiles * 512 * D * 4;
+        float a1 = time_ms([&] { tile_kernel<4, false, false><<<n_tiles, 64>>>(E, idx, n_tiles, out); }, 5);
+        float a2 = time_ms([&] { tile_kernel<4, true, false><<<n_tiles, 64>>>(E, idx, n_tiles, out); }, 5);
+        float a3 = time_ms([&] { tile_kernel<4, true, true><<<n_sm * 20, 64>>>(E, idx, n_tiles, out); }, 5);
+        float a4 = time_ms([&] { tile_kernel<4, false, true><<<n_sm * 20, 64>>>(E, idx, n_tiles, out); }, 5);
+        printf("tiles of 512 (U=4, 64 threads, 20 CTAs/SM): one CTA per tile %7.2f TB/s | + staged ids %7.2f TB/s | "
+               "persistent + staged %7.2f TB/s | persistent, direct ids %7.2f TB/s\n", b / a1 / 1e9, b / a2 / 1e9, b / a3 / 1e9,
+               b / a4 / 1e9);
+        // the real product has 2.05 M entries = 4013 tiles = 1.36 waves of 2960 CTAs: same kernels on that many tiles
+        const int nt2 = 4013;
+        const double b2 = (double)nt2 * 512 * D * 4;
+        float c1 = time_ms([&] { tile_kernel<4, true, false><<<nt2, 64>>>(E, idx, nt2, out); }, 20);
+        float c2 = time_ms([&] { tile_kernel<4, true, true><<<n_sm * 20, 64>>>(E, idx, nt2, out); }, 20);
+        printf("4013 tiles (= one product): one CTA per tile, staged %7.2f TB/s (%.1f us) | persistent, staged %7.2f TB/s (%.1f us)\n",
+               b2 / c1 / 1e9, c1 * 1e3, b2 / c2 / 1e9, c2 * 1e3);
     }
     CK(cudaGetLastError());
 
