@@ -163,6 +163,18 @@ int ngcf_node_dropout_compact(const ngcf_csr* csr_host, float drop_p, uint64_t s
  * search and one hash per direction and entry. */
 int ngcf_entry_keys(const ngcf_csr* csr_host, int64_t row_offset, uint32_t* key_l, uint32_t* key_t, void* stream);
 
+/* ---- row-shard exchange over peer memory (multi-GPU row partition; the reference has no multi-device code) ----------
+ * Every rank holds a full [N_pad, d] copy of a matrix in peer-mapped (symmetric) memory and owns rows
+ * [row0, row0 + n_rows) of it.  ngcf_push_rows stores the owner's rows into every peer's copy and returns (in stream
+ * order) once every peer's rows have landed in the local copy: an all-gather without a library collective, one launch.
+ *   matrix_on_rank_host[r] : base address of rank r's copy as mapped into THIS process (r == rank: the local one)
+ *   flags_on_rank_host[r]  : rank r's flag block, ngcf_exchange_flag_words() uint32, zero before the first exchange
+ *   local_state            : uint32[2] in local device memory, zero before the first exchange
+ * Every rank must issue the same sequence of exchanges on the same flag blocks. */
+int ngcf_exchange_flag_words(void);
+int ngcf_push_rows(float* const* matrix_on_rank_host, uint32_t* const* flags_on_rank_host, uint32_t* local_state,
+                   int world, int rank, int64_t row0, int64_t n_rows, int d, void* stream);
+
 /* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
  * pack:  wcat[k, o] = W1[o,k] (k < d_in), W2[o,k-d_in] (k >= d_in);  bias_eff = 2*b1 + b2
  *        (the reference applies w1_list[i] twice, NGCF.py:131,133, so its bias counts twice). */

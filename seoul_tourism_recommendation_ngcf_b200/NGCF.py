@@ -96,8 +96,13 @@ class _Propagate(torch.autograd.Function):
             bias = torch.empty(d_out, dtype=torch.float32, device=dev)
             _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
                                              d_in, d_out, wcat.data_ptr(), bias.data_ptr(), _stream()), "pack_weights")
+            xkey = None
             if sh is None:
                 Xn = En = torch.empty(N, d_out, dtype=torch.float32, device=dev)
+            elif mod._xchg is not None and d_out % 4 == 0:
+                xkey = ("E", k + 1)                                    # persistent symmetric matrix: this rank's rows are
+                Xn = mod._xchg.matrix(xkey, sh.N_pad, d_out)           # written in place, then pushed to the peers
+                En = Xn[r0:r0 + nloc]
             else:
                 Xn = torch.empty(sh.N_pad, d_out, dtype=torch.float32, device=dev)
                 En = torch.zeros(nloc, d_out, dtype=torch.float32, device=dev) if nv < nloc else \
@@ -109,8 +114,10 @@ class _Propagate(torch.autograd.Function):
                                           _lib.ptr(st.mess_bits[k]), float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, En.data_ptr(),
                                           _stream()),
                        "dense_fwd")                                                          # NGCF.py:131-142
-            if sh is not None:
-                all_gather_rows(Xn, En, mod._group)                    # every rank needs all of E_{k+1}
+            if xkey is not None:
+                mod._xchg.push(xkey, r0, nloc)                         # every rank needs all of E_{k+1}
+            elif sh is not None:
+                all_gather_rows(Xn, En, mod._group)
             st.S.append(S)
             st.E.append(Xn)
         D = sum(st.dims)
@@ -170,8 +177,17 @@ class _Propagate(torch.autograd.Function):
         for k in range(K - 1, -1, -1):
             d_in, d_out = dims[k], dims[k + 1]
             col_off -= d_out
-            gS = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
-            gEl = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
+            peer = sh is not None and mod._xchg is not None and d_in % 4 == 0
+            if peer:                                                  # gS rows in place in the symmetric matrix
+                gS_all = mod._xchg.matrix(("gS", d_in), N_all, d_in)
+                gS = gS_all[r0:r0 + nloc]
+            else:
+                gS = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
+            if peer and k == 0:                                       # gE_0 = gEl + L^T gS accumulates in place in ITS matrix
+                gE0_all = mod._xchg.matrix(("gE0", d_in), N_all, d_in)
+                gEl = gE0_all[r0:r0 + nloc]
+            else:
+                gEl = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
             mm = st.mess_mult[k] if st.mess_mult is not None else None
             _lib.check(lib.ngcf_dense_bwd(_lib.ptr(gE_next), slot_loc.data_ptr(), gsum.data_ptr(), D, col_off,
                                           st.E[k + 1][r0:r0 + nloc].data_ptr(), st.S[k].data_ptr(),
@@ -183,7 +199,9 @@ class _Propagate(torch.autograd.Function):
                                           gEl.data_ptr(),
                                           gW1[k].data_ptr(), gb1[k].data_ptr(), gW2[k].data_ptr(), gb2[k].data_ptr(),
                                           gM_scratch.data_ptr(), _stream()), "dense_bwd")
-            if sh is not None:                                        # L^T gS needs every rank's rows of gS
+            if peer:                                                  # L^T gS needs every rank's rows of gS
+                mod._xchg.push(("gS", d_in), r0, nloc)
+            elif sh is not None:
                 gS_all = torch.empty(N_all, d_in, dtype=torch.float32, device=dev)
                 all_gather_rows(gS_all, gS, mod._group)
             else:
@@ -199,8 +217,12 @@ class _Propagate(torch.autograd.Function):
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
                    "rowgrad_reset")
         if sh is not None:
-            gE0 = torch.empty(N_all, dims[0], dtype=torch.float32, device=dev)
-            all_gather_rows(gE0, gE_next, mod._group)                 # tables are replicated: full gradient everywhere
+            if mod._xchg is not None and dims[0] % 4 == 0:
+                mod._xchg.push(("gE0", dims[0]), r0, nloc)             # tables are replicated: full gradient everywhere
+                gE0 = gE0_all.clone()                                  # (the matrix is reused by the next step)
+            else:
+                gE0 = torch.empty(N_all, dims[0], dtype=torch.float32, device=dev)
+                all_gather_rows(gE0, gE_next, mod._group)
             dist.all_reduce(flat, group=mod._group)                   # W/b gradients: sum of the row blocks
         else:
             gE0 = gE_next
@@ -272,6 +294,7 @@ class NGCF(nn.Module):
         self._seed_dev = None    # device uint64 added to the RNG key (set by graph.GraphedStep)
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None
+        self._xchg = None        # sharded.PeerExchange (peer-memory exchange) when available
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
@@ -313,11 +336,30 @@ class NGCF(nn.Module):
         self._shard = RowShards(self.n_user + self.n_item, world, rank)
         self._group = group
         self._plans, self._table, self._slot = {}, None, None
+        # per-layer exchange: peer-memory stores (sharded.PeerExchange) when symmetric memory is available on this box,
+        # NCCL all-gathers otherwise (NGCF_B200_EXCHANGE=nccl forces them: A/B timing)
+        self._xchg = None
+        if world > 1 and os.environ.get("NGCF_B200_EXCHANGE", "peer") != "nccl":
+            try:
+                from .sharded import PeerExchange
+                self._xchg = PeerExchange(group, self.user_embedding.weight.device)
+            except Exception as e:                                     # no symmetric memory / no peer access
+                self._xchg_error = f"{type(e).__name__}: {e}"
+                ok = torch.tensor([0], device=self.user_embedding.weight.device)
+            else:
+                ok = torch.tensor([1], device=self.user_embedding.weight.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # all ranks or none
+            if int(ok) == 0:
+                self._xchg = None
         return self
 
     def exchange_description(self) -> str:
         if self._shard is None:
             return "single GPU"
+        if self._xchg is not None:
+            return ("equal row blocks; per-layer exchange of E / gS / table-gradient rows by peer-memory stores over NVLink "
+                    "(ngcf_push_rows on symmetric memory, no NCCL collective on the data path), NCCL all-reduce of the "
+                    "W/b gradients")
         return "equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads"
 
     # ---- internal buffers ---------------------------------------------------------------------------

@@ -68,6 +68,8 @@ SIGNATURES = {
                          _vp, _vp],
     "ngcf_sample_negatives": [_vp, _vp, _vp, _i64, _vp, C.c_int, C.c_int, _u64, _vp, _vp, _vp],
     "ngcf_laplacian_entries": [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
+    "ngcf_exchange_flag_words": [],
+    "ngcf_push_rows": [C.POINTER(_vp), C.POINTER(_vp), _vp, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp],
     "ngcf_score_topk": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp],
 }
 
@@ -105,6 +107,11 @@ def ptr(t) -> int | None:
 
 def ptr_array(tensors):
     return (_vp * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def ptr_array_int(addrs):
+    """void*[] from raw integer addresses (peer-mapped pointers)."""
+    return (_vp * len(addrs))(*[int(a) for a in addrs])
 
 
 def int_array(vals):

@@ -30,16 +30,16 @@ bool ngcf_pdl_enabled() {
 }
 
 int ngcf_num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            return 148;
+    static int cached[64] = {};                        // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cached[dev & 63];
+    if (c == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c = n;
+        else return 148;
     }
-    return cached;
+    return c;
 }
 
 // ---- TMA descriptors (tmap.h) ------------------------------------------------------------------------------------------

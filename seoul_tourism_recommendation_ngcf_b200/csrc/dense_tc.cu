@@ -1211,7 +1211,11 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
                       const float* bias_eff, float slope, const float* mess_mult, const uint32_t* mess_bits, float mess_p,
                       uint64_t seed, const uint64_t* seed_dev, int layer, int64_t row_offset, float* E_out,
                       cudaStream_t st) {
-    static bool attr_set = false;
+    // (function attributes are per device: a module on cuda:1 needs them set there too)
+    static bool attr_set_dev[64] = {};
+    int cur_dev = 0;
+    NGCF_CUDA(cudaGetDevice(&cur_dev));
+    bool& attr_set = attr_set_dev[cur_dev & 63];
     if (!attr_set) {
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NGCF_CUDA(cudaFuncSetAttribute(dense_fwd_tma_kernel<MM_MULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1305,11 +1309,7 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
         default: kern = pre ? dense_bwd_tc_kernel<MM_HASH, true> : dense_bwd_tc_kernel<MM_HASH, false>; break;
     }
     NGCF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    static bool attr_set = false;
-    if (!attr_set) {
-        NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    NGCF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     for (int ih = 0; ih < IH; ++ih)
         for (int oh = 0; oh < OH; ++oh) {
             BwdTcArgs a{gE_next, slot, gsum, ld_gsum, col_off, E_out, S, E, n_rows, 64, bn, W1, W2, slope, mess_mult,

@@ -274,11 +274,7 @@ int ngcf_score_topk_tc(const float* U, int64_t n_users, const float* I, int64_t 
     if (skip < 0) { const char* e = getenv("NGCF_B200_TOPK_SKIP_EPI"); skip = (e && e[0] == '1') ? 1 : 0; }
     ScoreTcArgs a{Up, Ip, n_users, n_items, D, k, n_split, (int)((itiles + n_split - 1) / n_split), pv, pi, skip};
     const size_t smem = 1024 + (size_t)ST_STAGES * ST_STAGE_BYTES + (size_t)(k + ST_EXTRA) * ST_ROWS * 8 + sizeof(ScoreBars);
-    static bool attr_set = false;
-    if (!attr_set) {
-        NGCF_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    NGCF_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
     dim3 grid((unsigned)ut, (unsigned)n_split);
     score_topk_tc_kernel<<<grid, ST_THREADS, smem, st>>>(a);
     NGCF_LAUNCH_OK("score_topk_tc_kernel");

@@ -90,6 +90,64 @@ def all_gather_rows(out: torch.Tensor, shard: torch.Tensor, group=None):
     return out
 
 
+class PeerExchange:
+    """All-gathers of row blocks by peer-memory stores (``ngcf_push_rows``) instead of NCCL collectives.
+
+    Every exchanged matrix lives in symmetric memory (``torch.distributed._symmetric_memory``: the same allocation
+    mapped into every rank of the box over NVLink); the producing kernel writes this rank's rows straight into the
+    local copy, one launch then stores them into every peer's copy and returns once the peers' rows have landed here.
+    Buffers are persistent (one per key), so a captured CUDA graph replays against fixed addresses; reuse across steps is
+    safe because a peer only stores into a copy after its owner has reached the same exchange (see exchange.cu)."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._symm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = torch.device(device)
+        lib = _lib.load()
+        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+        if enable is not None:
+            try:
+                enable(self.group.group_name)
+            except Exception:
+                pass
+        self.flags = symm_mem.empty(lib.ngcf_exchange_flag_words(), dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        self._flag_hdl = symm_mem.rendezvous(self.flags, self.group)
+        self._flag_ptrs = _lib.ptr_array_int([int(p) for p in self._flag_hdl.buffer_ptrs])
+        self.local_state = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._mats = {}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)                    # every rank's flag block is zero before anyone signals
+
+    def matrix(self, key, n_rows: int, d: int) -> torch.Tensor:
+        """The persistent symmetric [n_rows, d] fp32 matrix of ``key`` (allocated collectively on first use)."""
+        ent = self._mats.get(key)
+        if ent is None:
+            t = self._symm.empty(n_rows * d, dtype=torch.float32, device=self.device)
+            t.zero_()
+            hdl = self._symm.rendezvous(t, self.group)
+            from . import _lib
+            ptrs = _lib.ptr_array_int([int(p) for p in hdl.buffer_ptrs])
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)                # zero-filled everywhere before the first stores arrive
+            ent = self._mats[key] = (t.view(n_rows, d), hdl, ptrs)
+        if ent[0].shape != (n_rows, d):
+            raise RuntimeError(f"exchange matrix {key!r} was created as {tuple(ent[0].shape)}, asked for {(n_rows, d)}")
+        return ent[0]
+
+    def push(self, key, row0: int, n_rows: int):
+        """This rank's rows [row0, row0 + n_rows) of matrix ``key`` -> every peer; returns (in stream order) with every
+        peer's rows present in the local copy."""
+        from . import _lib
+        mat, _, ptrs = self._mats[key]
+        lib = _lib.load()
+        _lib.check(lib.ngcf_push_rows(ptrs, self._flag_ptrs, self.local_state.data_ptr(), self.world, self.rank,
+                                      int(row0), int(n_rows), int(mat.shape[1]), _lib.current_stream()), "push_rows")
+
+
 def parity_vs_unsharded(emb: int, layers: list, L: torch.Tensor, num_dict: dict, batch: dict, batch_size: int, device,
                         node_p: float = 0.3, mess_p: float = 0.1, weight_decay: float = 0.025, group=None) -> dict:
     """Runs ONE training step (forward + BPR + backward, node and message dropout ON, device RNG) twice on this rank's
