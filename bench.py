@@ -208,8 +208,20 @@ def run_ours(args):
     lib = _lib.load()
     L, batches, info = make_workload(args.shape)
     model = make_model(info, L, dev).to(dev)
+    shards = None
     if world > 1:
-        model.shard()          # row partition + per-layer all-gather (sharded.py); every rank steps the same batches
+        # row partition (sharded.py); every rank steps the same batches.  With the peer-memory exchange the blocks are cut
+        # by work (entries + 32 per row) instead of by row count: item rows are several times heavier than user rows
+        if os.environ.get("NGCF_B200_EXCHANGE", "peer") != "nccl" and os.environ.get("NGCF_B200_SHARDS", "balanced") == "balanced":
+            from seoul_tourism_recommendation_ngcf_b200.sharded import BalancedShards
+            row_nnz = np.bincount(L._indices()[0].numpy(), minlength=int(L.shape[0]))
+            shards = BalancedShards(int(L.shape[0]), world, rank, BalancedShards.cut(row_nnz + 32.0, world))
+        try:
+            model.shard(shards=shards)
+        except RuntimeError as e:                                     # no peer-memory exchange here: equal blocks + NCCL
+            log(f"[bench] {e}; falling back to equal blocks")
+            shards = None
+            model.shard()
     model.train()
 
     def max_over_ranks(ms: float) -> float:
@@ -232,7 +244,7 @@ def run_ours(args):
         pb = {k: torch.from_numpy(v) for k, v in batches[0].items()}
         res = parity_vs_unsharded(info["emb"], [info["emb"]] * info["layers"], L,
                                   synth.num_dict_for(info["n_user"], info["n_item"]), pb, BATCH, dev,
-                                  node_p=NODE_P, mess_p=MESS_P, weight_decay=WEIGHT_DECAY)
+                                  node_p=NODE_P, mess_p=MESS_P, weight_decay=WEIGHT_DECAY, shards=shards)
         worst = torch.tensor([res["out"], res["loss"], res["all_E"], res["worst_grad"]], dtype=torch.float64, device=dev)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)                 # the worst rank's figures
         parity = {"out": float(worst[0]), "loss": float(worst[1]), "all_E": float(worst[2]),
@@ -485,6 +497,8 @@ def run_ours(args):
         "run": {"nnz": int(L._nnz()), "N": int(L.shape[0]),
                 "parallelism": "single GPU" if world == 1 else
                 f"row-sharded x{world} ({model.exchange_description()})",
+                "row_blocks": None if world == 1 else ("balanced by entries + 32 per row: " + str(shards.starts) if shards
+                                                       is not None else "equal"),
                 "rng": "device (counter-based hash); node-dropout survivors compacted once per step",
                 "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)", "api": api},
         "parity_vs_1gpu": parity,
@@ -505,6 +519,183 @@ def run_ours(args):
     if world > 1:
         sys.stderr.flush()
         os._exit(0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 5 and its family: graphs generated on the device per row shard (no host copy exists)
+# ------------------------------------------------------------------------------------------------------------
+def run_pl(args):
+    import torch.distributed as dist
+    import seoul_tourism_recommendation_ngcf_b200 as pkg
+    from seoul_tourism_recommendation_ngcf_b200 import _lib, plgraph, synth
+    from seoul_tourism_recommendation_ngcf_b200.plan import node_dropout_bits, node_dropout_compact, spmm
+    from seoul_tourism_recommendation_ngcf_b200.sharded import BalancedShards, RowShards, parity_vs_unsharded
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (torchrun)")
+    balanced = os.environ.get("NGCF_B200_EXCHANGE", "peer") != "nccl" and os.environ.get("NGCF_B200_SHARDS", "balanced") == "balanced"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl")
+    lib = _lib.load()
+    n_user, n_item, n_edges, emb, K = synth.SHAPES[args.shape]
+    N = n_user + n_item
+    nd = synth.num_dict_for(n_user, n_item)
+    steps = min(args.steps, 10)
+    warm = max(min(args.warmup, 3), 3)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- N > 1: the sharded step on a device-built shard must be the 1-GPU step (checked on the 1/100-scale graph) -------
+    parity = None
+    if world > 1:
+        pu, pi, pe, _, _ = synth.SHAPES["pl-10m"]
+        shp = BalancedShards(pu + pi, world, rank, BalancedShards.cut_bipartite(pu, pi, pe, world)) if balanced \
+            else RowShards(pu + pi, world, rank)
+        L_full = plgraph.powerlaw_laplacian(pu, pi, pe, dev)
+        L_part = plgraph.powerlaw_laplacian(pu, pi, pe, dev, shard=shp)
+        pb = {k: torch.from_numpy(v) for k, v in synth.random_batch(pu, pi, BATCH, seed=1).items()}
+        res = parity_vs_unsharded(emb, [emb] * K, L_full, synth.num_dict_for(pu, pi), pb, BATCH, dev, node_p=NODE_P,
+                                  mess_p=MESS_P, weight_decay=WEIGHT_DECAY, L_shard=L_part, shards=shp)
+        worst = torch.tensor([res["out"], res["loss"], res["all_E"], res["worst_grad"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity = {"out": float(worst[0]), "loss": float(worst[1]), "all_E": float(worst[2]), "worst_grad": float(worst[3]),
+                  "tolerance": 1e-5, "what": "pl-10m (the same generator at 1/100 scale): one training step on device-built "
+                  "row shards vs the same step on the unsharded device-built graph on each rank's own GPU"}
+        log(f"[bench] parity_vs_1gpu (pl-10m): {parity}")
+        del L_full, L_part
+        torch.cuda.empty_cache()
+        if max(parity["out"], parity["loss"], parity["all_E"], parity["worst_grad"]) > 1e-5:
+            if rank == 0:
+                emit({"metric": METRIC, "error": "row-sharded step differs from the 1-GPU step", "n_gpus": world,
+                      "parity_vs_1gpu": parity})
+            os._exit(3)
+
+    t0 = time.time()
+    sh = None
+    if world > 1:
+        sh = BalancedShards(N, world, rank, BalancedShards.cut_bipartite(n_user, n_item, n_edges, world)) if balanced \
+            else RowShards(N, world, rank)
+    csr = plgraph.powerlaw_laplacian(n_user, n_item, n_edges, dev, shard=sh)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
+    nnz_tot = torch.tensor([csr.nnz], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(nnz_tot)
+    nnz_tot = int(nnz_tot)
+    log(f"[bench] rank {rank}: device-built Laplacian shard in {t_graph:.1f}s: rows {csr.n_rows}, nnz {csr.nnz} (all ranks {nnz_tot})")
+    torch.manual_seed(0)
+    t0 = time.time()
+    model = pkg.NGCF(emb, [emb] * K, NODE_P, [MESS_P] * K, 1.0, [csr, csr], nd, BATCH, torch.device("cpu")).to(dev)
+    if world > 1:
+        model.shard(shards=sh)
+    model.train()
+    # survivor lists cost 8 B x nnz per layer and direction: past ~40 GB the step uses per-step decision bytes instead
+    if csr.nnz * 8 * 2 * K > 40e9:
+        model._node_mode = "bits"
+    crit = pkg.BPR(WEIGHT_DECAY, BATCH)
+    batches = [synth.random_batch(n_user, n_item, BATCH, seed=1 + j) for j in range(4)]
+    hb = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
+    gstep = pkg.GraphedStep(model, crit, BATCH, node_flag=True)
+    for j in range(warm):
+        gstep(hb[j % len(hb)])
+    fence()
+    t_plan = time.time() - t0
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    w0 = time.time()
+    fence()
+    db = [{k: (v if k == "year" else v.to(dev)) for k, v in b.items()} for b in hb]
+    for j in range(steps):
+        ev[j][0].record()
+        gstep(db[j % len(db)])
+        ev[j][1].record()
+    fence()
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    last = 0.0
+    for j in range(steps):
+        last = float(gstep(hb[j % len(hb)]).detach())
+    e1.record()
+    fence()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
+    windows = [(w0, time.time())]
+    # roofline: layer 0's product on this rank's shard, exactly as the step runs it
+    plan = model._last.plan
+    r0 = model._shard.r0 if model._shard else 0
+    X = model._packed_table()
+    Y = torch.empty(plan.fwd.n_rows, emb, device=dev)
+    if model._node_mode == "compact":
+        comp, _ = node_dropout_compact(plan.fwd, NODE_P, 1, None, K, r0, as_L=True, as_Lt=False)
+        kept = int(comp[0][1].sum())
+        run = lambda: spmm(plan.fwd, None, X, emb, out=Y, compact=comp[0])
+    else:
+        bits, _ = node_dropout_bits(plan.fwd, NODE_P, 1, None, K, r0, as_L=True, as_Lt=False)
+        kept = plan.fwd.nnz
+        run = lambda: spmm(plan.fwd, None, X, emb, out=Y, keep_bits=bits, layer=0)
+    for _ in range(2):
+        run()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    torch.cuda.synchronize()
+    for a_, b_ in kev:
+        a_.record(); run(); b_.record()
+    torch.cuda.synchronize()
+    k_ms = statistics.mean(a_.elapsed_time(b_) for a_, b_ in kev)
+    alg = 8 * kept + 4 * (plan.fwd.n_rows + 1) + 4 * N * emb + 4 * plan.fwd.n_rows * emb
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    clocks = sampler.stop(windows)
+    mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    fence()
+    if rank != 0:
+        os._exit(0)
+    spe = n_edges // BATCH
+    out = {
+        "metric": METRIC, "value": round(ms * spe / 1e3, 3), "unit": "s/epoch", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": round(ms, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.shape}-shaped synthetic power-law graph (Zipf 0.8) generated on the device per row "
+                               f"shard, {n_user} users / {n_item} items / {n_edges} interactions, emb {emb}, {K} layers, "
+                               f"batch {BATCH}, node_flag=True, training mode", "steps_per_epoch": spe},
+        "run": {"nnz": nnz_tot, "N": N, "parallelism": "single GPU" if world == 1 else
+                f"row-sharded x{world} ({model.exchange_description()})",
+                "row_blocks": None if world == 1 else (f"balanced by entries + 32 per row: {sh.starts}" if balanced else "equal"),
+                "node_dropout": model._node_mode,
+                "graph_build_s": round(t_graph, 2), "plan_and_capture_s": round(t_plan, 2),
+                "peak_device_memory_gib_rank0": round(mem, 2), "l2": "working set exceeds L2 (no flush needed)",
+                "api": "GraphedStep over the drop-in modules; lap_list = device-built CSR row shards (plgraph.py)"},
+        "parity_vs_1gpu": parity,
+        "e2e": {"value": round(ms_e2e * spe / 1e3, 3), "unit": "s/epoch", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": 8 * BATCH * 8, "d2h_bytes_per_step": 4, "last_loss": last},
+        "gpu_launches": int(gstep.launches_per_step * steps), "gpu_launches_per_step": gstep.launches_per_step,
+        "roofline": {"kernel": f"ngcf_spmm (streaming kernel), layer 0 of the step on rank 0's row shard, node dropout "
+                               f"'{model._node_mode}'", "bound": "hbm", "achieved": round(alg / (k_ms * 1e-3) / 1e9, 1),
+                     "peak": peak, "unit": "GB/s", "frac": round(alg / (k_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                     "algorithmic_bytes": alg, "entries_gathered": kept, "kernel_ms": round(k_ms, 4),
+                     "note": "E (3.8 GB at pl-1b) does not fit L2: every gathered 256-byte row is an HBM access; "
+                             "gathered bytes = entries x 256"},
+        "cpu_baseline": None, "torch_cuda_baseline": None, "clocks": clocks,
+        "note": "the reference cannot build this graph at all (dense N x N Laplacian, matrix.py:55-62); no CPU baseline",
+    }
+    emit(out)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -739,6 +930,10 @@ def time_oracle(L, batches, info, max_steps, warmup, budget_s):
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.shape.startswith("pl-"):
+        emit({"impl": "reference", "unavailable": "the reference builds its Laplacian through dense N x N arrays "
+              "(matrix.py:55-62) and cannot hold this graph; no CPU run exists for the device-generated pl-* shapes"})
+        return
     L, batches, info = make_workload(args.shape)
     res = time_cpu_reference(L, batches, info, max_steps=args.steps, warmup=min(args.warmup, 2), budget_s=200.0)
     spe = info["steps_per_epoch"]
@@ -758,5 +953,7 @@ if __name__ == "__main__":
     protect_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif a.shape.startswith("pl-"):
+        run_pl(a)
     else:
         run_ours(a)

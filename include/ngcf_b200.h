@@ -163,6 +163,19 @@ int ngcf_node_dropout_compact(const ngcf_csr* csr_host, float drop_p, uint64_t s
  * search and one hash per direction and entry. */
 int ngcf_entry_keys(const ngcf_csr* csr_host, int64_t row_offset, uint32_t* key_l, uint32_t* key_t, void* stream);
 
+/* ---- graph construction on the device (matrix.py:41-83 for graphs the reference's dense builder cannot hold) --------
+ * ngcf_plgraph_entries: adjacency entries of a synthetic power-law bipartite graph (Zipf(alpha) user activity and item
+ * popularity, edge e a pure function of (seed, e)) for the rows [row0, row0 + n_rows) of the (n_user + n_item)-node
+ * graph, both directions of every edge, as unsorted 64-bit keys (row - row0) << 32 | col appended through *total_dev
+ * (zero on entry; keys_or_null == NULL only counts).  Sorting + deduplicating the keys gives the shard's CSR.
+ * ngcf_build_tiles: the SpMM tile list {r0, r1, e0, e1} (greedy: <= max_rows rows, <= max_ent entries) of a CSR;
+ * next_scratch is int32[n_rows]; *count_out receives the number of tiles (tiles beyond capacity are not written). */
+int ngcf_plgraph_entries(int64_t n_user, int64_t n_item, int64_t n_edges, double alpha, uint64_t seed,
+                         int64_t row0, int64_t n_rows, unsigned long long* total_dev,
+                         unsigned long long* keys_or_null, int64_t capacity, void* stream);
+int ngcf_build_tiles(const int32_t* rowptr, int64_t n_rows, int max_rows, int max_ent, int32_t* next_scratch,
+                     int32_t* tiles_out, int64_t capacity, int32_t* count_out, void* stream);
+
 /* ---- row-shard exchange over peer memory (multi-GPU row partition; the reference has no multi-device code) ----------
  * Every rank holds a full [N_pad, d] copy of a matrix in peer-mapped (symmetric) memory and owns rows
  * [row0, row0 + n_rows) of it.  ngcf_push_rows stores the owner's rows into every peer's copy and returns (in stream

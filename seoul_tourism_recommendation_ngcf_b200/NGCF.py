@@ -323,7 +323,7 @@ class NGCF(nn.Module):
         self.mess_dropout_list = nn.Sequential(*md)
 
     # ---- multi-GPU ------------------------------------------------------------------------------------
-    def shard(self, group=None):
+    def shard(self, group=None, shards=None):
         """Row-partitions the propagation over the ranks of ``group`` (default process group): this rank then
         computes rows [rank*rows, (rank+1)*rows) of every layer (sharded.py).  Parameters stay replicated; every
         rank must call forward with the same batch and the same torch CPU RNG state (the per-step RNG key is drawn
@@ -333,7 +333,9 @@ class NGCF(nn.Module):
         if self.rng != "device":
             raise ValueError("row-sharded runs need rng='device' (masks are keyed on global coordinates in-kernel)")
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        self._shard = RowShards(self.n_user + self.n_item, world, rank)
+        self._shard = shards if shards is not None else RowShards(self.n_user + self.n_item, world, rank)
+        if self._shard.N != self.n_user + self.n_item or self._shard.world != world or self._shard.rank != rank:
+            raise ValueError("the shard descriptor does not match this model / process group")
         self._group = group
         self._plans, self._table, self._slot = {}, None, None
         # per-layer exchange: peer-memory stores (sharded.PeerExchange) when symmetric memory is available on this box,
@@ -351,6 +353,9 @@ class NGCF(nn.Module):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # all ranks or none
             if int(ok) == 0:
                 self._xchg = None
+        if self._xchg is None and world > 1 and not getattr(self._shard, "equal", True):
+            raise RuntimeError("unequal row blocks (BalancedShards) need the peer-memory exchange, which is not available "
+                               "here: " + getattr(self, "_xchg_error", "disabled by NGCF_B200_EXCHANGE=nccl"))
         return self
 
     def exchange_description(self) -> str:

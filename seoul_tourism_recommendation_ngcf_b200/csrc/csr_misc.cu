@@ -250,3 +250,46 @@ extern "C" int ngcf_feature_mix(float* user_w, int64_t n_user, int d, const floa
     NGCF_LAUNCH_OK("featmix_apply_kernel");
     return NGCF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// SpMM tiles on the device (plan.greedy_tiles for graphs whose tile count rules out a host loop): consecutive tiles of at
+// most max_rows rows and max_ent entries.  next[r] = end of the tile that starts at row r, for every r in parallel; the
+// tile list is the orbit of row 0 under next[], walked by one thread (one dependent load per tile).
+// ------------------------------------------------------------------------------------------------
+__global__ void tile_next_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int max_rows, int max_ent,
+                                 int32_t* __restrict__ next) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int64_t limit = (int64_t)rowptr[r] + max_ent;
+    int64_t lo = r, hi = min(n_rows, r + max_rows);                    // last k in [r, hi] with rowptr[k] <= limit
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (rowptr[mid] <= limit) lo = mid; else hi = mid - 1;
+    }
+    next[r] = (int32_t)max(r + 1, lo);
+}
+__global__ void tile_chase_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ next, int64_t n_rows,
+                                  int4* __restrict__ tiles, int64_t capacity, int32_t* __restrict__ count) {
+    int64_t n = 0;
+    for (int64_t r = 0; r < n_rows;) {
+        const int32_t r1 = next[r];
+        if (n < capacity) tiles[n] = make_int4((int)r, r1, rowptr[r], rowptr[r1]);
+        ++n;
+        r = r1;
+    }
+    *count = (int32_t)n;
+}
+
+extern "C" int ngcf_build_tiles(const int32_t* rowptr, int64_t n_rows, int max_rows, int max_ent, int32_t* next_scratch,
+                                int32_t* tiles_out, int64_t capacity, int32_t* count_out, void* stream) {
+    NGCF_REQUIRE(rowptr && next_scratch && tiles_out && count_out, "build_tiles: null pointer");
+    NGCF_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31) && max_rows >= 1 && max_ent >= 1, "build_tiles: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    if (n_rows > 0) {
+        tile_next_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, max_rows, max_ent, next_scratch);
+        NGCF_LAUNCH_OK("tile_next_kernel");
+    }
+    tile_chase_kernel<<<1, 1, 0, st>>>(rowptr, next_scratch, n_rows, reinterpret_cast<int4*>(tiles_out), capacity, count_out);
+    NGCF_LAUNCH_OK("tile_chase_kernel");
+    return NGCF_OK;
+}

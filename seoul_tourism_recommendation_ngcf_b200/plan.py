@@ -40,10 +40,37 @@ def greedy_tiles(rowptr: np.ndarray, max_rows: int, max_ent: int) -> np.ndarray:
     return np.asarray(out, dtype=np.int32).reshape(-1, 4)
 
 
+def device_tiles(rowptr: torch.Tensor, max_rows: int, max_ent: int) -> torch.Tensor:
+    """``greedy_tiles`` evaluated on the device (``ngcf_build_tiles``): same tiles, no host loop — a 1 B-edge graph has
+    millions of them.  rowptr: int32 [n + 1] CUDA tensor.  Returns int32 [n_tiles, 4] on the device."""
+    lib = _lib.load()
+    dev = rowptr.device
+    n = int(rowptr.numel()) - 1
+    if n <= 0:
+        return torch.zeros(0, 4, dtype=torch.int32, device=dev)
+    nxt = torch.empty(n, dtype=torch.int32, device=dev)
+    cap = n                                               # at most one tile per row
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    # worst case one tile per row; allocate for the entry bound first and fall back to the row bound if it overflows
+    guess = int(min(n, int(rowptr[-1]) // max(1, max_ent // 2) + n // max_rows + 16))
+    for capacity in (guess, cap):
+        tiles = torch.empty(capacity, 4, dtype=torch.int32, device=dev)
+        _lib.check(lib.ngcf_build_tiles(rowptr.data_ptr(), n, int(max_rows), int(max_ent), nxt.data_ptr(),
+                                        tiles.data_ptr(), capacity, count.data_ptr(), _stream()), "build_tiles")
+        if int(count) <= capacity:
+            return tiles[:int(count)].contiguous()
+    raise RuntimeError("tile builder overflow")
+
+
+DEVICE_TILE_ROWS = 1 << 18        # CSRs with more rows than this get their tiles built on the device
+
+
 class CsrSide:
     """One direction (L or L^T) in execution layout; owns the device arrays behind an ``ngcf_csr`` struct."""
 
-    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, perm: torch.Tensor, n_rows: int, nnz: int):
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, perm, n_rows: int, nnz: int, vals=None):
+        """perm: position of each entry in the COO value array (reference-format Laplacians), or None with ``vals`` =
+        the entries' values in CSR order (device-built CSR Laplacians, plgraph.py)."""
         lib = _lib.load()
         dev = rowptr.device
         self.n_rows, self.nnz = int(n_rows), int(nnz)
@@ -53,12 +80,18 @@ class CsrSide:
         hub_mask = deg > split
         hub = torch.nonzero(hub_mask).flatten()
         self.n_hub = int(hub.numel())
-        colidx, perm = colidx[:self.nnz], perm[:self.nnz]
+        colidx = colidx[:self.nnz]
+        perm = perm[:self.nnz] if perm is not None else None
+        self.vals = vals
         if self.n_hub:
             row_of_entry = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), deg)
             ent_is_hub = hub_mask[row_of_entry]
             order = torch.cat([torch.nonzero(~ent_is_hub).flatten(), torch.nonzero(ent_is_hub).flatten()])
-            self.colidx, self.perm = colidx[order].contiguous(), perm[order].contiguous()
+            self.colidx = colidx[order].contiguous()
+            self.perm = perm[order].contiguous() if perm is not None else None
+            if vals is not None:
+                self.vals = vals[order].contiguous()
+            del row_of_entry, ent_is_hub, order
             hdeg = deg[hub]
             self.nnz_hub = int(hdeg.sum())
             short_deg = torch.where(hub_mask, torch.zeros_like(deg), deg)
@@ -81,21 +114,21 @@ class CsrSide:
             self.hub_rows = hub.to(torch.int32).contiguous()
             self.hub_done = torch.zeros(self.n_hub, **i32)   # completion counters of the product in flight
         else:
-            self.colidx, self.perm = colidx.contiguous(), perm.contiguous()
+            self.colidx, self.perm = colidx.contiguous(), (perm.contiguous() if perm is not None else None)
             self.nnz_hub, self.n_chunks = 0, 0
             short_deg = deg
             self.hub_of_row = self.hub_chunk_ptr = self.chunk_ptr = self.chunk_row = self.hub_rows = self.hub_done = None
         self.nnz_short = self.nnz - self.nnz_hub
         self.rowptr = torch.zeros(self.n_rows + 1, **i32)
         self.rowptr[1:] = torch.cumsum(short_deg, 0).to(torch.int32)
-        rp_host = self.rowptr.cpu().numpy()
-        self.tiles = torch.from_numpy(greedy_tiles(rp_host, lib.ngcf_spmm_tile_rows(),
-                                                   lib.ngcf_spmm_tile_entries())).to(dev)
-        if self.n_chunks:
-            self.chunk_tiles = torch.from_numpy(greedy_tiles(self.chunk_ptr.cpu().numpy(), lib.ngcf_spmm_tile_rows(),
-                                                             lib.ngcf_spmm_tile_entries())).to(dev)
+        tr, te = lib.ngcf_spmm_tile_rows(), lib.ngcf_spmm_tile_entries()
+        if self.n_rows > DEVICE_TILE_ROWS:
+            self.tiles = device_tiles(self.rowptr, tr, te)
+            self.chunk_tiles = device_tiles(self.chunk_ptr, tr, te) if self.n_chunks else None
         else:
-            self.chunk_tiles = None
+            self.tiles = torch.from_numpy(greedy_tiles(self.rowptr.cpu().numpy(), tr, te)).to(dev)
+            self.chunk_tiles = torch.from_numpy(greedy_tiles(self.chunk_ptr.cpu().numpy(), tr, te)).to(dev) \
+                if self.n_chunks else None
         self._pack_local_rows()
         # per row tile: which of its rows are hubs (the streaming kernel must not write those: hub_finish_kernel does)
         if self.n_hub and self.tiles.shape[0]:
@@ -197,7 +230,11 @@ class LaplacianPlan:
     """Execution plan of one ``lap_list`` element; ``shard`` (a sharded.RowShards) restricts it to this rank's row
     block of L and of L^T (``rows x N_pad`` matrices whose column ids stay global)."""
 
-    def __init__(self, L: torch.Tensor, device, shard=None):
+    def __init__(self, L, device, shard=None):
+        from .plgraph import CsrLaplacian
+        if isinstance(L, CsrLaplacian):
+            self._init_from_csr(L, torch.device(device), shard)
+            return
         if not (L.is_sparse and L.dim() == 2 and L.shape[0] == L.shape[1]):
             raise ValueError("lap_list entries must be square torch.sparse_coo tensors (matrix.py:79-83)")
         device = torch.device(device)
@@ -254,6 +291,28 @@ class LaplacianPlan:
         self.symmetric = bool(self.fwd.nnz == self.bwd.nnz and torch.equal(self.fwd.rowptr, self.bwd.rowptr) and
                               torch.equal(self.fwd.ent, self.bwd.ent))
 
+    def _init_from_csr(self, L, device, shard):
+        """A device-built CSR row shard (plgraph.CsrLaplacian) of a SYMMETRIC Laplacian: the execution layout is derived
+        from it directly (no COO, no sort), and L^T's row shard is the same matrix."""
+        if device.type != "cuda":
+            raise RuntimeError("LaplacianPlan needs a CUDA device: the NGCF B200 path has no CPU fallback")
+        self.src, self.N, self.shard = L, int(L.shape[0]), shard
+        n_cols = shard.N_pad if shard is not None else self.N
+        if n_cols >= (1 << CsrSide.LR_SHIFT):
+            raise ValueError(f"graphs of up to {1 << CsrSide.LR_SHIFT} nodes are supported (27-bit column ids)")
+        if shard is not None and (L.row0 != shard.r0 or L.n_rows != shard.rows):
+            raise ValueError("the CSR shard does not cover this rank's row block")
+        if shard is None and L.n_rows != self.N:
+            raise ValueError("an unsharded plan needs all rows of the Laplacian")
+        self.nnz = L.nnz
+        self.coo_val = L.vals                                      # (device marker for NGCF._plan; not COO-ordered)
+        side = CsrSide(L.rowptr.to(device), L.colidx.to(device), None, L.n_rows, L.nnz, vals=L.vals.to(device))
+        side.ent = self.entries(side, None)
+        side.vals = None                                           # folded into ent
+        torch.cuda.current_stream().synchronize()
+        self.fwd = self.bwd = side
+        self.symmetric = True
+
     def side(self, transposed: bool, masked: bool) -> CsrSide:
         if transposed and not (self.symmetric and not masked):
             return self.bwd
@@ -263,6 +322,13 @@ class LaplacianPlan:
         """Entry pairs in execution order, optionally with an explicit COO-order node-dropout mask folded in
         (NGCF.py:93-100).  Two trailing pad pairs keep vector reads in bounds."""
         lib = _lib.load()
+        if side.perm is None:                                      # device-built CSR: values are already in entry order
+            if keep_mask is not None:
+                raise ValueError("explicit COO-order edge masks need a reference-format (COO) Laplacian")
+            out = torch.zeros(side.nnz + 2, 2, dtype=torch.int32, device=side.colidx.device)
+            out[:side.nnz, 0] = side.colidx
+            out[:side.nnz, 1] = side.vals.view(torch.int32)
+            return out
         out = torch.zeros(side.nnz + 2, 2, dtype=torch.int32, device=self.coo_val.device)
         _lib.check(lib.ngcf_edge_entries(side.colidx.data_ptr(), self.coo_val.data_ptr(), side.perm.data_ptr(),
                                          _lib.ptr(keep_mask), out.data_ptr(), side.nnz, _stream()), "edge_entries")

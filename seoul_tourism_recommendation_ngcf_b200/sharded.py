@@ -24,6 +24,7 @@ class RowShards:
         self.N_pad = self.rows * self.world
         self.r0 = self.rank * self.rows
         self.valid = max(0, min(self.N, self.r0 + self.rows) - self.r0)      # rows of this rank that exist in L
+        self.equal = True
 
     def bounds(self, rank: int):
         r0 = rank * self.rows
@@ -36,6 +37,54 @@ class RowShards:
     def node(self, positions: torch.Tensor) -> torch.Tensor:
         """Node id at each position, -1 for padding."""
         return torch.where(positions < self.N, positions, torch.full_like(positions, -1))
+
+
+class BalancedShards(RowShards):
+    """Contiguous row blocks of UNEQUAL length, cut so that every rank gets the same share of the work
+    ``entries + row_weight * rows`` (the SpMM cost follows the entries, the dense kernels the rows; item rows of a
+    bipartite interaction graph are several times heavier than user rows, so equal blocks leave the item ranks with
+    most of the entries).  No padding: N_pad = N.  Needs the peer-memory exchange (sharded.PeerExchange): NCCL's
+    all_gather_into_tensor wants equal blocks."""
+
+    def __init__(self, N: int, world: int, rank: int, starts):
+        if not (0 <= rank < world):
+            raise ValueError("rank out of range")
+        starts = [int(x) for x in starts]
+        if len(starts) != world + 1 or starts[0] != 0 or starts[-1] != N or any(b < a for a, b in zip(starts, starts[1:])):
+            raise ValueError("starts must be world + 1 non-decreasing row indices from 0 to N")
+        self.N, self.world, self.rank = int(N), int(world), int(rank)
+        self.starts = starts
+        self.r0 = starts[rank]
+        self.rows = starts[rank + 1] - starts[rank]
+        self.valid = self.rows
+        self.N_pad = self.N
+        self.equal = False
+
+    def bounds(self, rank: int):
+        return self.starts[rank], self.starts[rank + 1]
+
+    @staticmethod
+    def cut(row_work, world: int):
+        """Block boundaries from a per-row work array (numpy / torch, length N): prefix sums cut into equal shares."""
+        import numpy as np
+        w = np.asarray(row_work.cpu() if hasattr(row_work, "cpu") else row_work, dtype=np.float64)
+        c = np.concatenate([[0.0], np.cumsum(w)])
+        targets = c[-1] * np.arange(1, world) / world
+        inner = np.searchsorted(c, targets, side="left")
+        return [0] + [int(x) for x in np.clip(inner, 0, w.size)] + [int(w.size)]
+
+    @staticmethod
+    def cut_bipartite(n_user: int, n_item: int, n_edges: int, world: int, row_weight: float = 32.0):
+        """The same for a bipartite graph whose users (items) all have the class's mean degree - exact in expectation
+        for the synthetic power-law graphs, whose Zipf ranks are scattered uniformly over each id range."""
+        wu, wi = n_edges / n_user + row_weight, n_edges / n_item + row_weight
+        total = wu * n_user + wi * n_item
+        starts = [0]
+        for r in range(1, world):
+            t = total * r / world
+            row = t / wu if t <= wu * n_user else n_user + (t - wu * n_user) / wi
+            starts.append(int(round(row)))
+        return starts + [n_user + n_item]
 
 
 class DealtShards(RowShards):
@@ -148,8 +197,9 @@ class PeerExchange:
                                       int(row0), int(n_rows), int(mat.shape[1]), _lib.current_stream()), "push_rows")
 
 
-def parity_vs_unsharded(emb: int, layers: list, L: torch.Tensor, num_dict: dict, batch: dict, batch_size: int, device,
-                        node_p: float = 0.3, mess_p: float = 0.1, weight_decay: float = 0.025, group=None) -> dict:
+def parity_vs_unsharded(emb: int, layers: list, L, num_dict: dict, batch: dict, batch_size: int, device,
+                        node_p: float = 0.3, mess_p: float = 0.1, weight_decay: float = 0.025, group=None,
+                        L_shard=None, shards=None) -> dict:
     """Runs ONE training step (forward + BPR + backward, node and message dropout ON, device RNG) twice on this rank's
     GPU — unsharded, and row-sharded over the ranks of ``group`` — and returns the relative differences
     ``{out, loss, all_E, worst_grad}`` (max|a-b| / max|b|).  The dropout keys are global coordinates, so both runs draw
@@ -161,9 +211,10 @@ def parity_vs_unsharded(emb: int, layers: list, L: torch.Tensor, num_dict: dict,
     b = {k: (v if k == "year" else v.to(device)) for k, v in batch.items()}
     for sharded in (False, True):
         torch.manual_seed(0)
-        m = NGCF(emb, list(layers), node_p, [mess_p] * len(layers), 1.0, [L, L], num_dict, batch_size, device).to(device)
+        Lm = L_shard if (sharded and L_shard is not None) else L    # (a device-built CSR row shard, plgraph.py)
+        m = NGCF(emb, list(layers), node_p, [mess_p] * len(layers), 1.0, [Lm, Lm], num_dict, batch_size, device).to(device)
         if sharded:
-            m.shard(group)
+            m.shard(group, shards)
         m.train()
         torch.manual_seed(7)
         uu, pp, nn_ = m(b["year"], b["u_id"], b["age"], b["sex"], b["month"], b["day"], b["dow"], b["pos_item"],

@@ -14,7 +14,10 @@ SHAPES = {
     "gowalla": (29858, 40981, 1027370, 64, 3),
     "yelp2018": (31668, 38048, 1561406, 64, 3),
     "amazon-book": (52643, 91599, 2984108, 128, 4),
+    # generated on the device per row shard (plgraph.py); the smaller ones are the same family at 1/10 and 1/100 scale
     "pl-1b": (10_000_000, 5_000_000, 1_000_000_000, 64, 3),
+    "pl-100m": (1_000_000, 500_000, 100_000_000, 64, 3),
+    "pl-10m": (100_000, 50_000, 10_000_000, 64, 3),
 }
 
 # the reference dataset's feature cardinalities (saved_model_data/num_dict.pkl)

@@ -225,3 +225,85 @@ def test_row_sharded_step_on_two_ranks_equals_the_one_gpu_step():
         for r in range(world):
             res = ret[r]
             assert res["out"] <= 1e-6 and res["loss"] <= 1e-6 and res["all_E"] <= 1e-6 and res["worst_grad"] <= 1e-5, res
+
+
+def test_device_built_power_law_laplacian_matches_the_host_builder():
+    """SURVEY.md 8(f) #2 / BASELINE config 5: plgraph builds the CSR Laplacian of a synthetic power-law graph on the
+    device.  Its structure and values must equal laplacian.laplacian_coo (the bit-exact sparse restatement of the
+    reference's Matrix.create_matrix, matrix.py:41-83) fed with the same edges; the generator must be symmetric,
+    heavy-tailed and nearly duplicate-free; device-built SpMM tiles must equal the host's greedy tiles; and a plan built
+    from the CSR must multiply like torch's sparse mm."""
+    from seoul_tourism_recommendation_ngcf_b200 import plgraph
+    from seoul_tourism_recommendation_ngcf_b200.plan import LaplacianPlan, device_tiles, greedy_tiles, spmm
+    from seoul_tourism_recommendation_ngcf_b200 import _lib
+    n_user, n_item, n_edges = 3000, 1700, 90000
+    N = n_user + n_item
+    csr = plgraph.powerlaw_laplacian(n_user, n_item, n_edges, torch.device(DEV), alpha=0.8, seed=3)
+    rp, col, val = csr.rowptr.cpu().numpy().astype(np.int64), csr.colidx.cpu().numpy().astype(np.int64), csr.vals.cpu().numpy()
+    row = np.repeat(np.arange(N), np.diff(rp))
+    assert rp[-1] == col.size and 1.5 * n_edges < col.size <= 2 * n_edges            # both directions; repeated pairs collapse
+    up = row < n_user
+    assert (col[up] >= n_user).all() and (col[~up] < n_user).all()                    # bipartite
+    a = set(zip(row[up].tolist(), col[up].tolist()))
+    assert a == set(zip(col[~up].tolist(), row[~up].tolist()))                        # symmetric
+    deg = np.diff(rp)
+    assert deg.max() > 8 * deg.mean()                                                 # heavy tail
+    L = laplacian.laplacian_coo(row[up], col[up] - n_user, np.ones(up.sum(), np.float32), n_user, n_item).coalesce()
+    idx, v = L.indices().numpy(), L.values().numpy()
+    assert np.array_equal(idx[0], row) and np.array_equal(idx[1], col)
+    assert np.abs(val - v).max() <= 5e-7 * np.abs(v).max()      # numpy's float32 pow is not correctly rounded
+    # tiles
+    lib = _lib.load()
+    tr, te = lib.ngcf_spmm_tile_rows(), lib.ngcf_spmm_tile_entries()
+    t_dev = device_tiles(csr.rowptr, tr, te).cpu().numpy()
+    assert np.array_equal(t_dev, greedy_tiles(rp, tr, te))
+    # a plan straight from the CSR
+    plan = LaplacianPlan(csr, torch.device(DEV))
+    X = torch.randn(N, 64, device=DEV)
+    want = torch.sparse.mm(L.to(DEV), X)
+    got = spmm(plan.fwd, None, X, 64)
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) <= 2e-6
+    assert plan.fwd.n_hub > 0
+
+
+def _rank_pl(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from seoul_tourism_recommendation_ngcf_b200 import plgraph
+        from seoul_tourism_recommendation_ngcf_b200.sharded import RowShards, parity_vs_unsharded
+        n_user, n_item, n_edges, B = 30001, 20000, 1500000, 512
+        dev = torch.device("cuda", rank)
+        sh = RowShards(n_user + n_item, world, rank)
+        full = plgraph.powerlaw_laplacian(n_user, n_item, n_edges, dev, seed=1)
+        part = plgraph.powerlaw_laplacian(n_user, n_item, n_edges, dev, seed=1, shard=sh)
+        # the shard IS the row block of the unsharded CSR
+        r0, r1 = sh.r0, min(sh.r0 + sh.rows, n_user + n_item)
+        e0, e1 = int(full.rowptr[r0]), int(full.rowptr[r1])
+        same = bool(torch.equal(part.colidx, full.colidx[e0:e1]) and torch.equal(part.vals, full.vals[e0:e1]) and
+                    torch.equal(part.rowptr[:r1 - r0 + 1].long(), full.rowptr[r0:r1 + 1].long() - e0))
+        b = {k: torch.from_numpy(v) for k, v in synth.random_batch(n_user, n_item, B, seed=1).items()}
+        res = parity_vs_unsharded(64, [64, 64, 64], full, synth.num_dict_for(n_user, n_item), b, B, dev, L_shard=part)
+        res["shard_is_row_block"] = same
+        ret[rank] = res
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_device_built_row_shards_train_like_the_unsharded_graph():
+    """BASELINE config 5 at test scale: every rank generates ONLY its own rows on the device; the shard must be the row
+    block of the unsharded CSR bit for bit, and the sharded training step must equal the 1-GPU step."""
+    import torch.multiprocessing as mp
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_rank_pl, args=(world, 29573, ret), nprocs=world, join=True)
+        for r in range(world):
+            res = ret[r]
+            assert res["shard_is_row_block"], res
+            assert res["out"] <= 1e-6 and res["loss"] <= 1e-6 and res["all_E"] <= 1e-6 and res["worst_grad"] <= 1e-5, res

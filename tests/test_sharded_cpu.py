@@ -134,3 +134,25 @@ def test_dealt_shards_cover_nodes_and_balance_entries():
     rank_of = np.empty(N, dtype=np.int64); rank_of[order] = np.arange(N)
     rows = torch.from_numpy(rank_of[rows.numpy()])
     assert imbalance(RowShards) > 3.0 and imbalance(DealtShards) < 1.06
+
+
+def test_balanced_shards_cut_by_work():
+    """BalancedShards: contiguous blocks of unequal length with equal work; bounds cover [0, N) exactly."""
+    import numpy as np
+    from seoul_tourism_recommendation_ngcf_b200.sharded import BalancedShards
+    rng = np.random.default_rng(0)
+    work = np.concatenate([rng.integers(1, 40, 3000), rng.integers(100, 400, 1000)]).astype(np.float64)   # light users, heavy items
+    for world in (2, 3, 8):
+        starts = BalancedShards.cut(work, world)
+        assert starts[0] == 0 and starts[-1] == work.size and all(b >= a for a, b in zip(starts, starts[1:]))
+        shares = [work[a:b].sum() for a, b in zip(starts, starts[1:])]
+        assert max(shares) / (work.sum() / world) < 1.02
+        sh = [BalancedShards(work.size, world, r, starts) for r in range(world)]
+        assert sum(s.rows for s in sh) == work.size and all(s.N_pad == work.size and s.valid == s.rows for s in sh)
+        assert [s.bounds(s.rank) for s in sh] == list(zip(starts, starts[1:]))
+    # the analytic cut for a bipartite graph with class-uniform degrees
+    st = BalancedShards.cut_bipartite(10_000_000, 5_000_000, 1_000_000_000, 8, row_weight=0.0)
+    assert st[4] == 10_000_000 and st[1] == 2_500_000 and st[5] == 11_250_000
+    import pytest
+    with pytest.raises(ValueError):
+        BalancedShards(10, 2, 0, [0, 6, 9])
