@@ -605,6 +605,8 @@ def run_pl(args):
     # survivor lists cost 8 B x nnz per layer and direction: past ~40 GB the step uses per-step decision bytes instead
     if csr.nnz * 8 * 2 * K > 40e9:
         model._node_mode = "bits"
+    if os.environ.get("NGCF_B200_NODE_MODE"):
+        model._node_mode = os.environ["NGCF_B200_NODE_MODE"]       # (A/B runs: the 1-GPU run only fits with "bits")
     crit = pkg.BPR(WEIGHT_DECAY, BATCH)
     batches = [synth.random_batch(n_user, n_item, BATCH, seed=1 + j) for j in range(4)]
     hb = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]

@@ -183,10 +183,18 @@ int ngcf_build_tiles(const int32_t* rowptr, int64_t n_rows, int max_rows, int ma
  *   matrix_on_rank_host[r] : base address of rank r's copy as mapped into THIS process (r == rank: the local one)
  *   flags_on_rank_host[r]  : rank r's flag block, ngcf_exchange_flag_words() uint32, zero before the first exchange
  *   local_state            : uint32[2] in local device memory, zero before the first exchange
- * Every rank must issue the same sequence of exchanges on the same flag blocks. */
+ * Every rank must issue the same sequence of exchanges on the same flag blocks.
+ *   multicast_or_null      : the NVLS multicast mapping of the matrix (one multimem.st reaches every rank's copy through
+ *                            the NVSwitch), when the platform offers one; NULL: one store per peer
+ * ngcf_push_selected_rows does the same for the rows list[q][j] + list_offsets[q] only (those this rank owns): the
+ * last layer's output is needed on other ranks for the <= 3 B batch rows alone (NGCF.py:151-155). */
 int ngcf_exchange_flag_words(void);
 int ngcf_push_rows(float* const* matrix_on_rank_host, uint32_t* const* flags_on_rank_host, uint32_t* local_state,
-                   int world, int rank, int64_t row0, int64_t n_rows, int d, void* stream);
+                   int world, int rank, int64_t row0, int64_t n_rows, int d, float* multicast_or_null, void* stream);
+int ngcf_push_selected_rows(float* const* matrix_on_rank_host, uint32_t* const* flags_on_rank_host, uint32_t* local_state,
+                            int world, int rank, int64_t row0, int64_t n_rows, int d,
+                            const int64_t* const* lists_host, const int64_t* list_offsets_host,
+                            const int64_t* list_sizes_host, int n_lists, float* multicast_or_null, void* stream);
 
 /* ---- per-layer epilogue: NGCF.py:131-142 ------------------------------------------------------------
  * pack:  wcat[k, o] = W1[o,k] (k < d_in), W2[o,k-d_in] (k >= d_in);  bias_eff = 2*b1 + b2

@@ -30,7 +30,7 @@ def _stream() -> int:
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
     __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
-                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode")
+                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode", "last_partial")
 
 
 class _Propagate(torch.autograd.Function):
@@ -57,6 +57,7 @@ class _Propagate(torch.autograd.Function):
         side = st.plan.fwd
         st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
         st.node_mode = mod._node_mode
+        st.last_partial = None
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
             # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
@@ -114,7 +115,12 @@ class _Propagate(torch.autograd.Function):
                                           _lib.ptr(st.mess_bits[k]), float(st.mess_p[k]), st.seed, _lib.ptr(st.seed_dev), k, r0, En.data_ptr(),
                                           _stream()),
                        "dense_fwd")                                                          # NGCF.py:131-142
-            if xkey is not None:
+            if xkey is not None and k == K - 1 and mod._sparse_last:
+                # nothing downstream gathers from the LAST layer's output: other ranks need it for the <= 3 B batch rows only
+                # (NGCF.py:151-155); all_users_emb / all_items_emb complete it on first read (_materialize)
+                mod._xchg.push_selected(xkey, r0, nloc, st.rows[:n_sets], st.offsets[:n_sets])
+                st.last_partial = xkey
+            elif xkey is not None:
                 mod._xchg.push(xkey, r0, nloc)                         # every rank needs all of E_{k+1}
             elif sh is not None:
                 all_gather_rows(Xn, En, mod._group)
@@ -295,6 +301,7 @@ class NGCF(nn.Module):
         self._shard = None       # sharded.RowShards once shard() was called
         self._group = None
         self._xchg = None        # sharded.PeerExchange (peer-memory exchange) when available
+        self._sparse_last = os.environ.get("NGCF_B200_SPARSE_LAST", "1") == "1"
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
@@ -362,9 +369,10 @@ class NGCF(nn.Module):
         if self._shard is None:
             return "single GPU"
         if self._xchg is not None:
-            return ("equal row blocks; per-layer exchange of E / gS / table-gradient rows by peer-memory stores over NVLink "
-                    "(ngcf_push_rows on symmetric memory, no NCCL collective on the data path), NCCL all-reduce of the "
-                    "W/b gradients")
+            how = "NVLS multicast stores (multimem.st)" if self._xchg.multicast() else "peer-memory stores"
+            return (f"contiguous row blocks; per-layer exchange of E / gS / table-gradient rows by {how} over NVLink "
+                    "(ngcf_push_rows on symmetric memory, no NCCL collective on the data path; the last layer's output "
+                    "travels for the batch rows only), NCCL all-reduce of the W/b gradients")
         return "equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads"
 
     # ---- internal buffers ---------------------------------------------------------------------------
@@ -519,6 +527,10 @@ class NGCF(nn.Module):
             raise AttributeError("all_users_emb / all_items_emb exist after the first forward (NGCF.py:148-149)")
         if self._all_E is None:
             self._check_fresh(self._last, "all_users_emb / all_items_emb")
+            if self._last.last_partial is not None:                   # row-sharded: the last layer travelled for the batch
+                sh = self._shard                                       # rows only; complete it now (COLLECTIVE: every rank
+                self._xchg.push(self._last.last_partial, sh.r0, sh.rows)    # must read the attribute)
+                self._last.last_partial = None
             st, lib = self._last, _lib.load()
             N, D = self.n_user + self.n_item, sum(st.dims)
             out = torch.empty(N, D, dtype=torch.float32, device=st.E[0].device)

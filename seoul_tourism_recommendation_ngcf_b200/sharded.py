@@ -9,6 +9,8 @@ tables stay replicated so ``state_dict`` is unchanged).  The helpers in this fil
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -168,8 +170,12 @@ class PeerExchange:
         self._flag_ptrs = _lib.ptr_array_int([int(p) for p in self._flag_hdl.buffer_ptrs])
         self.local_state = torch.zeros(2, dtype=torch.int32, device=self.device)
         self._mats = {}
+        self.use_multicast = os.environ.get("NGCF_B200_MULTICAST", "0") == "1"    # NVLS multimem.st: measured slower (the switch also returns the sender its own rows)
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                    # every rank's flag block is zero before anyone signals
+
+    def multicast(self) -> bool:
+        return any(m[3] for m in self._mats.values())
 
     def matrix(self, key, n_rows: int, d: int) -> torch.Tensor:
         """The persistent symmetric [n_rows, d] fp32 matrix of ``key`` (allocated collectively on first use)."""
@@ -180,9 +186,15 @@ class PeerExchange:
             hdl = self._symm.rendezvous(t, self.group)
             from . import _lib
             ptrs = _lib.ptr_array_int([int(p) for p in hdl.buffer_ptrs])
+            mc = 0
+            if self.use_multicast:
+                try:
+                    mc = int(hdl.multicast_ptr) if hdl.has_multicast_support(self.device.type, self.device.index) else 0
+                except Exception:
+                    mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
             torch.cuda.synchronize(self.device)
             dist.barrier(self.group)                # zero-filled everywhere before the first stores arrive
-            ent = self._mats[key] = (t.view(n_rows, d), hdl, ptrs)
+            ent = self._mats[key] = (t.view(n_rows, d), hdl, ptrs, mc)
         if ent[0].shape != (n_rows, d):
             raise RuntimeError(f"exchange matrix {key!r} was created as {tuple(ent[0].shape)}, asked for {(n_rows, d)}")
         return ent[0]
@@ -191,10 +203,21 @@ class PeerExchange:
         """This rank's rows [row0, row0 + n_rows) of matrix ``key`` -> every peer; returns (in stream order) with every
         peer's rows present in the local copy."""
         from . import _lib
-        mat, _, ptrs = self._mats[key]
+        mat, _, ptrs, mc = self._mats[key]
         lib = _lib.load()
         _lib.check(lib.ngcf_push_rows(ptrs, self._flag_ptrs, self.local_state.data_ptr(), self.world, self.rank,
-                                      int(row0), int(n_rows), int(mat.shape[1]), _lib.current_stream()), "push_rows")
+                                      int(row0), int(n_rows), int(mat.shape[1]), mc or None, _lib.current_stream()),
+                   "push_rows")
+
+    def push_selected(self, key, row0: int, n_rows: int, row_lists, offsets):
+        """Only the rows ``row_lists[q] + offsets[q]`` (int64 CUDA tensors of node ids) that this rank owns -> every peer."""
+        from . import _lib
+        mat, _, ptrs, mc = self._mats[key]
+        lib = _lib.load()
+        _lib.check(lib.ngcf_push_selected_rows(ptrs, self._flag_ptrs, self.local_state.data_ptr(), self.world, self.rank,
+                                               int(row0), int(n_rows), int(mat.shape[1]), _lib.ptr_array(row_lists),
+                                               _lib.i64_array(offsets), _lib.i64_array([t.numel() for t in row_lists]),
+                                               len(row_lists), mc or None, _lib.current_stream()), "push_selected_rows")
 
 
 def parity_vs_unsharded(emb: int, layers: list, L, num_dict: dict, batch: dict, batch_size: int, device,
