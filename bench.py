@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-epoch", action="store_true", help="skip the measured whole-epoch leg")
     ap.add_argument("--eager", action="store_true", help="time the eager drop-in path only (no CUDA graph)")
     ap.add_argument("--breakdown", action="store_true", help="print a per-entry-point time table to stderr")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other named shapes at the same N)")
     return ap.parse_args()
 
 
@@ -187,6 +188,52 @@ class CallTimer:
             t, c = agg.get(name, (0.0, 0))
             agg[name] = (t + e0.elapsed_time(e1), c + 1)
         return agg
+
+
+def time_shape(pkg, shape, dev, world, rank, steps=10, warmup=3):
+    """ms per step (CUDA graph replay, device-resident batches, max over ranks) of another named shape at this N: the
+    extra legs of the bench line (BASELINE.json configs 3 and 4)."""
+    import torch.distributed as dist
+    L, batches, info = make_workload(shape, n_batches=4)
+    model = make_model(info, L, dev).to(dev)
+    if world > 1:
+        shards = None
+        if os.environ.get("NGCF_B200_EXCHANGE", "peer") != "nccl" and os.environ.get("NGCF_B200_SHARDS", "balanced") == "balanced":
+            from seoul_tourism_recommendation_ngcf_b200.sharded import BalancedShards
+            row_nnz = np.bincount(L._indices()[0].numpy(), minlength=int(L.shape[0]))
+            shards = BalancedShards(int(L.shape[0]), world, rank, BalancedShards.cut(row_nnz + 32.0, world))
+        try:
+            model.shard(shards=shards)
+        except RuntimeError:
+            model.shard()
+    model.train()
+    crit = pkg.BPR(WEIGHT_DECAY, BATCH)
+    db = [{k: (torch.from_numpy(v) if k == "year" else torch.from_numpy(v).to(dev)) for k, v in b.items()} for b in batches]
+    gstep = pkg.GraphedStep(model, crit, BATCH, node_flag=True)
+    for j in range(warmup):
+        gstep(db[j % len(db)])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for j in range(steps):
+        ev[j][0].record()
+        gstep(db[j % len(db)])
+        ev[j][1].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    out = {"ms_per_step": round(ms, 4), "value": round(ms * info["steps_per_epoch"] / 1e3, 4), "unit": "s/epoch",
+           "workload": info["workload"], "steps": steps, "gpu_launches_per_step": gstep.launches_per_step,
+           "l2": "not flushed (back-to-back replays)"}
+    del gstep, model, L
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -439,8 +486,8 @@ def run_ours(args):
     if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get(args.shape), tj.get("source")
-    roofline = {"kernel": "spmm_tile_kernel<16> (hub-chunk tiles + row tiles in one launch) = one ngcf_spmm call: "
-                          "layer 0 of the step, node-dropout survivors (p = 0.3) compacted"
+    roofline = {"kernel": "spmm_stream_kernel<16> (hub-chunk tiles + row tiles in one launch) + hub_finish_kernel = one "
+                          "ngcf_spmm call: layer 0 of the step, node-dropout survivors (p = 0.3) compacted"
                           + (f", row shard of rank 0 of {world}" if world > 1 else ""),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
@@ -448,8 +495,11 @@ def run_ours(args):
                 "entries_gathered": nnz_kept, "kernel_ms": round(k_ms, 5), "peak_source": peak_src,
                 "timing": "CUDA events around the call, cold L2 (flushed), mean of 20",
                 "l2_gather_tb_s": round(nnz_kept * 4 * d / (k_ms * 1e-3) / 1e12, 2),
+                "l2_gather_ceiling_tb_s": 19.6,
                 "note": "every entry gathers one 4*d-byte embedding row through L2 (l2_gather_tb_s): that traffic, "
-                        "not HBM, bounds the kernel; see DESIGN.md section 4",
+                        "not HBM, bounds the kernel.  l2_gather_ceiling_tb_s = what a kernel that ONLY gathers this "
+                        "product's column stream reaches on a B200 (tools/l2_gather_bench.cu, profiles/r02_l2_gather_bench.txt); "
+                        "see DESIGN.md section 4",
                 "no_dropout": {"kernel_ms": round(k_ms_full, 5), "algorithmic_bytes": alg_bytes_full,
                                "achieved": round(alg_bytes_full / (k_ms_full * 1e-3) / 1e9, 1),
                                "frac": round(alg_bytes_full / (k_ms_full * 1e-3) / 1e9 / peak, 4),
@@ -469,6 +519,22 @@ def run_ours(args):
         breakdown = {k: {"ms_per_step": round(t / 10, 4), "calls_per_step": c / 10} for k, (t, c) in sorted(agg.items())}
         for k, v in breakdown.items():
             log(f"[breakdown] {k:28s} {v['ms_per_step']:8.4f} ms/step  x{v['calls_per_step']:.0f}")
+
+    # ---- extra legs: the other named single-node shapes at this N (BASELINE.json configs 3 / 4) -------------------------
+    extra = None
+    if not args.no_extra and args.shape == "gowalla":
+        extra = {}
+        try:
+            del gstep_opt
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        for shp in ("amazon-book", "yelp2018"):
+            try:
+                extra[shp] = time_shape(pkg, shp, dev, world, rank)
+                log(f"[bench] extra {shp}: {extra[shp]['ms_per_step']} ms/step")
+            except Exception as e:
+                extra[shp] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline beside it ------------------------------------------------------------------------------
     cpu, torch_cuda = None, None
@@ -512,6 +578,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": torch_cuda, "clocks": clocks,
         "training_iteration_with_adam": with_adam,
         "measured_epoch": measured_epoch,
+        "extra": extra,
     }
     if breakdown:
         out["breakdown"] = breakdown

@@ -92,15 +92,15 @@ __global__ void __launch_bounds__(EX_THREADS) push_rows_kernel(PushArgs a) {
         const int64_t per = (n4 + n_chunks - 1) / n_chunks;
         const int64_t i0 = (int64_t)chunk * per, i1 = min(i0 + per, n4);
         int64_t i = i0 + tid;
-        for (; i + 3 * EX_THREADS < i1; i += 4 * EX_THREADS) {           // four 16-byte loads in flight per thread
-            const float4 v0 = src[i], v1 = src[i + EX_THREADS], v2 = src[i + 2 * EX_THREADS], v3 = src[i + 3 * EX_THREADS];
-            if (MC) {
-                multimem_st_f4(reinterpret_cast<float*>(dst + i), v0);
-                multimem_st_f4(reinterpret_cast<float*>(dst + i + EX_THREADS), v1);
-                multimem_st_f4(reinterpret_cast<float*>(dst + i + 2 * EX_THREADS), v2);
-                multimem_st_f4(reinterpret_cast<float*>(dst + i + 3 * EX_THREADS), v3);
-            } else {
-                dst[i] = v0; dst[i + EX_THREADS] = v1; dst[i + 2 * EX_THREADS] = v2; dst[i + 3 * EX_THREADS] = v3;
+        constexpr int U = 8;                                             // 16-byte loads in flight per thread
+        for (; i + (U - 1) * EX_THREADS < i1; i += U * EX_THREADS) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = src[i + u * EX_THREADS];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (MC) multimem_st_f4(reinterpret_cast<float*>(dst + i + u * EX_THREADS), v[u]);
+                else dst[i + u * EX_THREADS] = v[u];
             }
         }
         for (; i < i1; i += EX_THREADS) {
@@ -180,11 +180,11 @@ extern "C" int ngcf_push_rows(float* const* matrix_on_rank_host, uint32_t* const
     const int64_t bytes = a.n_elem * 4;
     if (a.mc) {
         // one store per element reaches every peer: as many CTAs as keep the link busy, at most one per SM
-        const int grid = (int)min((int64_t)ngcf_num_sms(), max((int64_t)1, bytes / (64 * 1024)));
+        const int grid = (int)min((int64_t)2 * ngcf_num_sms(), max((int64_t)1, bytes / (64 * 1024)));
         a.ctas_per_peer = grid;
         NGCF_CUDA(ngcf_launch_pdl(push_rows_kernel<true, false>, dim3((unsigned)grid), dim3(EX_THREADS), 0, as_stream(stream), a));
     } else {
-        int per_peer = (int)min((int64_t)ngcf_num_sms() / (world - 1), max((int64_t)1, bytes / (64 * 1024)));
+        int per_peer = (int)min((int64_t)2 * ngcf_num_sms() / (world - 1), max((int64_t)1, bytes / (64 * 1024)));
         if (per_peer < 1) per_peer = 1;
         a.ctas_per_peer = per_peer;
         NGCF_CUDA(ngcf_launch_pdl(push_rows_kernel<false, false>, dim3((unsigned)(per_peer * (world - 1))), dim3(EX_THREADS), 0,

@@ -377,28 +377,56 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel
     if (a.dbg) stamp_done(a.dbg);
 }
 
-// One warp per hub row: the chunk partials (written by spmm_stream_kernel right before) summed in chunk order.
+// One CTA per hub row: the chunk partials (written by spmm_stream_kernel right before) summed in a fixed order - lane
+// group g adds chunks g, g + NGRP, ... (4 loads in flight), group 0 then adds the group sums in group order.  (First
+// version: one warp per hub; the widest hub of the Gowalla-shaped graph has 107 chunks = 14 dependent round trips for
+// one warp, an 11-us launch for 2 MB of data.)
+constexpr int HF_THREADS = 128;
 template <int G>
-__global__ void __launch_bounds__(128) hub_finish_kernel(SpmmArgs a) {
+__global__ void __launch_bounds__(HF_THREADS) hub_finish_kernel(SpmmArgs a) {
+    constexpr int NGRP = HF_THREADS / G;
+    __shared__ __align__(16) float gs[HF_THREADS * 4];                   // [NGRP][G * 4]
     pdl_launch_dependents();
-    const int lane = threadIdx.x & 31;
-    const int h = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    pdl_wait();
-    if (h >= a.n_hub) return;
-    const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];
+    const int tid = threadIdx.x, g = tid / G, l = tid % G;
+    const int h = blockIdx.x;
+    const int c0 = a.hub_chunk_ptr[h], c1 = a.hub_chunk_ptr[h + 1];      // static plan data
     const int64_t row = a.hub_rows[h];
-    float4 sum = sum_partials_split<G>(a.chunks.Y, c0, c1, a.d, lane);
-    if (lane < G && lane * 4 < a.d) {
-        const int c = lane * 4;
-        float* dst = a.Yrows + row * a.ld_yrows + c;
-        if (a.add_mode) {                                             // Y holds the addend; this warp owns the row
+    pdl_wait();
+    const bool ok = l * 4 < a.d;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+        const float* p = a.chunks.Y + l * 4;
+        int c = c0 + g;
+        for (; c + 3 * NGRP < c1; c += 4 * NGRP) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(c + u * NGRP) * a.d));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+        }
+        for (; c < c1; c += NGRP) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)c * a.d));
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+    }
+    st_f4(gs + g * (G * 4) + l * 4, acc);
+    __syncthreads();
+    if (g == 0 && ok) {
+        float4 sum = acc;
+#pragma unroll
+        for (int q = 1; q < NGRP; ++q) {
+            const float4 v = ld_f4(gs + q * (G * 4) + l * 4);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        float* dst = a.Yrows + row * a.ld_yrows + l * 4;
+        if (a.add_mode) {                                             // Y holds the addend; this CTA owns the row
             const float4 ad = ld_f4(dst);
             sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
         }
         const int s = a.slot ? a.slot[row] : -1;
         if (s >= 0) {
-            const float4 gs = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + c);
-            sum.x += gs.x; sum.y += gs.y; sum.z += gs.z; sum.w += gs.w;
+            const float4 gsv = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + l * 4);
+            sum.x += gsv.x; sum.y += gsv.y; sum.z += gsv.z; sum.w += gsv.w;
         }
         st_f4(dst, sum);
     }
@@ -588,7 +616,7 @@ int launch(const SpmmArgs& a, int n_ctas, bool stream, cudaStream_t st) {
             NGCF_CUDA(ngcf_launch_pdl(spmm_stream_kernel<G>, dim3((unsigned)n_ctas), dim3(SP_THREADS), 0, st, a));
             NGCF_LAUNCH_OK("spmm_stream_kernel");
             if (a.n_hub > 0) {
-                NGCF_CUDA(ngcf_launch_pdl(hub_finish_kernel<G>, dim3((unsigned)ceil_div64(a.n_hub, 4)), dim3(128), 0, st, a));
+                NGCF_CUDA(ngcf_launch_pdl(hub_finish_kernel<G>, dim3((unsigned)a.n_hub), dim3(HF_THREADS), 0, st, a));
                 NGCF_LAUNCH_OK("hub_finish_kernel");
             }
             return NGCF_OK;

@@ -170,7 +170,11 @@ class PeerExchange:
         self._flag_ptrs = _lib.ptr_array_int([int(p) for p in self._flag_hdl.buffer_ptrs])
         self.local_state = torch.zeros(2, dtype=torch.int32, device=self.device)
         self._mats = {}
-        self.use_multicast = os.environ.get("NGCF_B200_MULTICAST", "0") == "1"    # NVLS multimem.st: measured slower (the switch also returns the sender its own rows)
+        # NVLS multicast (one multimem.st per element, replicated by the switch): the sender's egress shrinks (W-1)-fold but
+        # the switch also returns the sender its own rows - measured slower at 2 ranks (426 vs 231 us for 128 MB), faster
+        # inside the 8-rank step (75 vs 85 ms at pl-1b).  NGCF_B200_MULTICAST=0/1 overrides.
+        mc_env = os.environ.get("NGCF_B200_MULTICAST", "auto")
+        self.use_multicast = mc_env == "1" or (mc_env == "auto" and self.world >= 4)
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                    # every rank's flag block is zero before anyone signals
 
