@@ -163,7 +163,17 @@ class _Propagate(torch.autograd.Function):
                                               K + 1, slot.data_ptr(), gsum.data_ptr(), D, _stream()), "rowgrad_normalize")
         slot_loc = slot[r0:r0 + nloc]
         sizes = [dims[k + 1] * dims[k] for k in range(K)]
-        flat = torch.zeros(2 * sum(sizes) + 2 * sum(dims[1:]), dtype=torch.float32, device=dev)
+        n_flat = 2 * sum(sizes) + 2 * sum(dims[1:])
+        if sh is not None and mod._xchg is not None:
+            # W/b gradients of all ranks side by side in one symmetric [world, F] matrix: this rank accumulates into its own
+            # row, pushes it, and every rank adds the rows up in rank order (same bits everywhere, no NCCL launch)
+            f_pad = (n_flat + 3) // 4 * 4
+            wg_all = mod._xchg.matrix(("wgrad", f_pad), sh.world, f_pad)
+            flat = wg_all[sh.rank, :n_flat]
+            flat.zero_()
+        else:
+            wg_all = None
+            flat = torch.zeros(n_flat, dtype=torch.float32, device=dev)
         gW1, gW2, gb1, gb2, o = [], [], [], [], 0
         for k in range(K):
             gW1.append(flat[o:o + sizes[k]].view(dims[k + 1], dims[k])); o += sizes[k]
@@ -229,7 +239,17 @@ class _Propagate(torch.autograd.Function):
             else:
                 gE0 = torch.empty(N_all, dims[0], dtype=torch.float32, device=dev)
                 all_gather_rows(gE0, gE_next, mod._group)
-            dist.all_reduce(flat, group=mod._group)                   # W/b gradients: sum of the row blocks
+            if wg_all is not None:                                    # W/b gradients: sum of the row blocks
+                mod._xchg.push(("wgrad", wg_all.shape[1]), sh.rank, 1)
+                total = wg_all.sum(0)[:n_flat]
+                gW1, gW2, gb1, gb2, o = [], [], [], [], 0
+                for k in range(K):
+                    gW1.append(total[o:o + sizes[k]].view(dims[k + 1], dims[k])); o += sizes[k]
+                    gW2.append(total[o:o + sizes[k]].view(dims[k + 1], dims[k])); o += sizes[k]
+                    gb1.append(total[o:o + dims[k + 1]]); o += dims[k + 1]
+                    gb2.append(total[o:o + dims[k + 1]]); o += dims[k + 1]
+            else:
+                dist.all_reduce(flat, group=mod._group)
         else:
             gE0 = gE_next
         gU, gI = gE0[:mod.n_user], gE0[mod.n_user:N]
@@ -371,8 +391,8 @@ class NGCF(nn.Module):
         if self._xchg is not None:
             how = "NVLS multicast stores (multimem.st)" if self._xchg.multicast() else "peer-memory stores"
             return (f"contiguous row blocks; per-layer exchange of E / gS / table-gradient rows by {how} over NVLink "
-                    "(ngcf_push_rows on symmetric memory, no NCCL collective on the data path; the last layer's output "
-                    "travels for the batch rows only), NCCL all-reduce of the W/b gradients")
+                    "(ngcf_push_rows on symmetric memory, no NCCL collective anywhere in the step; the last layer's "
+                    "output travels for the batch rows only; W/b gradients: one more push + a rank-ordered sum)")
         return "equal row blocks, per-layer NCCL all-gather of E / gS, all-reduce of W/b grads"
 
     # ---- internal buffers ---------------------------------------------------------------------------
