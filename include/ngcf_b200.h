@@ -84,7 +84,6 @@ typedef struct ngcf_csr {
     int32_t n_tiles, n_hub, n_chunks, n_chunk_tiles;
     int32_t rowptr_nnz;             /* entries in `ent` (= rowptr[n_rows]); per-entry side arrays continue with hub_ent */
     const uint32_t* tile_hubmask;   /* [n_tiles] bit i = row r0 + i of the tile is a hub row; may be NULL when n_hub == 0 */
-    int32_t* work_ctr;              /* [2] work counters of the warp-streaming ngcf_spmm kernel: zero between calls */
 } ngcf_csr;
 
 int ngcf_spmm_split_threshold(void);
@@ -113,8 +112,8 @@ int ngcf_feature_mix(float* user_w, int64_t n_user, int d,
 /* ---- SpMM: torch.mm(L, E), NGCF.py:130, and its backward L^T·gS (autograd MmBackward0) ----------
  * Y[i,:] = sum_t val[t] * X[col[t],:]  (+ addend[i,:])  (+ rowgrad rows, see below), d <= 128.
  * Hub rows are pre-reduced chunk-wise into hub_partial (scratch [n_chunks, d]) and summed in chunk order, so the
- * result is deterministic (no float atomics on shared sums).  Widths that are multiples of 4 run the persistent
- * warp-streaming kernel: it ADDS its row sums to Y after Y := addend (pass addend == Y to accumulate in place and
+ * result is deterministic (no float atomics on shared sums).  Widths that are multiples of 4 run the
+ * streaming kernel: it ADDS its row sums to Y after Y := addend (pass addend == Y to accumulate in place and
  * save the copy); other widths run the row-per-warp kernel.  The column word of an entry carries, above its 27-bit
  * column id, the index of the entry's row inside its tile (see plan.py).
  *   slot/gsum : optional sparse row addend — if slot[i] >= 0, Y[i,:] += gsum[slot[i]*ld_gsum + 0..d)
@@ -268,6 +267,10 @@ int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_h
  *   gM_scratch: optional [n_rows, d_out] scratch; when given the tcgen05 path runs for d_in = 64 with d_out in
  *   {32, 64}, and for widths 64 / 128 on either side as 64-wide blocks (a 128-wide d_out needs gh_normalized): both
  *   GEMMs as 3xTF32 tensor-core products, the weight gradients accumulated in TMEM. */
+/* Optional: the tensor-core weight-gradient launches of the following ngcf_dense_bwd calls (this thread) go to this
+ * stream, ordered after the backward kernel by an event; the caller joins it before reading gW / gb and must not reuse
+ * gM_scratch before then.  NULL restores single-stream operation. */
+int ngcf_set_wgrad_stream(void* stream_or_null);
 int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,

@@ -189,7 +189,16 @@ class _Propagate(torch.autograd.Function):
             _, st.bits_b = node_dropout_bits(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         gE_next = None
         col_off = D
-        gM_scratch = torch.empty(nloc, max(dims[1:]), dtype=torch.float32, device=dev)
+        # the weight-gradient kernels need gM only: with the gS exchange queued behind the backward kernel (row-sharded
+        # runs) they run beside it on a second stream; each layer then keeps its own gM until the join below
+        overlap = mod._wgrad_overlap == "1" or (mod._wgrad_overlap == "auto" and sh is not None and mod._xchg is not None)
+        if overlap:
+            if mod._side_stream is None:
+                mod._side_stream = torch.cuda.Stream(device=dev)
+            _lib.check(lib.ngcf_set_wgrad_stream(mod._side_stream.cuda_stream), "set_wgrad_stream")
+            gM_keep = []
+        else:
+            gM_scratch = torch.empty(nloc, max(dims[1:]), dtype=torch.float32, device=dev)
         for k in range(K - 1, -1, -1):
             d_in, d_out = dims[k], dims[k + 1]
             col_off -= d_out
@@ -205,6 +214,9 @@ class _Propagate(torch.autograd.Function):
             else:
                 gEl = torch.empty(nloc, d_in, dtype=torch.float32, device=dev)
             mm = st.mess_mult[k] if st.mess_mult is not None else None
+            if overlap:
+                gM_scratch = torch.empty(nloc, dims[k + 1], dtype=torch.float32, device=dev)
+                gM_keep.append(gM_scratch)
             _lib.check(lib.ngcf_dense_bwd(_lib.ptr(gE_next), slot_loc.data_ptr(), gsum.data_ptr(), D, col_off,
                                           st.E[k + 1][r0:r0 + nloc].data_ptr(), st.S[k].data_ptr(),
                                           st.E[k][r0:r0 + nloc].data_ptr(), nv, d_in, d_out,
@@ -230,6 +242,9 @@ class _Propagate(torch.autograd.Function):
                            compact=st.comp_b[k] if st.comp_b is not None else None)   # gE_k = gEl + L^T gS (+ row grads)
             if mod._trace is not None:                                # debugging aid: per-layer backward tensors
                 mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
+        if overlap:                                                   # join: the weight gradients are complete
+            _lib.check(lib.ngcf_set_wgrad_stream(None), "set_wgrad_stream")
+            torch.cuda.current_stream().wait_stream(mod._side_stream)
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
                    "rowgrad_reset")
         if sh is not None:
@@ -322,6 +337,8 @@ class NGCF(nn.Module):
         self._group = None
         self._xchg = None        # sharded.PeerExchange (peer-memory exchange) when available
         self._sparse_last = os.environ.get("NGCF_B200_SPARSE_LAST", "1") == "1"
+        self._wgrad_overlap = os.environ.get("NGCF_B200_WGRAD_OVERLAP", "auto")    # "0" | "1" | "auto" (row-sharded runs)
+        self._side_stream = None
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 

@@ -21,7 +21,7 @@ class NgcfCsr(C.Structure):
                 ("hub_of_row", _vp), ("hub_chunk_ptr", _vp), ("chunk_ptr", _vp), ("hub_ent", _vp),
                 ("chunk_row", _vp), ("chunk_tiles", _vp), ("hub_rows", _vp), ("hub_done", _vp), ("key_l", _vp), ("key_t", _vp), ("key_row_offset", _i64),
                 ("n_tiles", _i32), ("n_hub", _i32), ("n_chunks", _i32),
-                ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32), ("tile_hubmask", _vp), ("work_ctr", _vp)]
+                ("n_chunk_tiles", _i32), ("rowptr_nnz", _i32), ("tile_hubmask", _vp)]
 
 
 _csr_p = C.POINTER(NgcfCsr)
@@ -56,6 +56,7 @@ SIGNATURES = {
     "ngcf_rowgrad_reset": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, _vp, _vp],
     "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32,
                        _u64, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngcf_set_wgrad_stream": [_vp],
     "ngcf_rowgrad_normalize": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, C.POINTER(_vp),
                                C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, _vp],
     "ngcf_adam_step": [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.c_int,

@@ -1279,6 +1279,15 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
     return NGCF_OK;
 }
 
+// Optional second stream for the weight-gradient launches (ngcf_set_wgrad_stream): they depend on the backward kernel's
+// gM only, so a caller with other work queued behind the backward kernel (the row-sharded step: the gS exchange and the
+// transposed product) can let them run beside it.  Thread-local; the caller joins the stream.
+static thread_local cudaStream_t g_wgrad_stream = nullptr;
+extern "C" int ngcf_set_wgrad_stream(void* stream_or_null) {
+    g_wgrad_stream = as_stream(stream_or_null);
+    return NGCF_OK;
+}
+
 // d_in = 64 with d_out in {32, 64} is one block; 128-wide sides are decomposed into 64-wide blocks of the same kernels:
 // T = gM·[W1|W2] is linear in gM, so the d_out halves accumulate into gS / gEl in place; the weight-gradient blocks are
 // independent.  A blocked d_out needs the output-row gradients already normalize-backwarded (gh_normalized): the
@@ -1322,10 +1331,20 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
     const int n_chunks = (int)ceil_div64(n_rows, WG_ROWS);
     const size_t smem2 = 1024 + (size_t)2 * (8 + 2 * KBo) * WG_BLOCK + sizeof(WgBars);
     const int grid2 = (int)min((int64_t)n_chunks, (int64_t)ngcf_num_sms());
+    cudaStream_t ws = st;
+    if (g_wgrad_stream && g_wgrad_stream != st) {                        // fork: the weight gradients wait for gM only
+        static cudaEvent_t ev[64] = {};
+        int dev = 0;
+        NGCF_CUDA(cudaGetDevice(&dev));
+        if (!ev[dev & 63]) NGCF_CUDA(cudaEventCreateWithFlags(&ev[dev & 63], cudaEventDisableTiming));
+        NGCF_CUDA(cudaEventRecord(ev[dev & 63], st));
+        NGCF_CUDA(cudaStreamWaitEvent(g_wgrad_stream, ev[dev & 63], 0));
+        ws = g_wgrad_stream;
+    }
     for (int ih = 0; ih < IH; ++ih)
         for (int oh = 0; oh < OH; ++oh) {
             WgradArgs w{S, E, gM_scratch, n_rows, bn, gW1, gW2, n_chunks, d_in, ih * 64, d_out, oh * bn};
-            NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, st, w));
+            NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, ws, w));
             NGCF_LAUNCH_OK("wgrad_tc_kernel");
         }
     return NGCF_OK;

@@ -59,9 +59,8 @@ struct SpmmArgs {
     int transposed;
     uint32_t row_off;
     unsigned long long* dbg;        // optional [n_ctas][4] = {start, staged, done, smid} in globaltimer ns (tools/spmm_timeline.py)
-    // warp-streaming kernel
+    // streaming kernel
     const uint32_t* tile_hubmask;   // [n_row_tiles] bit i = row i of the tile is a hub (written by hub_finish_kernel); NULL: no hubs
-    int32_t* work_ctr;              // [2] = {next tile, warps done}; zero between launches
     int n_row_tiles;
     int add_mode;                   // Y already holds the addend: row sums are ADDED to it (red.global.add)
     const int32_t* hub_rows;        // [n_hub]
@@ -598,7 +597,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32) compact_kernel(CompactArgs a, i
     }
 }
 
-// NGCF_B200_SPMM=rows selects the row-per-warp kernel (A/B comparisons); default: the warp-streaming kernel
+// NGCF_B200_SPMM=rows selects the row-per-warp kernel (A/B comparisons); default: the streaming kernel
 bool spmm_use_stream() {
     static int v = -1;
     if (v < 0) {
@@ -683,10 +682,9 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
                      (!addend || (aligned16(addend) && ld_add % 4 == 0)) &&
                      (!slot || (aligned16(gsum) && ld_gsum % 4 == 0)) && (g->n_hub == 0 || aligned16(hub_partial));
     const bool hubs = g->n_hub > 0 && g->n_chunks > 0;
-    // vector widths: the persistent warp-streaming kernel (needs the plan's work counter); NGCF_B200_SPMM=rows or any
-    // other width: the row-per-warp kernel
-    const bool stream_k = vec && spmm_use_stream() && g->work_ctr != nullptr && (!hubs || (g->tile_hubmask && g->hub_rows));
-    NGCF_REQUIRE(stream_k || !c_ent, "spmm: compacted survivor lists need the warp-streaming kernel (width %% 4 == 0)");
+    // vector widths: the streaming kernel; NGCF_B200_SPMM=rows or any other width: the row-per-warp kernel
+    const bool stream_k = vec && spmm_use_stream() && (!hubs || (g->tile_hubmask && g->hub_rows));
+    NGCF_REQUIRE(stream_k || !c_ent, "spmm: compacted survivor lists need the streaming kernel (width %% 4 == 0)");
     NGCF_REQUIRE(stream_k || !hubs || g->hub_done, "spmm: hub_done counters missing");
     SpmmArgs a{};
     a.rows = TileSide{reinterpret_cast<const TileInfo*>(g->tiles), g->rowptr, reinterpret_cast<const int2*>(g->ent), nullptr,
@@ -709,7 +707,6 @@ extern "C" int ngcf_spmm(const ngcf_csr* g, const float* X, int64_t ldx, int d, 
     a.Yrows = Y;
     a.ld_yrows = ldy;
     a.tile_hubmask = hubs ? g->tile_hubmask : nullptr;
-    a.work_ctr = g->work_ctr;
     a.n_row_tiles = g->n_tiles;
     a.hub_rows = g->hub_rows;
     a.n_hub = hubs ? g->n_hub : 0;

@@ -142,7 +142,6 @@ class CsrSide:
             self.tile_hubmask = (bits & 0xFFFFFFFF).to(torch.int32)      # bit pattern of a uint32
         else:
             self.tile_hubmask = None
-        self.work_ctr = torch.zeros(2, **i32)    # tile counter + finished-warp counter of the streaming SpMM
         self.ent = None          # base entry pairs, set by LaplacianPlan
         self.key_l = self.key_t = None   # static node-dropout keys (ensure_keys)
         self.key_row_offset = 0
@@ -200,7 +199,6 @@ class CsrSide:
             s.n_chunk_tiles = int(self.chunk_tiles.shape[0]) if self.chunk_tiles is not None else 0
             s.rowptr_nnz = self.nnz_short
             s.tile_hubmask = _lib.ptr(self.tile_hubmask)
-            s.work_ctr = self.work_ctr.data_ptr()
             self._struct_cache[key] = s
         return s
 
