@@ -224,6 +224,11 @@ int ngcf_mess_dropout_bits(int64_t n_rows, int d_out, float mess_p, uint64_t see
 int ngcf_gather_concat(const float* const* layers_host, const int* dims_host, int n_layers_plus1,
                        const int64_t* rows, int64_t row_offset, int64_t n_out,
                        float* out, int64_t ld_out, void* stream);
+/* The same for up to four row sets at once (the user / positive / negative rows of a batch, NGCF.py:151-155): one launch;
+ * set j gathers rows rows_host[j][i] + offsets_host[j] into outs_host[j] ([sizes_host[j], ld_out]). */
+int ngcf_gather_concat_sets(const float* const* layers_host, const int* dims_host, int n_layers_plus1,
+                            const int64_t* const* rows_host, const int64_t* offsets_host, const int64_t* sizes_host,
+                            float* const* outs_host, int n_sets, int64_t ld_out, void* stream);
 
 /* ---- BPR loss: bprloss.py:15-22, forward and row gradients in one kernel ------------------------------
  * loss = (-sum_b logsigmoid(|u_b.p_b| - |u_b.n_b|)

@@ -127,14 +127,12 @@ class _Propagate(torch.autograd.Function):
             st.S.append(S)
             st.E.append(Xn)
         D = sum(st.dims)
-        outs = []
         layers, dims = _lib.ptr_array(st.E), _lib.int_array(st.dims)
-        for j in range(n_sets):
-            rows = st.rows[j]
-            o = torch.empty(rows.numel(), D, dtype=torch.float32, device=dev)
-            _lib.check(lib.ngcf_gather_concat(layers, dims, K + 1, rows.data_ptr(), st.offsets[j], rows.numel(),
-                                              o.data_ptr(), D, _stream()), "gather_concat")      # NGCF.py:144-155
-            outs.append(o)
+        outs = [torch.empty(st.rows[j].numel(), D, dtype=torch.float32, device=dev) for j in range(n_sets)]
+        _lib.check(lib.ngcf_gather_concat_sets(layers, dims, K + 1, _lib.ptr_array(st.rows[:n_sets]),
+                                               _lib.i64_array(st.offsets[:n_sets]),
+                                               _lib.i64_array([r.numel() for r in st.rows[:n_sets]]), _lib.ptr_array(outs),
+                                               n_sets, D, _stream()), "gather_concat_sets")       # NGCF.py:144-155
         ctx.st, ctx.mod, ctx.n_sets = st, mod, n_sets
         return tuple(outs)
 

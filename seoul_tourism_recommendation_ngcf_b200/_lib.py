@@ -50,6 +50,8 @@ SIGNATURES = {
                        _vp],
     "ngcf_mess_dropout_bits": [_i64, C.c_int, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp],
     "ngcf_gather_concat": [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, _vp, _i64, _i64, _vp, _i64, _vp],
+    "ngcf_gather_concat_sets": [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64),
+                                C.POINTER(_vp), C.c_int, _i64, _vp],
     "ngcf_bpr_fwd_bwd": [_vp, _vp, _vp, _i64, C.c_int, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "ngcf_rowgrad_scatter": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64), C.c_int, C.c_int, _vp,
                              _vp, _vp],

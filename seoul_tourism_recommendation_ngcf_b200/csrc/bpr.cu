@@ -16,13 +16,21 @@ struct GatherArgs {
     int64_t ld_out;
 };
 
-// one warp per output row
-__global__ void gather_concat_kernel(GatherArgs a) {
-    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (b >= a.n_out) return;
-    const int64_t r = (a.rows ? a.rows[b] : b) + a.row_offset;
-    float* o = a.out + b * a.ld_out;
+// up to four row sets (users, positives, negatives of a batch) gathered by ONE launch
+struct GatherSetsArgs {
+    const float* layer[NGCF_MAX_LAYERS + 1];
+    int dim[NGCF_MAX_LAYERS + 1];
+    int n;
+    const int64_t* rows[4];
+    int64_t row_offset[4];
+    int64_t base[5];     // first global output index of set j; base[n_sets] = total
+    float* out[4];
+    int n_sets;
+    int64_t ld_out;
+};
+
+template <typename A>
+__device__ __forceinline__ void gather_row(const A& a, int64_t r, float* o, int lane) {
     int off = 0;
     for (int k = 0; k < a.n; ++k) {
         const int d = a.dim[k];
@@ -44,6 +52,23 @@ __global__ void gather_concat_kernel(GatherArgs a) {
         }
         off += d;
     }
+}
+
+// one warp per output row
+__global__ void gather_concat_kernel(GatherArgs a) {
+    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= a.n_out) return;
+    gather_row(a, (a.rows ? a.rows[b] : b) + a.row_offset, a.out + b * a.ld_out, lane);
+}
+__global__ void gather_concat_sets_kernel(GatherSetsArgs a) {
+    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= a.base[a.n_sets]) return;
+    int j = 0;
+    while (b >= a.base[j + 1]) ++j;
+    const int64_t i = b - a.base[j];
+    gather_row(a, a.rows[j][i] + a.row_offset[j], a.out[j] + i * a.ld_out, lane);
 }
 
 // ---- BPR ----------------------------------------------------------------------------------------------
@@ -216,6 +241,37 @@ extern "C" int ngcf_gather_concat(const float* const* layers_host, const int* di
     if (n_out <= 0) return NGCF_OK;
     gather_concat_kernel<<<(unsigned)ceil_div64(n_out * 32, 256), 256, 0, as_stream(stream)>>>(a);
     NGCF_LAUNCH_OK("gather_concat_kernel");
+    return NGCF_OK;
+}
+
+extern "C" int ngcf_gather_concat_sets(const float* const* layers_host, const int* dims_host, int n_layers_plus1,
+                                       const int64_t* const* rows_host, const int64_t* offsets_host,
+                                       const int64_t* sizes_host, float* const* outs_host, int n_sets, int64_t ld_out,
+                                       void* stream) {
+    NGCF_REQUIRE(layers_host && dims_host && rows_host && offsets_host && sizes_host && outs_host, "gather_concat_sets: null pointer");
+    NGCF_REQUIRE(n_layers_plus1 >= 1 && n_layers_plus1 <= NGCF_MAX_LAYERS + 1, "gather_concat_sets: %d blocks", n_layers_plus1);
+    NGCF_REQUIRE(n_sets >= 1 && n_sets <= 4, "gather_concat_sets: n_sets %d not in [1,4]", n_sets);
+    GatherSetsArgs a{};
+    int D = 0;
+    for (int k = 0; k < n_layers_plus1; ++k) {
+        NGCF_REQUIRE(layers_host[k] && dims_host[k] > 0 && dims_host[k] <= NGCF_MAX_WIDTH, "gather_concat_sets: bad block %d", k);
+        a.layer[k] = layers_host[k];
+        a.dim[k] = dims_host[k];
+        D += dims_host[k];
+    }
+    NGCF_REQUIRE(ld_out >= D, "gather_concat_sets: ld_out %lld < total width %d", (long long)ld_out, D);
+    a.n = n_layers_plus1; a.n_sets = n_sets; a.ld_out = ld_out;
+    int64_t total = 0;
+    for (int j = 0; j < n_sets; ++j) {
+        NGCF_REQUIRE(sizes_host[j] >= 0 && (sizes_host[j] == 0 || (rows_host[j] && outs_host[j])), "gather_concat_sets: set %d", j);
+        a.rows[j] = rows_host[j]; a.row_offset[j] = offsets_host[j]; a.out[j] = outs_host[j];
+        a.base[j] = total;
+        total += sizes_host[j];
+    }
+    for (int j = n_sets; j <= 4; ++j) a.base[j] = total;
+    if (total == 0) return NGCF_OK;
+    gather_concat_sets_kernel<<<(unsigned)ceil_div64(total * 32, 256), 256, 0, as_stream(stream)>>>(a);
+    NGCF_LAUNCH_OK("gather_concat_sets_kernel");
     return NGCF_OK;
 }
 
