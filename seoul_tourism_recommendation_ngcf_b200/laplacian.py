@@ -66,24 +66,39 @@ def laplacian_coo_device(users, items, ratings, n_user: int, n_item: int, device
     return torch.sparse_coo_tensor(idx, val[order], (N, N), is_coalesced=False, check_invariants=False)
 
 
-def build_lap_list(years, users, items, ratings, n_user: int, n_item: int, device=None) -> list:
-    """Year loop of Matrix.create_matrix (matrix.py:41-67): R is never reset, so each year's graph is the
-    previous one overwritten by that year's ratings; the slot is ``year % 18``."""
+def accumulate_years(years, users, items, ratings, n_item: int):
+    """The year loop of Matrix.create_matrix (matrix.py:41-47) without a per-edge Python loop: R is never reset, so
+    after year y it holds every (user, item) seen so far with the LAST rating written (rows in frame order, years in
+    first-seen order).  Yields (year, keys = user * n_item + item, ratings) of the accumulated R after each year."""
     years = np.asarray(years)
     users = np.asarray(users, dtype=np.int64)
     items = np.asarray(items, dtype=np.int64)
     ratings = np.asarray(ratings, dtype=np.float32)
-    uniq = list(dict.fromkeys(years.tolist()))
-    lap_list = [[] for _ in uniq]
-    acc = {}                                                    # (user*n_item+item) -> rating, later rows win
     keys_all = users * n_item + items
-    for y in uniq:
+    acc_k = np.empty(0, dtype=np.int64)
+    acc_v = np.empty(0, dtype=np.float32)
+    for y in dict.fromkeys(years.tolist()):
         m = years == y
-        for k, r in zip(keys_all[m].tolist(), ratings[m].tolist()):
-            acc[k] = r
-        keys = np.fromiter(acc.keys(), dtype=np.int64, count=len(acc))
-        vals = np.fromiter(acc.values(), dtype=np.float32, count=len(acc))
-        if device is not None and torch.device(device).type == "cuda":
+        k = np.concatenate([acc_k, keys_all[m]])               # later positions win: the year's rows come after R
+        v = np.concatenate([acc_v, ratings[m]])
+        _, last = np.unique(k[::-1], return_index=True)        # first occurrence in the reversed array = last write
+        pos = np.sort(k.size - 1 - last)                       # keep dict insertion order irrelevant: sorted by position
+        acc_k, acc_v = k[pos], v[pos]
+        yield y, acc_k, acc_v
+
+
+def build_lap_list(years, users, items, ratings, n_user: int, n_item: int, device=None, fmt: str = "coo") -> list:
+    """Year loop of Matrix.create_matrix (matrix.py:41-67): R is never reset, so each year's graph is the
+    previous one overwritten by that year's ratings; the slot is ``year % 18``.  fmt="coo": the reference's
+    ``torch.sparse_coo`` elements (host builder, or the device builder when ``device`` is CUDA); fmt="csr": device-built
+    ``plgraph.CsrLaplacian`` elements - the kernels' layout directly, no COO in between (needs a CUDA ``device``)."""
+    uniq = list(dict.fromkeys(np.asarray(years).tolist()))
+    lap_list = [[] for _ in uniq]
+    for y, keys, vals in accumulate_years(years, users, items, ratings, n_item):
+        if fmt == "csr":
+            from .plgraph import laplacian_csr_device
+            lap_list[y % 18] = laplacian_csr_device(keys // n_item, keys % n_item, vals, n_user, n_item, device)
+        elif device is not None and torch.device(device).type == "cuda":
             lap_list[y % 18] = laplacian_coo_device(keys // n_item, keys % n_item, vals, n_user, n_item, device)
         else:
             lap_list[y % 18] = laplacian_coo(keys // n_item, keys % n_item, vals, n_user, n_item)

@@ -33,8 +33,10 @@ class Matrix(nn.Module):
         self.args = args                  # the reference reads parsers.args for the pickle's file name (matrix.py:72)
         # "host": numpy, bit-identical to the reference's values; "device": ngcf_laplacian_entries on `device` (CUDA),
         # equal to 5e-7 relative (d^-1/2 correctly rounded instead of numpy's float32 power) — for graphs where even the O(nnz) host pass is the slow part
-        if builder not in ("host", "device"):
-            raise ValueError("builder is 'host' or 'device'")
+        # "csr": built on the device straight into the kernels' CSR (plgraph.CsrLaplacian elements: no COO at all; NGCF
+        # accepts them in lap_list like the reference's sparse tensors)
+        if builder not in ("host", "device", "csr"):
+            raise ValueError("builder is 'host', 'device' or 'csr'")
         self.builder = builder
         self.lap_list = [[] for _ in self.df['year'].unique()]
 
@@ -42,8 +44,9 @@ class Matrix(nn.Module):
         df = self.df
         laps = build_lap_list(df['year'].to_numpy(), df['userid'].to_numpy(), df['itemid'].to_numpy(),
                               df[self.rating_col].to_numpy(), self.n_user, self.n_item,
-                              device=self.device if self.builder == "device" else None)
-        self.lap_list = [L.to(self.device) if not isinstance(L, list) else L for L in laps]
+                              device=self.device if self.builder != "host" else None,
+                              fmt="csr" if self.builder == "csr" else "coo")
+        self.lap_list = [L.to(self.device) if hasattr(L, "is_sparse") and L.is_sparse else L for L in laps]
         print('Laplacian Matrix Created!')
         if self.save_data:
             a, d1 = self.args, datetime.now()

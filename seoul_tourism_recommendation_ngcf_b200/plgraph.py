@@ -91,3 +91,36 @@ def powerlaw_laplacian(n_user: int, n_item: int, n_edges: int, device, alpha: fl
         row0, n_rows, world = shard.r0, shard.rows, shard.world
     keys = powerlaw_entries(n_user, n_item, n_edges, alpha, seed, row0, n_rows, device)
     return laplacian_from_keys(keys, N, row0, n_rows, group, world, shard)
+
+
+def laplacian_csr_device(users, items, ratings, n_user: int, n_item: int, device) -> CsrLaplacian:
+    """One year's Laplacian (matrix.py:48-67) from distinct (user, item, rating) triples, built on the device straight
+    into CSR: both directions of every non-zero rating as keys ``row << 32 | col``, one sort, count degrees
+    (matrix.py:55), values ``d_i * (a_ij * d_j)`` evaluated in float64 and stored as float32 (matrix.py:56-62,82).
+    Same structure as ``laplacian.laplacian_coo`` and values within 5e-7 (numpy's float32 power is not correctly
+    rounded)."""
+    import numpy as np
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("laplacian_csr_device builds on a CUDA device only")
+    u = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(device)
+    i = torch.as_tensor(np.asarray(items, dtype=np.int64)).to(device) + n_user
+    r = torch.as_tensor(np.asarray(ratings, dtype=np.float32)).to(device)
+    nz = r != 0                                                  # zero ratings are not edges (dok_matrix drops them)
+    u, i, r = u[nz], i[nz], r[nz]
+    N = n_user + n_item
+    keys = torch.cat([(u << 32) | i, (i << 32) | u])
+    keys, order = torch.sort(keys)
+    a = torch.cat([r, r])[order]
+    row, col = keys >> 32, (keys & 0xFFFFFFFF)
+    deg = torch.bincount(row, minlength=N)
+    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    d_sqrt = torch.pow(deg.to(torch.float32), -0.5)
+    d_sqrt[torch.isinf(d_sqrt)] = 0.0
+    vals = (d_sqrt[row].double() * (a.double() * d_sqrt[col].double())).float()
+    keep = vals != 0
+    if not bool(keep.all()):                                     # (a product that underflows to 0 is no entry either)
+        row, col, vals = row[keep], col[keep], vals[keep]
+        rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=N), 0)
+    return CsrLaplacian(rowptr.to(torch.int32), col.to(torch.int32), vals, N, 0)
