@@ -37,9 +37,10 @@ class _Propagate(torch.autograd.Function):
     """K-layer propagation + output-row gather (NGCF.py:120-156) and its hand-written backward.
 
     With ``mod._shard`` set (row-sharded multi-GPU run, sharded.py) every per-layer tensor below holds this rank's
-    row block only, ``st.E[k]`` is the all-gathered full ``[N_pad, d_k]`` layer input, and the collectives are: one
-    all-gather per layer in each direction, one all-gather of the table gradient and one all-reduce of the W/b
-    gradients.  Without it ``st.E[k]`` is simply E_k and nothing is communicated."""
+    row block only and ``st.E[k]`` is the full ``[N_pad, d_k]`` layer input, assembled by one exchange per layer and
+    direction plus one for the table gradient and one for the W/b gradients: peer-memory stores over NVLink
+    (sharded.PeerExchange; the last layer's output travels for the batch rows only) or, without symmetric memory, NCCL
+    all-gathers / an all-reduce.  Without a shard ``st.E[k]`` is simply E_k and nothing is communicated."""
 
     @staticmethod
     def forward(ctx, mod, st: _Ctx, n_sets, user_w, item_w, *wb):
@@ -367,7 +368,8 @@ class NGCF(nn.Module):
     # ---- multi-GPU ------------------------------------------------------------------------------------
     def shard(self, group=None, shards=None):
         """Row-partitions the propagation over the ranks of ``group`` (default process group): this rank then
-        computes rows [rank*rows, (rank+1)*rows) of every layer (sharded.py).  Parameters stay replicated; every
+        computes its contiguous block of rows of every layer (equal blocks, or ``shards`` = a sharded.BalancedShards
+        cut by work).  Parameters stay replicated; every
         rank must call forward with the same batch and the same torch CPU RNG state (the per-step RNG key is drawn
         from it).  Explicit-mask node dropout (rng="reference") is not available in this mode."""
         if not dist.is_initialized():

@@ -1,11 +1,13 @@
 """Row partition of the propagation across the GPUs of one box (BASELINE.json north_star).
 
-Rank r owns the equal block of rows [r*rows, (r+1)*rows) of L and of every per-layer tensor (E_k, S_k, gradients);
-N is padded to ``world * rows`` with empty rows so one ``all_gather_into_tensor`` assembles a full, contiguous
-``[N_pad, d]`` tensor whose row index is the global node id.  The reference has no multi-device code at all; this
-is the design the contract prescribes: per layer one all-gather of the E shards (forward) and of the gS shards
-(backward), an all-reduce of the W/b gradients and an all-gather of the table-gradient shards (the two embedding
-tables stay replicated so ``state_dict`` is unchanged).  The helpers in this file are pure host logic (CPU-testable).
+Rank r owns a contiguous block of rows of L and of every per-layer tensor (E_k, S_k, gradients): equal blocks
+(``RowShards``; N is padded to ``world * rows`` with empty rows) or blocks cut by work (``BalancedShards``).  The
+reference has no multi-device code at all; this is the design the contract prescribes.  Per layer and direction every
+rank needs every rank's rows of one ``[N_pad, d]`` matrix; the table gradient has to be complete everywhere (the two
+embedding tables stay replicated so ``state_dict`` is unchanged) and the W/b gradients are sums over the blocks.
+``PeerExchange`` moves all of that with peer-memory stores over NVLink (``ngcf_push_rows`` on symmetric memory, no
+library collective); ``all_gather_rows`` / ``dist.all_reduce`` are the NCCL fallback for equal blocks.  The shard
+descriptors are pure host logic (CPU-testable).
 """
 from __future__ import annotations
 
