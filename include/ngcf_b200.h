@@ -201,6 +201,10 @@ int ngcf_push_selected_rows(float* const* matrix_on_rank_host, uint32_t* const* 
 int ngcf_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
                       int d_in, int d_out, float* wcat /*[2*d_in, d_out]*/, float* bias_eff /*[d_out]*/,
                       void* stream);
+/* The same for every layer of a step in one launch (host arrays of n_layers pointers / widths). */
+int ngcf_pack_weights_all(const float* const* W1_host, const float* const* b1_host, const float* const* W2_host,
+                          const float* const* b2_host, const int* d_in_host, const int* d_out_host, int n_layers,
+                          float* const* wcat_host, float* const* bias_host, void* stream);
 /* E_out = Dropout(LeakyReLU_slope((S+E)·W1^T + (S*E)·W2^T + bias_eff)).
  *   mess_mult : optional [n_rows, d_out] multipliers standing in for nn.Dropout (mask injection);
  *   mess_p>0  : device-RNG inverted dropout keyed on (seed + *seed_dev, layer, element); ignored with mess_mult.

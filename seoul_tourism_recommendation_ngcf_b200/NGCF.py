@@ -30,7 +30,7 @@ def _stream() -> int:
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
     __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
-                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode", "last_partial")
+                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode", "last_partial", "comp_b_stream", "needs_grad")
 
 
 class _Propagate(torch.autograd.Function):
@@ -59,6 +59,8 @@ class _Propagate(torch.autograd.Function):
         st.bits_f = st.bits_b = st.comp_f = st.comp_b = None
         st.node_mode = mod._node_mode
         st.last_partial = None
+        st.comp_b_stream = None
+        needs_grad = st.needs_grad
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
             # each of the 2K products; a symmetric L serves both directions from one pass.  "compact" (default) also
@@ -69,7 +71,21 @@ class _Propagate(torch.autograd.Function):
             # (every width, the last one too: the batch-row gradient rows of the final backward product are D_total wide)
             node_mode = mod._node_mode if all(d % 4 == 0 for d in st.dims) or mod._node_mode == "inkernel" else "bits"
             st.node_mode = node_mode
-            if node_mode == "compact":
+            if node_mode == "compact" and shared and needs_grad and mod._compact_overlap:
+                # the forward needs L's survivors now; L^T's are first read by the backward, so that half of the pass
+                # runs on a second stream beside the forward's first kernels (joined before the first backward product)
+                st.comp_f, _ = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=False)
+                main = torch.cuda.current_stream()
+                if mod._side_stream2 is None:
+                    mod._side_stream2 = torch.cuda.Stream(device=dev)
+                mod._side_stream2.wait_stream(main)
+                with torch.cuda.stream(mod._side_stream2):
+                    _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
+                for e_, c_ in st.comp_b:                                # allocated under the side stream, used on main
+                    e_.record_stream(main)
+                    c_.record_stream(main)
+                st.comp_b_stream = mod._side_stream2
+            elif node_mode == "compact":
                 st.comp_f, ct = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=shared)
                 if shared:
                     st.comp_b = ct
@@ -88,16 +104,19 @@ class _Propagate(torch.autograd.Function):
                                                       _lib.ptr(st.seed_dev), k, r0, bits.data_ptr(), _stream()),
                            "mess_dropout_bits")
                 st.mess_bits[k] = bits
+        # [W1^T ; W2^T] and 2 b1 + b2 of every layer: one launch (NGCF.py:131-136 applies w1_list[i] twice)
+        wcats = [torch.empty(2 * st.dims[k] * st.dims[k + 1], dtype=torch.float32, device=dev) for k in range(K)]
+        biases = [torch.empty(st.dims[k + 1], dtype=torch.float32, device=dev) for k in range(K)]
+        _lib.check(lib.ngcf_pack_weights_all(_lib.ptr_array(W1), _lib.ptr_array(b1), _lib.ptr_array(W2), _lib.ptr_array(b2),
+                                             _lib.int_array(st.dims[:K]), _lib.int_array(st.dims[1:]), K,
+                                             _lib.ptr_array(wcats), _lib.ptr_array(biases), _stream()), "pack_weights_all")
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
             S = spmm(side, vals, st.E[k], d_in, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
                      row_offset=r0, keep_bits=st.bits_f,
                      compact=st.comp_f[k] if st.comp_f is not None else None)               # NGCF.py:124-130
-            wcat = torch.empty(2 * d_in * d_out, dtype=torch.float32, device=dev)
-            bias = torch.empty(d_out, dtype=torch.float32, device=dev)
-            _lib.check(lib.ngcf_pack_weights(W1[k].data_ptr(), b1[k].data_ptr(), W2[k].data_ptr(), b2[k].data_ptr(),
-                                             d_in, d_out, wcat.data_ptr(), bias.data_ptr(), _stream()), "pack_weights")
+            wcat, bias = wcats[k], biases[k]
             xkey = None
             if sh is None:
                 Xn = En = torch.empty(N, d_out, dtype=torch.float32, device=dev)
@@ -182,6 +201,9 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
+        if st.comp_b_stream is not None:                              # L^T's survivor lists were compacted beside the forward
+            torch.cuda.current_stream().wait_stream(st.comp_b_stream)
+            st.comp_b_stream = None
         if st.drop_p > 0 and st.node_mode == "compact" and st.comp_b is None:
             _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         if st.drop_p > 0 and st.node_mode == "bits" and st.bits_b is None:
@@ -338,6 +360,10 @@ class NGCF(nn.Module):
         self._sparse_last = os.environ.get("NGCF_B200_SPARSE_LAST", "1") == "1"
         self._wgrad_overlap = os.environ.get("NGCF_B200_WGRAD_OVERLAP", "auto")    # "0" | "1" | "auto" (row-sharded runs)
         self._side_stream = None
+        self._side_stream2 = None
+        # L^T's survivor lists on a second stream beside the forward: measured slower on one B200 (0.518 vs 0.510 ms per
+        # step: the compaction is issue-bound and takes SM time from the forward's first kernels), so opt-in only
+        self._compact_overlap = os.environ.get("NGCF_B200_COMPACT_OVERLAP", "0") == "1"
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
@@ -535,6 +561,8 @@ class NGCF(nn.Module):
         st.rows = [u_id, pos_item] + ([neg_item] if has_neg else [])
         st.offsets = [0, self.n_user] + ([self.n_user] if has_neg else [])
 
+        # (autograd.Function.forward runs with grad mode off: whether a backward will follow is decided here)
+        st.needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         wb = [l.weight for l in self.w1_list] + [l.bias for l in self.w1_list] + \
              [l.weight for l in self.w2_list] + [l.bias for l in self.w2_list]
         outs = _Propagate.apply(self, st, len(st.rows), self.user_embedding.weight, self.item_embedding.weight, *wb)

@@ -46,6 +46,8 @@ SIGNATURES = {
                                   C.POINTER(_vp), _vp],
     "ngcf_node_dropout_bits": [_csr_p, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp, _vp],
     "ngcf_pack_weights": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp],
+    "ngcf_pack_weights_all": [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int),
+                              C.POINTER(C.c_int), C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp],
     "ngcf_dense_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32, _u64, _vp, C.c_int, _i64, _vp,
                        _vp],
     "ngcf_mess_dropout_bits": [_i64, C.c_int, _f32, _u64, _vp, C.c_int, _i64, _vp, _vp],

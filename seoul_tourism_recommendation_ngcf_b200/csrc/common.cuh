@@ -162,10 +162,18 @@ __device__ __forceinline__ bool node_keep(float p, uint64_t seed, int layer, uin
     return (node_keep_bits(p, seed, layer + 1, row, col) >> layer) & 1u;
 }
 
+// 64 bits for the message-dropout decisions of one quad: three mixes (the layer is folded into the first word) instead
+// of ngcf_hash64's four - the dense epilogues spend most of their per-tile time on this chain (profiles/
+// r02_dense_fwd_timeline.txt)
+__device__ __forceinline__ uint2 ngcf_mess_hash(uint64_t seed, int layer, uint64_t quad) {
+    uint32_t h = ngcf_mix((uint32_t)quad ^ (uint32_t)seed ^ NGCF_STREAM_MESS ^ ((uint32_t)layer * 0x632BE5ABu));
+    h = ngcf_mix(h ^ ((uint32_t)(quad >> 32) + 0x9E3779B9u) ^ (uint32_t)(seed >> 32));
+    return make_uint2(h, ngcf_mix(h ^ 0x68E31DA4u));
+}
 // inverted-dropout multipliers of message dropout (NGCF.py:142) in device-RNG mode: one call covers the four
 // consecutive elements 4*quad .. 4*quad+3 of the flattened [N, d_out] layer output
 __device__ __forceinline__ float4 mess_multiplier4(float p, uint64_t seed, int layer, uint64_t quad) {
-    const uint2 r = ngcf_hash64(seed, (uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)layer, NGCF_STREAM_MESS);
+    const uint2 r = ngcf_mess_hash(seed, layer, quad);
     const uint32_t thr = ngcf_threshold16(p);
     const float s = 1.0f / (1.0f - p);
     return make_float4((r.x & 0xffffu) >= thr ? s : 0.f, (r.x >> 16) >= thr ? s : 0.f, (r.y & 0xffffu) >= thr ? s : 0.f,
@@ -173,7 +181,7 @@ __device__ __forceinline__ float4 mess_multiplier4(float p, uint64_t seed, int l
 }
 // the same decisions with the threshold and 1/(1-p) hoisted out of the caller's loop
 __device__ __forceinline__ float4 mess_multiplier4_pre(uint32_t thr, float s, uint64_t seed, int layer, uint64_t quad) {
-    const uint2 r = ngcf_hash64(seed, (uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)layer, NGCF_STREAM_MESS);
+    const uint2 r = ngcf_mess_hash(seed, layer, quad);
     return make_float4((r.x & 0xffffu) >= thr ? s : 0.f, (r.x >> 16) >= thr ? s : 0.f, (r.y & 0xffffu) >= thr ? s : 0.f,
                        (r.y >> 16) >= thr ? s : 0.f);
 }

@@ -25,6 +25,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
         bias_eff[o] = 2.0f * b1[o] + b2[o];
 }
 
+struct PackAllArgs {
+    const float* W1[NGCF_MAX_LAYERS];
+    const float* b1[NGCF_MAX_LAYERS];
+    const float* W2[NGCF_MAX_LAYERS];
+    const float* b2[NGCF_MAX_LAYERS];
+    float* wcat[NGCF_MAX_LAYERS];
+    float* bias[NGCF_MAX_LAYERS];
+    int d_in[NGCF_MAX_LAYERS], d_out[NGCF_MAX_LAYERS];
+};
+// every layer of a step in one launch: blockIdx.y = layer
+__global__ void pack_weights_all_kernel(PackAllArgs a) {
+    const int l = blockIdx.y, d_in = a.d_in[l], d_out = a.d_out[l];
+    const float* __restrict__ W1 = a.W1[l];
+    const float* __restrict__ W2 = a.W2[l];
+    const int total = 2 * d_in * d_out;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / d_out, o = i % d_out;
+        a.wcat[l][i] = k < d_in ? W1[o * d_in + k] : W2[o * d_in + (k - d_in)];
+    }
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < d_out; o += gridDim.x * blockDim.x)
+        a.bias[l][o] = 2.0f * a.b1[l][o] + a.b2[l][o];
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward epilogue
 // ------------------------------------------------------------------------------------------------
@@ -459,6 +482,26 @@ extern "C" int ngcf_pack_weights(const float* W1, const float* b1, const float* 
                  "pack_weights: widths %d -> %d not in [1,%d]", d_in, d_out, NGCF_MAX_WIDTH);
     pack_weights_kernel<<<32, 256, 0, as_stream(stream)>>>(W1, b1, W2, b2, d_in, d_out, wcat, bias_eff);
     NGCF_LAUNCH_OK("pack_weights_kernel");
+    return NGCF_OK;
+}
+
+extern "C" int ngcf_pack_weights_all(const float* const* W1_host, const float* const* b1_host, const float* const* W2_host,
+                                     const float* const* b2_host, const int* d_in_host, const int* d_out_host, int n_layers,
+                                     float* const* wcat_host, float* const* bias_host, void* stream) {
+    NGCF_REQUIRE(W1_host && b1_host && W2_host && b2_host && d_in_host && d_out_host && wcat_host && bias_host,
+                 "pack_weights_all: null pointer");
+    NGCF_REQUIRE(n_layers >= 1 && n_layers <= NGCF_MAX_LAYERS, "pack_weights_all: %d layers", n_layers);
+    PackAllArgs a{};
+    for (int l = 0; l < n_layers; ++l) {
+        NGCF_REQUIRE(W1_host[l] && b1_host[l] && W2_host[l] && b2_host[l] && wcat_host[l] && bias_host[l],
+                     "pack_weights_all: null pointer (layer %d)", l);
+        NGCF_REQUIRE(d_in_host[l] > 0 && d_in_host[l] <= NGCF_MAX_WIDTH && d_out_host[l] > 0 && d_out_host[l] <= NGCF_MAX_WIDTH,
+                     "pack_weights_all: widths %d -> %d not in [1,%d]", d_in_host[l], d_out_host[l], NGCF_MAX_WIDTH);
+        a.W1[l] = W1_host[l]; a.b1[l] = b1_host[l]; a.W2[l] = W2_host[l]; a.b2[l] = b2_host[l];
+        a.wcat[l] = wcat_host[l]; a.bias[l] = bias_host[l]; a.d_in[l] = d_in_host[l]; a.d_out[l] = d_out_host[l];
+    }
+    pack_weights_all_kernel<<<dim3(32, (unsigned)n_layers), 256, 0, as_stream(stream)>>>(a);
+    NGCF_LAUNCH_OK("pack_weights_all_kernel");
     return NGCF_OK;
 }
 
