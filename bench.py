@@ -529,12 +529,24 @@ def run_ours(args):
         except NameError:
             pass
         torch.cuda.empty_cache()
-        for shp in ("amazon-book", "yelp2018"):
+        # BASELINE.json configs 4 and 3, and at N = 1 config 0: the reference's own shape (width 65 everywhere, main.py:63-64:
+        # the exact-fp32 FFMA dense kernels and the row-per-warp SpMM) with the reference's CPU step beside it
+        for shp in ("amazon-book", "yelp2018") + (("seoul",) if world == 1 else ()):
             try:
                 extra[shp] = time_shape(pkg, shp, dev, world, rank)
                 log(f"[bench] extra {shp}: {extra[shp]['ms_per_step']} ms/step")
             except Exception as e:
                 extra[shp] = {"error": f"{type(e).__name__}: {e}"}
+        if "seoul" in extra and "error" not in extra["seoul"] and not args.no_cpu_baseline:
+            try:
+                Ls, bs, infos = make_workload("seoul", n_batches=4)
+                mods = load_reference_modules()
+                if mods is not None:
+                    s_cpu, n_cpu = time_reference_modules(mods, Ls, bs, infos, "cpu", 10, 1, 4.0, threads=os.cpu_count() or 1)
+                    extra["seoul"]["reference_cpu"] = {"ms_per_step": round(s_cpu * 1e3, 2), "steps": n_cpu,
+                                                       "cores": os.cpu_count() or 1, "kind": "reference"}
+            except Exception as e:
+                log(f"[bench] seoul CPU reference failed ({type(e).__name__}: {e})")
 
     # ---- CPU baseline beside it ------------------------------------------------------------------------------
     cpu, torch_cuda = None, None

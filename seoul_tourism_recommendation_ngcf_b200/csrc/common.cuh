@@ -86,6 +86,12 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 // streaming 128-bit load of data this kernel only reads once: no L1 line is allocated.  In the tensor-core kernels
 // ~216 KB of the SM's 256 KB are shared memory, the L1 that remains is a few tens of KB, and every outstanding
 // allocating load pins a line of it: 8 loader warps x 8 loads x 4 lines could not even be in flight together.
+// Asks the memory system to bring [p, p + bytes) into L2 (no registers, no completion to wait for): one thread of a
+// persistent CTA issues it for the tile it will need a few tiles from now, so that the tile's loads meet L2 latency
+// instead of DRAM latency.  p 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"

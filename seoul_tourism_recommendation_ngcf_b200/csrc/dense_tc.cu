@@ -650,6 +650,10 @@ struct BwdTcArgs {
     // (row stride d_in_full) and of W1 / W2.  accumulate: add to the gS / gEl already there (an earlier d_out block);
     // first_in: this launch also writes gM and the bias gradients (once per d_out block).
     int d_out_full, out_off, d_in_full, in_off, accumulate, first_in;
+    // L2 prefetch distance in tiles (0 = off): the MMA warp's elected thread asks for the E_out / gE_next / S / E rows of
+    // tile it + pf while tile it is in progress.  The kernel's loads are in-flight-limited (32 KB per SM in the loaders'
+    // registers, 64 KB of cp.async in the epilogue) against DRAM latency; against L2 latency the same window is enough.
+    int pf;
 };
 
 struct BwdBars {
@@ -700,6 +704,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     }
     if (warp == TC_EPI_WARPS) tmem_alloc(&bars->tmem_base, 256);          // T x2 (128 columns each)
     if (tid < 64) bars->colsum[tid] = 0.f;
+    // rows of tile t in the three forward-pass tensors this kernel reads (contiguous: full-width launches only)
+    auto prefetch_tile = [&](int tile, bool fwd_tensors, bool grad) {
+        const int64_t row0 = (int64_t)tile * TC_ROWS;
+        if (row0 >= a.n_rows) return;
+        const int64_t nr = a.n_rows - row0 < TC_ROWS ? a.n_rows - row0 : TC_ROWS;
+        if (fwd_tensors) {
+            l2_prefetch_bulk(a.E_out + row0 * a.d_out_full, (uint32_t)(nr * a.d_out_full * 4));
+            l2_prefetch_bulk(a.S + row0 * a.d_in_full, (uint32_t)(nr * a.d_in_full * 4));
+            l2_prefetch_bulk(a.E + row0 * a.d_in_full, (uint32_t)(nr * a.d_in_full * 4));
+        }
+        if (grad && a.gE_next) l2_prefetch_bulk(a.gE_next + row0 * a.d_out_full, (uint32_t)(nr * a.d_out_full * 4));
+    };
+    if (a.pf > 0 && warp == TC_EPI_WARPS + 1 && lane == 0) {
+        // the first tiles' forward-pass tensors (E_out, S, E: nothing between the forward and here writes them) are asked
+        // for while the previous kernel still drains
+        for (int i = 0; i < a.pf; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < a.n_tiles) prefetch_tile(tile, true, false);
+        }
+    }
     // BT[n][o] = W1[o][n] (n < 64), W2[o][n-64]; W1/W2 are [d_out, d_in] row-major
     // W1 / W2 are the layer's parameters: nothing inside a step writes them, so their tile is built BEFORE pdl_wait()
     // (consecutive threads take consecutive n = consecutive addresses of W1 / W2: coalesced)
@@ -817,9 +841,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_bwd_tc_kernel(BwdTcArgs a
     } else if (warp == TC_EPI_WARPS) {
         // ======================= MMA issuer =====================================================================
         const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, 2 * d_in, 0, 0);
+        if (a.pf > 0 && lane == 0)                                        // gE_next comes from the kernel right before
+            for (int i = 0; i < a.pf && i < n_my; ++i) prefetch_tile(blockIdx.x + i * gridDim.x, false, true);
         for (int it = 0; it < n_my; ++it) {
             const int buf = it & 1;
             BWD_STAMP(1, it, 0);
+            if (a.pf > 0 && lane == 0 && it + a.pf < n_my) prefetch_tile(blockIdx.x + (it + a.pf) * gridDim.x, true, true);
             mbar_wait(&bars->full_gm, it & 1);
             BWD_STAMP(1, it, 1);
             mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -1028,6 +1055,7 @@ struct WgradArgs {
     // block decomposition: columns [in_off, in_off + 64) of S / E (row stride d_in_full) against columns
     // [out_off, out_off + d_out) of gM (row stride d_out_full) -> rows out_off.., columns in_off.. of gW1 / gW2
     int d_in_full, in_off, d_out_full, out_off;
+    int pf;                       // != 0: an idle epilogue thread asks for the CTA's S / E / gM rows in L2 up front
 };
 
 struct WgBars {
@@ -1067,6 +1095,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
 
     if (warp < TC_EPI_WARPS) {
         // ======================= final flush =====================================================================
+        // until then these warps are idle: one thread asks for every chunk of this CTA in L2 (the whole input of the
+        // launch, 12 * d bytes per row, fits L2 many times over), so the loaders' register-staged loads - 48 KB in flight
+        // per SM - meet L2 latency instead of DRAM latency
+        if (a.pf && warp == 0 && lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int64_t row0 = (int64_t)(blockIdx.x + it * gridDim.x) * WG_ROWS;
+                if (row0 >= a.n_rows) break;
+                const int64_t nr = a.n_rows - row0 < WG_ROWS ? a.n_rows - row0 : WG_ROWS;
+                l2_prefetch_bulk(a.gM + row0 * a.d_out_full, (uint32_t)(nr * a.d_out_full * 4));
+                l2_prefetch_bulk(a.S + row0 * a.d_in_full, (uint32_t)(nr * a.d_in_full * 4));
+                l2_prefetch_bulk(a.E + row0 * a.d_in_full, (uint32_t)(nr * a.d_in_full * 4));
+            }
+        }
         mbar_wait(&bars->d_full, 0);
         BWD_STAMP(0, 0, 0);
         tc_fence_after_sync();
@@ -1288,6 +1329,22 @@ extern "C" int ngcf_set_wgrad_stream(void* stream_or_null) {
     return NGCF_OK;
 }
 
+// NGCF_B200_PREFETCH = L2 prefetch distance of the backward kernel in tiles; != 0 also switches the weight-gradient
+// kernel's up-front prefetch on.  Default 0 = off: measured on a B200 (profiles/r02_prefetch_experiment.txt) the step is
+// not faster with it (0.505 ms off, 0.513 ms at distance 2 or 4) - the in-kernel timelines show both kernels' steady
+// state already near the DRAM rate (backward ~15 k cycles per 224-KB tile, weight gradients ~2.4 k cycles per 48-KB
+// stage = 5.8 TB/s), what separates them from the roofline is per-launch fixed cost, not load latency.
+static int dense_prefetch_tiles() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NGCF_B200_PREFETCH");
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
+        if (v > 8) v = 8;
+    }
+    return v;
+}
+
 // d_in = 64 with d_out in {32, 64} is one block; 128-wide sides are decomposed into 64-wide blocks of the same kernels:
 // T = gM·[W1|W2] is linear in gM, so the d_out halves accumulate into gS / gEl in place; the weight-gradient blocks are
 // independent.  A blocked d_out needs the output-row gradients already normalize-backwarded (gh_normalized): the
@@ -1325,6 +1382,10 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
                         mess_bits, mess_p, seed, seed_dev, layer, gS, gEl, gM_scratch, gb1, gb2, n_tiles, row_offset};
             a.d_out_full = d_out; a.out_off = oh * bn; a.d_in_full = d_in; a.in_off = ih * 64;
             a.accumulate = oh > 0; a.first_in = ih == 0;
+            // whole-row prefetches: full-width launches on 16-byte aligned tensors only
+            const bool contiguous = d_out == bn && d_in == 64 && ((uintptr_t)E_out & 15) == 0 && ((uintptr_t)S & 15) == 0 &&
+                                    ((uintptr_t)E & 15) == 0 && ((uintptr_t)gE_next & 15) == 0 && bn % 4 == 0;
+            a.pf = contiguous ? dense_prefetch_tiles() : 0;
             NGCF_CUDA(ngcf_launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, st, a));
             NGCF_LAUNCH_OK("dense_bwd_tc_kernel");
         }
@@ -1343,7 +1404,9 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
     }
     for (int ih = 0; ih < IH; ++ih)
         for (int oh = 0; oh < OH; ++oh) {
-            WgradArgs w{S, E, gM_scratch, n_rows, bn, gW1, gW2, n_chunks, d_in, ih * 64, d_out, oh * bn};
+            WgradArgs w{S, E, gM_scratch, n_rows, bn, gW1, gW2, n_chunks, d_in, ih * 64, d_out, oh * bn, 0};
+            w.pf = (d_out == bn && d_in == 64 && ((uintptr_t)S & 15) == 0 && ((uintptr_t)E & 15) == 0 &&
+                    ((uintptr_t)gM_scratch & 15) == 0 && bn % 4 == 0) ? dense_prefetch_tiles() : 0;
             NGCF_CUDA(ngcf_launch_pdl(wgrad_tc_kernel, dim3(grid2), dim3(TC_THREADS), smem2, ws, w));
             NGCF_LAUNCH_OK("wgrad_tc_kernel");
         }

@@ -2,11 +2,13 @@
 // Replaces torch.mm(L, E) (NGCF.py:130: coalesce -> COO->CSR -> cusparseSpMM on CUDA) and the transposed
 // product of its backward (MmBackward0).  See spmm_core.cuh for the data layout and the mapping.
 //
-// ONE launch covers the hub-chunk tiles (first: they are the longest) and the ordinary-row tiles; the warp that
-// stores the last chunk partial of a hub row completes that row from the partial sums, in chunk order.  (First version: hub pass and row pass
-// as two launches, the row pass reading hub_of_row[row] before every row — tools/spmm_timeline.py showed that
-// dependent load plus the narrow tail batches as 4-8 exposed round trips per 16-row tile, and the two launches
-// each paid their own tail.)  One CTA (8 warps) per tile; the hardware block scheduler balances the tiles.
+// spmm_stream_kernel (widths that are multiples of 4): ONE launch covers the hub-chunk tiles (first: they are the
+// longest) and the ordinary-row tiles, one 64-thread CTA per tile, the hardware block scheduler balances them;
+// hub_finish_kernel behind it sums the chunk partials of every hub row in a fixed order.  spmm_tile_kernel (any width
+// <= 128, e.g. the reference's 65): one row per warp; the warp that stores the last chunk partial of a hub row completes
+// that row (fence + counter).  (First version: hub pass and row pass as two launches, the row pass reading
+// hub_of_row[row] before every row - tools/spmm_timeline.py showed that dependent load plus the narrow tail batches as
+// 4-8 exposed round trips per 16-row tile, and the two launches each paid their own tail.)
 #include <stdlib.h>
 #include <string.h>
 
@@ -260,7 +262,11 @@ __global__ void __launch_bounds__(SP_THREADS, NGCF_SPMM_CTAS) spmm_stream_kernel
     const int nr = ti.r1 - ti.r0;
     // rows of this tile that are hubs (their entries live in the chunk tiles; hub_finish_kernel writes them)
     const uint32_t hubmask = (!chunk_side && a.tile_hubmask) ? a.tile_hubmask[t] : 0u;
-    for (int i = tid; i < nr * G; i += SP_THREADS) reinterpret_cast<float4*>(ysum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // every row slot is cleared, not just the tile's nr: the loop then does not wait for the tile record, whose round
+    // trip overlaps the survivor count's below instead of preceding it (one L2 round trip less in every CTA's serial
+    // chain record -> count -> entries -> gathers)
+#pragma unroll
+    for (int i = tid; i < SP_TILE_ROWS * G; i += SP_THREADS) reinterpret_cast<float4*>(ysum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_wait();
     int cnt;
     if (sd.ccnt) {
@@ -392,6 +398,14 @@ __global__ void __launch_bounds__(HF_THREADS) hub_finish_kernel(SpmmArgs a) {
     const int64_t row = a.hub_rows[h];
     pdl_wait();
     const bool ok = l * 4 < a.d;
+    // the row's addend and batch-row gradient slot are requested before the partial sums, not after them
+    float* const dst = a.Yrows + row * a.ld_yrows + l * 4;
+    float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = -1;
+    if (g == 0 && ok) {
+        if (a.add_mode) ad = ld_f4(dst);
+        if (a.slot) s = a.slot[row];
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) {
         const float* p = a.chunks.Y + l * 4;
@@ -417,12 +431,9 @@ __global__ void __launch_bounds__(HF_THREADS) hub_finish_kernel(SpmmArgs a) {
             const float4 v = ld_f4(gs + q * (G * 4) + l * 4);
             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
-        float* dst = a.Yrows + row * a.ld_yrows + l * 4;
         if (a.add_mode) {                                             // Y holds the addend; this CTA owns the row
-            const float4 ad = ld_f4(dst);
             sum.x += ad.x; sum.y += ad.y; sum.z += ad.z; sum.w += ad.w;
         }
-        const int s = a.slot ? a.slot[row] : -1;
         if (s >= 0) {
             const float4 gsv = ld_f4(a.gsum + (int64_t)s * a.ld_gsum + l * 4);
             sum.x += gsv.x; sum.y += gsv.y; sum.z += gsv.z; sum.w += gsv.w;
