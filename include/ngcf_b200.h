@@ -280,6 +280,10 @@ int ngcf_rowgrad_reset(const int64_t* const* rows_host, const int64_t* offsets_h
  * stream, ordered after the backward kernel by an event; the caller joins it before reading gW / gb and must not reuse
  * gM_scratch before then.  NULL restores single-stream operation. */
 int ngcf_set_wgrad_stream(void* stream_or_null);
+/* 1 if a weight-gradient launch went to that stream since the last call of this function (this thread), else 0: only
+ * then is there anything to join (a layer on the FFMA kernels never forks; under CUDA-graph capture waiting on a
+ * stream that holds no captured work is an error). */
+int ngcf_wgrad_stream_forked(void);
 int ngcf_dense_bwd(const float* gE_next, const int32_t* slot, const float* gsum, int64_t ld_gsum, int col_off,
                    const float* E_out, const float* S, const float* E, int64_t n_rows, int d_in, int d_out,
                    const float* W1, const float* W2, float slope,

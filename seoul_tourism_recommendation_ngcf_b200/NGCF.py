@@ -212,11 +212,12 @@ class _Propagate(torch.autograd.Function):
         col_off = D
         # the weight-gradient kernels need gM only: with the gS exchange queued behind the backward kernel (row-sharded
         # runs) they run beside it on a second stream; each layer then keeps its own gM until the join below
-        overlap = mod._wgrad_overlap == "1" or (mod._wgrad_overlap == "auto" and sh is not None and mod._xchg is not None)
+        overlap = mod._wgrad_overlap != "0"
         if overlap:
             if mod._side_stream is None:
                 mod._side_stream = torch.cuda.Stream(device=dev)
             _lib.check(lib.ngcf_set_wgrad_stream(mod._side_stream.cuda_stream), "set_wgrad_stream")
+            lib.ngcf_wgrad_stream_forked()                            # clear the flag
             gM_keep = []
         else:
             gM_scratch = torch.empty(nloc, max(dims[1:]), dtype=torch.float32, device=dev)
@@ -265,7 +266,8 @@ class _Propagate(torch.autograd.Function):
                 mod._trace.append(dict(k=k, gS=gS.clone(), gEl=gEl.clone(), gE=gE_next.clone()))
         if overlap:                                                   # join: the weight gradients are complete
             _lib.check(lib.ngcf_set_wgrad_stream(None), "set_wgrad_stream")
-            torch.cuda.current_stream().wait_stream(mod._side_stream)
+            if lib.ngcf_wgrad_stream_forked():                        # (FFMA layers never fork: nothing to wait for)
+                torch.cuda.current_stream().wait_stream(mod._side_stream)
         _lib.check(lib.ngcf_rowgrad_reset(rows_h, offs_h, batch_h, n_sets, slot.data_ptr(), _stream()),
                    "rowgrad_reset")
         if sh is not None:
@@ -358,7 +360,9 @@ class NGCF(nn.Module):
         self._group = None
         self._xchg = None        # sharded.PeerExchange (peer-memory exchange) when available
         self._sparse_last = os.environ.get("NGCF_B200_SPARSE_LAST", "1") == "1"
-        self._wgrad_overlap = os.environ.get("NGCF_B200_WGRAD_OVERLAP", "auto")    # "0" | "1" | "auto" (row-sharded runs)
+        # weight-gradient kernels on a second stream beside the transposed product (and the gS exchange of a row-sharded
+        # run): 0.508 -> 0.494 ms per step on one B200, 0.611 -> 0.594 ms at 2 ranks; "0" switches it off
+        self._wgrad_overlap = os.environ.get("NGCF_B200_WGRAD_OVERLAP", "1")
         self._side_stream = None
         self._side_stream2 = None
         # L^T's survivor lists on a second stream beside the forward: measured slower on one B200 (0.518 vs 0.510 ms per

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ngcf_dense_bwd": [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32,
                        _u64, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ngcf_set_wgrad_stream": [_vp],
+    "ngcf_wgrad_stream_forked": [],
     "ngcf_rowgrad_normalize": [C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.c_int, C.POINTER(_vp),
                                C.POINTER(C.c_int), C.c_int, _vp, _vp, C.c_int, _vp],
     "ngcf_adam_step": [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.c_int,

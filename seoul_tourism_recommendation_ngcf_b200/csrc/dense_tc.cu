@@ -1324,9 +1324,17 @@ int ngcf_dense_fwd_tc(const float* S, const float* E, int64_t n_rows, int d_in, 
 // gM only, so a caller with other work queued behind the backward kernel (the row-sharded step: the gS exchange and the
 // transposed product) can let them run beside it.  Thread-local; the caller joins the stream.
 static thread_local cudaStream_t g_wgrad_stream = nullptr;
+static thread_local int g_wgrad_forked = 0;      // a launch went to the second stream since the last query
 extern "C" int ngcf_set_wgrad_stream(void* stream_or_null) {
     g_wgrad_stream = as_stream(stream_or_null);
     return NGCF_OK;
+}
+// 1 if any weight-gradient launch since the last call went to the second stream (the caller then has to join it; a
+// layer on the FFMA kernels never forks, and waiting on a stream without captured work breaks a graph capture)
+extern "C" int ngcf_wgrad_stream_forked(void) {
+    const int v = g_wgrad_forked;
+    g_wgrad_forked = 0;
+    return v;
 }
 
 // NGCF_B200_PREFETCH = L2 prefetch distance of the backward kernel in tiles; != 0 also switches the weight-gradient
@@ -1401,6 +1409,7 @@ int ngcf_dense_bwd_tc(const float* gE_next, const int32_t* slot, const float* gs
         NGCF_CUDA(cudaEventRecord(ev[dev & 63], st));
         NGCF_CUDA(cudaStreamWaitEvent(g_wgrad_stream, ev[dev & 63], 0));
         ws = g_wgrad_stream;
+        g_wgrad_forked = 1;
     }
     for (int ih = 0; ih < IH; ++ih)
         for (int oh = 0; oh < OH; ++oh) {
