@@ -30,7 +30,15 @@ def _stream() -> int:
 class _Ctx:
     """Per-forward state shared by the autograd node and the module (layer activations, plan, masks)."""
     __slots__ = ("plan", "E", "S", "dims", "vals_f", "vals_b", "mess_mult", "mess_p", "seed", "seed_dev", "masked", "drop_p", "bits_f", "bits_b", "comp_f", "comp_b", "mess_bits",
-                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode", "last_partial", "comp_b_stream", "needs_grad")
+                 "rows", "offsets", "W1", "W2", "fresh_key", "node_mode", "last_partial", "comp_b_stream", "needs_grad", "comp_b_late",
+                 "fm_stream")
+
+
+def _join_feature_mix(st):
+    """The feature mix of this forward ran on a second stream (NGCF.forward): whatever reads the table next waits for it."""
+    if st.fm_stream is not None:
+        torch.cuda.current_stream().wait_stream(st.fm_stream)
+        st.fm_stream = None
 
 
 class _Propagate(torch.autograd.Function):
@@ -53,6 +61,7 @@ class _Propagate(torch.autograd.Function):
         r0, nloc, nv = (sh.r0, sh.rows, sh.valid) if sh is not None else (0, N, N)
         X0 = mod._packed_table()                                       # [N(_pad), d0] = cat(user, item), NGCF.py:120
         if mod._snapshot:                                              # the reference's cat() is a copy: opt-in here
+            _join_feature_mix(st)
             X0 = X0.clone()
         st.E, st.S, st.W1, st.W2 = [X0], [], list(W1), list(W2)
         side = st.plan.fwd
@@ -60,6 +69,7 @@ class _Propagate(torch.autograd.Function):
         st.node_mode = mod._node_mode
         st.last_partial = None
         st.comp_b_stream = None
+        st.comp_b_late = False
         needs_grad = st.needs_grad
         if st.drop_p > 0:
             # this step's node-dropout decisions for all K layers, drawn once instead of a hash evaluation per entry in
@@ -71,9 +81,15 @@ class _Propagate(torch.autograd.Function):
             # (every width, the last one too: the batch-row gradient rows of the final backward product are D_total wide)
             node_mode = mod._node_mode if all(d % 4 == 0 for d in st.dims) or mod._node_mode == "inkernel" else "bits"
             st.node_mode = node_mode
-            if node_mode == "compact" and shared and needs_grad and mod._compact_overlap:
-                # the forward needs L's survivors now; L^T's are first read by the backward, so that half of the pass
-                # runs on a second stream beside the forward's first kernels (joined before the first backward product)
+            if node_mode == "compact" and shared and needs_grad and mod._compact_overlap == "late" and sh is None:
+                # the forward needs L's survivors now; L^T's are first read by the backward's first product: that half of
+                # the pass is queued on a second stream BEHIND the last layer (below), where the small launches between
+                # the two passes (row gather, BPR, row-gradient scatter: a few CTAs each) leave the GPU nearly idle
+                st.comp_f, _ = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=False)
+                st.comp_b_late = True
+            elif node_mode == "compact" and shared and needs_grad and mod._compact_overlap == "1":
+                # the same split with L^T's half forked right here, beside the forward's first kernels (measured slower
+                # than one combined pass: it takes SM time from the critical path)
                 st.comp_f, _ = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=True, as_Lt=False)
                 main = torch.cuda.current_stream()
                 if mod._side_stream2 is None:
@@ -110,6 +126,7 @@ class _Propagate(torch.autograd.Function):
         _lib.check(lib.ngcf_pack_weights_all(_lib.ptr_array(W1), _lib.ptr_array(b1), _lib.ptr_array(W2), _lib.ptr_array(b2),
                                              _lib.int_array(st.dims[:K]), _lib.int_array(st.dims[1:]), K,
                                              _lib.ptr_array(wcats), _lib.ptr_array(biases), _stream()), "pack_weights_all")
+        _join_feature_mix(st)                                          # the first product reads the mixed user rows
         for k in range(K):
             d_in, d_out = st.dims[k], st.dims[k + 1]
             vals = st.vals_f[k] if st.vals_f is not None else None
@@ -146,6 +163,17 @@ class _Propagate(torch.autograd.Function):
                 all_gather_rows(Xn, En, mod._group)
             st.S.append(S)
             st.E.append(Xn)
+        if st.comp_b_late:
+            main = torch.cuda.current_stream()
+            if mod._side_stream2 is None:
+                mod._side_stream2 = torch.cuda.Stream(device=dev)
+            mod._side_stream2.wait_stream(main)
+            with torch.cuda.stream(mod._side_stream2):
+                _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
+            for e_, c_ in st.comp_b:                                    # allocated under the side stream, used on main
+                e_.record_stream(main)
+                c_.record_stream(main)
+            st.comp_b_stream = mod._side_stream2
         D = sum(st.dims)
         layers, dims = _lib.ptr_array(st.E), _lib.int_array(st.dims)
         outs = [torch.empty(st.rows[j].numel(), D, dtype=torch.float32, device=dev) for j in range(n_sets)]
@@ -201,9 +229,6 @@ class _Propagate(torch.autograd.Function):
         # explicit (COO-order) masks need the separately sorted L^T; in-kernel device-RNG dropout is keyed on the
         # entry's coordinates, so a symmetric L keeps sharing its forward arrays (transposed=1 swaps the key)
         side = st.plan.side(True, st.vals_b is not None)
-        if st.comp_b_stream is not None:                              # L^T's survivor lists were compacted beside the forward
-            torch.cuda.current_stream().wait_stream(st.comp_b_stream)
-            st.comp_b_stream = None
         if st.drop_p > 0 and st.node_mode == "compact" and st.comp_b is None:
             _, st.comp_b = node_dropout_compact(side, st.drop_p, st.seed, st.seed_dev, K, r0, as_L=False, as_Lt=True)
         if st.drop_p > 0 and st.node_mode == "bits" and st.bits_b is None:
@@ -258,6 +283,9 @@ class _Propagate(torch.autograd.Function):
                 gS_all = gS
             vals = st.vals_b[k] if st.vals_b is not None else None
             last = (k == 0)
+            if st.comp_b_stream is not None:                          # L^T's survivor lists were compacted on a second stream
+                torch.cuda.current_stream().wait_stream(st.comp_b_stream)
+                st.comp_b_stream = None
             gE_next = spmm(side, vals, gS_all, d_in, addend=gEl, slot=slot_loc if last else None,
                            gsum=gsum if last else None, drop_p=st.drop_p, seed=st.seed, seed_dev=st.seed_dev, layer=k,
                            transposed=True, row_offset=r0, keep_bits=st.bits_b,
@@ -367,7 +395,15 @@ class NGCF(nn.Module):
         self._side_stream2 = None
         # L^T's survivor lists on a second stream beside the forward: measured slower on one B200 (0.518 vs 0.510 ms per
         # step: the compaction is issue-bound and takes SM time from the forward's first kernels), so opt-in only
-        self._compact_overlap = os.environ.get("NGCF_B200_COMPACT_OVERLAP", "0") == "1"
+        # L^T's half of the node-dropout compaction on a second stream: "1" = forked at the start of the forward, "late" =
+        # behind the last layer (beside the small launches between the passes).  Both measured SLOWER than the one combined
+        # pass on one B200 (0.518 / 0.509-0.513 vs 0.502-0.510 ms per step: two more launches and the entries read twice
+        # cost more than the overlap hides), so the default is "0"; profiles/r02_overlap_experiments.txt
+        self._compact_overlap = os.environ.get("NGCF_B200_COMPACT_OVERLAP", "0")          # "0" | "1" | "late"
+        # the feature mix (two small launches that rewrite <= B user rows) on a second stream beside the node-dropout
+        # compaction, which does not touch the table; joined before the first product (0.502 -> 0.499 ms per step)
+        self._featmix_overlap = os.environ.get("NGCF_B200_FEATMIX_OVERLAP", "1") == "1"
+        self._side_stream3 = None
         self._trace = None       # debugging aid: set to a list to record the backward's per-layer tensors
         self._inject = None      # tests only: dict(edge_keep=[K x uint8[nnz]], mess_mult=[K x [N,d]])
 
@@ -511,13 +547,27 @@ class NGCF(nn.Module):
         if self._winner is None or self._winner.device != dev or self._winner.numel() != self.n_user:
             self._winner = torch.full((self.n_user,), -1, dtype=torch.int32, device=dev)
         tabs = [self.age_emb.weight, self.sex_emb.weight, self.month_emb.weight, self.day_emb.weight, self.dow_emb.weight]
-        _lib.check(lib.ngcf_feature_mix(table.data_ptr(), self.n_user, self.emb_size, _lib.ptr_array(tabs),
-                                        _lib.int_array(self.feat_widths), _lib.ptr_array(feats_idx), u_id.data_ptr(),
-                                        u_id.numel(), float(self.emb_ratio), self._winner.data_ptr(), _stream()),
-                   "feature_mix")                                            # NGCF.py:103-115
+        def mix():
+            _lib.check(lib.ngcf_feature_mix(table.data_ptr(), self.n_user, self.emb_size, _lib.ptr_array(tabs),
+                                            _lib.int_array(self.feat_widths), _lib.ptr_array(feats_idx), u_id.data_ptr(),
+                                            u_id.numel(), float(self.emb_ratio), self._winner.data_ptr(), _stream()),
+                       "feature_mix")                                        # NGCF.py:103-115
+
+        fm_stream = None
+        if self._featmix_overlap and bool(node_flag) and (self.node_dropout or 0) > 0 and self.rng == "device":
+            main = torch.cuda.current_stream()
+            if self._side_stream3 is None:
+                self._side_stream3 = torch.cuda.Stream(device=dev)
+            self._side_stream3.wait_stream(main)
+            with torch.cuda.stream(self._side_stream3):
+                mix()
+            fm_stream = self._side_stream3
+        else:
+            mix()
 
         self._mix_count += 1
         st = _Ctx()
+        st.fm_stream = fm_stream
         st.fresh_key = self._fresh_key()
         st.plan = plan = self._plan(year_idx, dev)
         if self._shard is not None and "edge_keep" in (self._inject or {}):
