@@ -34,6 +34,10 @@ class _Ctx:
                  "fm_stream")
 
 
+def _capturing() -> bool:
+    return torch.cuda.is_current_stream_capturing()
+
+
 def _join_feature_mix(st):
     """The feature mix of this forward ran on a second stream (NGCF.forward): whatever reads the table next waits for it."""
     if st.fm_stream is not None:
@@ -237,7 +241,10 @@ class _Propagate(torch.autograd.Function):
         col_off = D
         # the weight-gradient kernels need gM only: with the gS exchange queued behind the backward kernel (row-sharded
         # runs) they run beside it on a second stream; each layer then keeps its own gM until the join below
-        overlap = mod._wgrad_overlap != "0"
+        # (second streams cost the HOST two event calls per fork and join: they pay under CUDA-graph capture, where the
+        # step is replayed without host work, and in row-sharded runs; the eager single-GPU step is host-bound already)
+        overlap = mod._wgrad_overlap != "0" and (mod._wgrad_overlap == "force" or _capturing() or
+                                                  (sh is not None and mod._xchg is not None))
         if overlap:
             if mod._side_stream is None:
                 mod._side_stream = torch.cuda.Stream(device=dev)
@@ -389,7 +396,8 @@ class NGCF(nn.Module):
         self._xchg = None        # sharded.PeerExchange (peer-memory exchange) when available
         self._sparse_last = os.environ.get("NGCF_B200_SPARSE_LAST", "1") == "1"
         # weight-gradient kernels on a second stream beside the transposed product (and the gS exchange of a row-sharded
-        # run): 0.508 -> 0.494 ms per step on one B200, 0.611 -> 0.594 ms at 2 ranks; "0" switches it off
+        # run): 0.508 -> 0.494 ms per step on one B200 (GraphedStep), 0.611 -> 0.594 ms at 2 ranks; "0" switches it off,
+        # "force" also uses it in the eager single-GPU step (slower there: the eager step is bound by host issue)
         self._wgrad_overlap = os.environ.get("NGCF_B200_WGRAD_OVERLAP", "1")
         self._side_stream = None
         self._side_stream2 = None
@@ -554,7 +562,7 @@ class NGCF(nn.Module):
                        "feature_mix")                                        # NGCF.py:103-115
 
         fm_stream = None
-        if self._featmix_overlap and bool(node_flag) and (self.node_dropout or 0) > 0 and self.rng == "device":
+        if self._featmix_overlap and _capturing() and bool(node_flag) and (self.node_dropout or 0) > 0 and self.rng == "device":
             main = torch.cuda.current_stream()
             if self._side_stream3 is None:
                 self._side_stream3 = torch.cuda.Stream(device=dev)
