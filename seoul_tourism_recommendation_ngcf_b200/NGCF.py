@@ -562,7 +562,8 @@ class NGCF(nn.Module):
                        "feature_mix")                                        # NGCF.py:103-115
 
         fm_stream = None
-        if self._featmix_overlap and _capturing() and bool(node_flag) and (self.node_dropout or 0) > 0 and self.rng == "device":
+        if self._featmix_overlap and self._shard is None and _capturing() and bool(node_flag) and \
+                (self.node_dropout or 0) > 0 and self.rng == "device":
             main = torch.cuda.current_stream()
             if self._side_stream3 is None:
                 self._side_stream3 = torch.cuda.Stream(device=dev)
