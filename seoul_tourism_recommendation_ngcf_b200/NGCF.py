@@ -541,6 +541,9 @@ class NGCF(nn.Module):
             raise RuntimeError("NGCF (B200) runs on a CUDA device only; there is no CPU fallback. "
                                "Move the module with .to('cuda').")
         K, N = self.n_layer, self.n_user + self.n_item
+        if (self._side_stream is None or self._side_stream.device != dev) and not _capturing():
+            # second streams of the capture-time overlaps, handed out of torch's pool BEFORE any capture begins
+            self._side_stream, self._side_stream2, self._side_stream3 = (torch.cuda.Stream(device=dev) for _ in range(3))
 
         def ix(t):
             return t.to(device=dev, dtype=torch.int64).contiguous()
